@@ -1,0 +1,159 @@
+/* k2b200.h -- C ABI of libk2b200.so, the B200 (sm_100a) kernel library behind the Kandinsky-2
+ * denoising hot path.
+ *
+ * The reference (ai-forever/Kandinsky-2) has no FFI: its "operator API" for this path is the set of
+ * PyTorch library calls issued by kandinsky2/model/unet.py, kandinsky2/model/nn.py,
+ * kandinsky2/model/gaussian_diffusion.py and kandinsky2/vqgan/movq_modules.py.  Each entry point
+ * below replaces one such call-site family (cited per function) and is what the Python boundary
+ * modules in kandinsky-2_b200/kandinsky2/ bind through ctypes.
+ *
+ * Conventions
+ *   - every function returns 0 on success and <0 on error; k2_last_error() gives the thread-local
+ *     message; no C++ exception crosses the boundary;
+ *   - all pointers are DEVICE pointers unless a parameter is documented as host memory; the library
+ *     never allocates user-visible memory and never synchronises the device;
+ *   - every launch is enqueued on the caller's stream (pass torch.cuda.current_stream().cuda_stream);
+ *   - activations are NHWC fp16 ("rows" = pixels, row stride `ld*` in ELEMENTS so that a tensor may
+ *     be a channel slice of a wider buffer); weights are pre-packed by the host (layout per function);
+ *   - there is no CPU fallback: without an sm_100 device every call fails.
+ */
+#ifndef K2B200_H_
+#define K2B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* k2_stream_t; /* cudaStream_t */
+
+const char* k2_last_error(void);
+int k2_version(void);
+/* Number of kernels launched by this library in this process since the last reset (bench evidence). */
+long long k2_launch_count(void);
+void k2_reset_launch_count(void);
+/* Tuning knobs: key 0 = force conv/GEMM N tile (0 = auto). */
+int k2_set_tuning(int key, int value);
+
+/* ---------------------------------------------------------------------------------------------
+ * Convolution / GEMM on tcgen05 tensor cores.
+ * Replaces nn.Conv2d 3x3 (unet.py:152,180,426,562; movq_modules.py:139-148), nn.Conv2d 1x1
+ * (unet.py:191; movq_modules.py:150-157,188-199) and nn.Conv1d k=1 (unet.py:251,257,258).
+ *
+ *   out[m, n] = bias[n] + residual[m, n] + sum_s sum_tap sum_c A_s[shift_tap(m), c] * Wp[n, k(s,tap,c)]
+ *
+ * m runs over the NB*H*W output pixels (NHWC order).  Up to 3 activation sources accumulate into the
+ * same output; source s has `taps` = 9 (3x3, zero padding 1) or 1 (1x1).  Packed weights Wp are fp16
+ * [w_rows >= Cout][Ktot], K contiguous, k ordered source-major, then tap (ky*3+kx), then channel, each
+ * source's channel count padded to a multiple of 64 (zero weights for the padding).
+ * out_mode 0: fp16 rows [M, ldo]; out_mode 1: fp32 NCHW [NB, Cout, H, W] (output heads).
+ * A plain GEMM [M,K]x[K,N] is the call with NB=1, H=1, W=M, one source with taps=1.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* ptr; /* fp16, NHWC; may point at a channel offset inside a wider buffer */
+  int C;           /* channels of this source (multiple of 8) */
+  int ld;          /* row stride in elements */
+  int taps;        /* 9 or 1 */
+} K2ConvSrc;
+
+int k2_conv_gemm(const K2ConvSrc* srcs, int nsrc, int NB, int H, int W, const void* w_packed, int w_rows,
+                 int Ktot, int Cout, const float* bias, const void* residual, int ldr, void* out, int ldo,
+                 int out_mode, k2_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * GroupNorm (32 groups in the UNet) statistics + fused apply.
+ * Replaces GroupNorm32.forward (nn.py:31-37), the FiLM  norm(h)*(1+scale)+shift  and SiLU of
+ * ResBlock.forward (unet.py:209-216), Upsample/Downsample on h and x (unet.py:67-77,105-107), the
+ * torch.cat of the up path (text2im_model2_1.py:99) and MoVQ SpatialNorm (movq_modules.py:61-68).
+ *
+ * k2_gn_stats: per (image, group) mean and rstd of the channel-concatenation [src0 | src1]
+ *   (src1 may be NULL); stats is fp32 [NB, groups, 2]; scratch is fp32 workspace of
+ *   k2_gn_scratch_floats(NB, HW, groups) floats plus one int counter array (see .cu); deterministic.
+ * k2_gn_apply: y = act( ((x-mean)*rstd*gamma+beta) * (1+scale[n,c]) + shift[n,c] ), written as fp16
+ *   rows of the concatenated tensor, optionally resampled:
+ *     resample 0: same size; 1: 2x2 average pool of y (and of raw x into xres); 2: nearest 2x upsample.
+ *   film is fp32 rows (scale[0..C) | shift[C..2C)) with row stride film_ld, or NULL.  act: 0 none, 1 SiLU.
+ *   spatial (MoVQ): if zq != NULL, y = GN(x) * (Wy.zq + by) + (Wb.zq + bb) with zq fp32 NHWC
+ *   [NB, zh, zw, 4] nearest-resized to (H, W); sn_w is fp32 [C, 10] = (Wy[4], by, Wb[4], bb).
+ * ------------------------------------------------------------------------------------------- */
+long long k2_gn_scratch_floats(int NB, int HW, int groups);
+int k2_gn_stats(const void* src0, int C0, int ld0, const void* src1, int C1, int ld1, int NB, int HW,
+                int groups, float eps, float* stats, float* scratch, k2_stream_t stream);
+int k2_gn_apply(const void* src0, int C0, int ld0, const void* src1, int C1, int ld1, int NB, int H, int W,
+                int groups, const float* stats, const float* gamma, const float* beta, const float* film,
+                int film_ld, int act, int resample, void* y, int ldy, void* xres, int ldx, const float* zq, int zh,
+                int zw, const float* sn_w, k2_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Attention, head dim 64, online softmax, on tcgen05 (QK^T and PV) with encoder K/V prepended.
+ * Replaces QKVAttention.forward (unet.py:286-340) incl. the optional flash-attn path (:303-332).
+ *   qkv   fp16 [B, T, ldq] rows; head h owns channels [h*hs, (h+1)*hs) with q at +q_off, k at +k_off,
+ *         v at +v_off (reference layout: hs=192, 0/64/128 -- unet.py:296).
+ *   enc   fp16 [B, Tc, lde] rows or NULL (Tc=0); head h: k at h*ehs+ek_off, v at h*ehs+ev_off.
+ *   out   fp16 [B, T, ldo], channel h*64+d.
+ *   scale multiplies q.k (reference: 1/sqrt(64), applied as d^-1/4 on each operand, unet.py:334-337).
+ * ------------------------------------------------------------------------------------------- */
+int k2_attention_d64(const void* qkv, int ldq, int hs, int q_off, int k_off, int v_off, const void* enc,
+                     int lde, int ehs, int ek_off, int ev_off, int B, int heads, int T, int Tc, float scale,
+                     void* out, int ldo, k2_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Small dense layers (fp32 math): nn.Linear (+ optional SiLU on the input and/or the output),
+ * nn.LayerNorm, and the sinusoidal timestep embedding.
+ * Replaces time_embed (unet.py:414-419), emb_layers (unet.py:166-172), the conditioning head
+ * (text2im_model2_1.py:57-80) and timestep_embedding (nn.py:101-121).
+ *   y[m, n] = (silu_out ? silu : id)( b[n] + sum_k (silu_in ? silu(x[m,k]) : x[m,k]) * W[n,k] ) (+ add[m,n])
+ * x fp32 [M, K] (ldx), W fp16 or fp32 [N, K] (w_is_half), y fp32 [M, N] (ldy).
+ * ------------------------------------------------------------------------------------------- */
+int k2_linear(const float* x, int ldx, const void* W, int w_is_half, const float* b, const float* add,
+              int ldadd, float* y, int ldy, int M, int N, int K, int silu_in, int silu_out,
+              k2_stream_t stream);
+int k2_layernorm(const float* x, const float* gamma, const float* beta, float* y, int M, int N, float eps,
+                 k2_stream_t stream);
+int k2_timestep_embedding(const float* t, float* out, int B, int dim, float max_period, k2_stream_t stream);
+/* fp32 rows -> fp16 rows (context tokens), and generic strided copy helpers */
+int k2_f32_to_f16(const float* x, void* y, long long n, k2_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stem im2col: fp32 NCHW latent (+ optional inpaint image*mask and mask, text2im_model2_1.py:146-155)
+ * -> fp16 rows [NB*H*W, Kpad] holding the 3x3xCin patch (k = tap*Cin + c), zero padded, so that
+ * input_blocks.0 (unet.py:426) runs through k2_conv_gemm as a GEMM.
+ * ------------------------------------------------------------------------------------------- */
+int k2_stem_im2col(const float* x, int Cx, const float* x2, int C2, const float* x3, int C3, int mul23,
+                   int NB, int H, int W, void* out, int Kpad, k2_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Sampler step (classifier-free guidance + DDPM learned-range posterior), fused.
+ * Replaces model_fn (kandinsky2_1_model.py:222-233), p_mean_variance / process_xstart / p_sample
+ * (gaussian_diffusion.py:223-322,352-382) and denoised_fun (kandinsky2_1_model.py:237-243).
+ *   model_out fp32 NCHW [2B, 8, H, W]; x fp32 [B, 4, H, W] (in place -> x_{t-1}); noise fp32 [B,4,H,W].
+ *   coef (device, fp32[8]): sqrt_recip_ac, sqrt_recipm1_ac, post_coef1, post_coef2, min_log, max_log,
+ *   nonzero, unused.  cond_first: 1 = rows [0,B) conditional (2.1), 0 = unconditional first (2.2).
+ *   threshold_mode 0: x0 = clamp(x0, -clip, clip); 1: additionally the reference's dynamic threshold
+ *   s = max(percentile_99.5(|x0[sample 0]|), 1); x0 = clip(x0, -s, s)/s   (gaussian_diffusion.py:284-294).
+ *   Inpainting: x0 = x0*(1-mask) + init*mask after the clamp (mask fp32 [B,1,H,W], init fp32 [B,4,H,W]).
+ *   work: fp32 scratch of at least B*4*H*W + 4096 floats.
+ * ------------------------------------------------------------------------------------------- */
+int k2_sampler_step(const float* model_out, float* x, const float* noise, const float* coef, int B, int H,
+                    int W, float guidance, int cond_first, float clip, int threshold_mode,
+                    const float* inpaint_init, const float* inpaint_mask, float* work, k2_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * MoVQ helpers: nearest-codebook search (quntize.py:89-98; fp32, ties -> lowest index, int64 out),
+ * fp32 NCHW -> NHWC transposes for the 4-channel latent, final image quantisation
+ * (utils.py:57-70: ((x+1)*127.5).round().clamp(0,255) -> uint8 NHWC).
+ * ------------------------------------------------------------------------------------------- */
+int k2_vq_argmin(const float* z, const float* codebook, long long* idx, int n, int n_embed, int dim,
+                 k2_stream_t stream);
+/* y[n,o,:] = b[o] + sum_i w[o,i] x[n,i,:] on fp32 NCHW (MoVQ post_quant_conv 4->4, autoencoder.py:183) */
+int k2_pointwise_nchw_f32(const float* x, const float* w, const float* b, float* y, int NB, int Ci, int Co, int HW,
+                          k2_stream_t stream);
+int k2_nchw_to_nhwc_f32(const float* x, float* y, int NB, int C, int H, int W, k2_stream_t stream);
+int k2_images_to_u8(const float* x_nchw, uint8_t* out_nhwc, int NB, int C, int H, int W, int crop_h,
+                    int crop_w, k2_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* K2B200_H_ */

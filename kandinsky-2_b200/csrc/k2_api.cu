@@ -1,0 +1,208 @@
+// k2_api.cu -- C-ABI plumbing: error state, launch counter, TMA descriptor encoding, and the
+// k2_conv_gemm entry point (geometry selection + tensor maps) declared in include/k2b200.h.
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+
+#include "../../include/k2b200.h"
+#include "k2_internal.h"
+
+namespace k2 {
+
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+static int g_force_bn = 0;
+
+void set_error(const std::string& msg) { g_err = msg; }
+int fail(const std::string& msg) {
+  g_err = msg;
+  return -1;
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int encode_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail("cuTensorMapEncodeTiled unavailable (no CUDA driver / not an sm_100 box)");
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5];
+  cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+  }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
+                  gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof buf,
+             "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu %llu box %u %u %u %u base %p",
+             static_cast<int>(r), rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+             (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0],
+             rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0, base);
+    return fail(buf);
+  }
+  return 0;
+}
+
+// Pick the (TN, TH, TW) output box of one M tile: <= 128 pixels, minimising the tile count.
+static void choose_tile(int NB, int H, int W, int& TN, int& TH, int& TW) {
+  if (H * W <= 128) {
+    TW = W;
+    TH = H;
+    TN = 128 / (H * W);
+    if (TN > NB) TN = NB;
+    if (TN < 1) TN = 1;
+    return;
+  }
+  TN = 1;
+  long long best_tiles = -1;
+  int bw = 1, bh = 1;
+  int wmax = W < 128 ? W : 128;
+  for (int tw = 1; tw <= wmax; ++tw) {
+    int thmax = 128 / tw;
+    if (thmax > H) thmax = H;
+    if (thmax < 1) continue;
+    long long tiles_h = (H + thmax - 1) / thmax;
+    int th = static_cast<int>((H + tiles_h - 1) / tiles_h);  // balanced
+    long long tiles = tiles_h * ((W + tw - 1) / tw);
+    bool better = best_tiles < 0 || tiles < best_tiles;
+    if (!better && tiles == best_tiles) {
+      // tie: prefer the squarer box (halo reuse), then the wider one
+      int d_new = tw > th ? tw - th : th - tw;
+      int d_old = bw > bh ? bw - bh : bh - bw;
+      better = (d_new < d_old) || (d_new == d_old && tw > bw);
+    }
+    if (better) {
+      best_tiles = tiles;
+      bw = tw;
+      bh = th;
+    }
+  }
+  TW = bw;
+  TH = bh;
+}
+
+}  // namespace k2
+
+using namespace k2;
+
+extern "C" {
+
+const char* k2_last_error(void) { return g_err.c_str(); }
+int k2_version(void) { return 100; }
+long long k2_launch_count(void) { return g_launches.load(); }
+void k2_reset_launch_count(void) { g_launches.store(0); }
+int k2_set_tuning(int key, int value) {
+  if (key == 0) {
+    g_force_bn = value;
+    return 0;
+  }
+  return fail("k2_set_tuning: unknown key");
+}
+
+int k2_conv_gemm(const K2ConvSrc* srcs, int nsrc, int NB, int H, int W, const void* w_packed, int w_rows,
+                 int Ktot, int Cout, const float* bias, const void* residual, int ldr, void* out, int ldo,
+                 int out_mode, k2_stream_t stream) {
+  K2_REQUIRE(nsrc >= 1 && nsrc <= 3, "conv_gemm: 1..3 sources");
+  K2_REQUIRE(NB > 0 && H > 0 && W > 0 && Cout > 0, "conv_gemm: bad geometry");
+  K2_REQUIRE(w_rows >= Cout, "conv_gemm: w_rows < Cout");
+  K2_REQUIRE(Ktot % 64 == 0, "conv_gemm: Ktot must be a multiple of 64");
+  ConvGemmParams p;
+  memset(&p, 0, sizeof p);
+  p.NB = NB;
+  p.H = H;
+  p.W = W;
+  choose_tile(NB, H, W, p.TN, p.TH, p.TW);
+  p.tiles_w = (W + p.TW - 1) / p.TW;
+  p.tiles_h = (H + p.TH - 1) / p.TH;
+  p.tiles_n = (NB + p.TN - 1) / p.TN;
+  p.m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  p.a_box_bytes = static_cast<uint32_t>(p.TN * p.TH * p.TW * 128);
+
+  int kchunks = 0;
+  for (int s = 0; s < nsrc; ++s) {
+    const K2ConvSrc& src = srcs[s];
+    K2_REQUIRE(src.taps == 9 || src.taps == 1, "conv_gemm: taps must be 9 or 1");
+    K2_REQUIRE(src.C > 0 && src.C % 8 == 0 && src.ld % 8 == 0 && src.ld >= src.C, "conv_gemm: bad source C/ld");
+    K2_REQUIRE((reinterpret_cast<uintptr_t>(src.ptr) & 15) == 0, "conv_gemm: source not 16B aligned");
+    p.seg_taps[s] = src.taps;
+    p.seg_kchunks[s] = (src.C + 63) / 64;
+    kchunks += src.taps * p.seg_kchunks[s];
+    uint64_t dims[4] = {static_cast<uint64_t>(src.C), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                        static_cast<uint64_t>(NB)};
+    uint64_t str[3] = {static_cast<uint64_t>(src.ld) * 2, static_cast<uint64_t>(src.ld) * 2 * W,
+                       static_cast<uint64_t>(src.ld) * 2 * W * H};
+    uint32_t box[4] = {64, static_cast<uint32_t>(p.TW), static_cast<uint32_t>(p.TH), static_cast<uint32_t>(p.TN)};
+    if (encode_tmap_f16(&p.tmA[s], src.ptr, 4, dims, str, box)) return -1;
+  }
+  K2_REQUIRE(kchunks * 64 == Ktot, "conv_gemm: Ktot does not match the sources (taps * ceil(C/64)*64 summed)");
+  p.num_k_chunks = kchunks;
+
+  int BN = g_force_bn;
+  if (BN == 0) {
+    if (Cout <= 16) BN = 16;
+    else if (Cout <= 64) BN = 64;
+    else if (Cout % 256 == 0) BN = 256;
+    else if (Cout % 192 == 0) BN = 192;
+    else BN = 128;
+  }
+  p.n_tiles = (Cout + BN - 1) / BN;
+  p.Cout = Cout;
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(Ktot), static_cast<uint64_t>(w_rows)};
+    uint64_t str[1] = {static_cast<uint64_t>(Ktot) * 2};
+    uint32_t box[2] = {64, static_cast<uint32_t>(BN)};
+    if (encode_tmap_f16(&p.tmB, w_packed, 2, dims, str, box)) return -1;
+  }
+  p.bias = bias;
+  p.residual = reinterpret_cast<const __half*>(residual);
+  p.ldr = ldr;
+  p.out = out;
+  p.ldo = ldo;
+  p.out_mode = out_mode;
+  if (out_mode == 0) {
+    K2_REQUIRE(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "conv_gemm: out alignment");
+    if (residual)
+      K2_REQUIRE(ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0, "conv_gemm: residual alignment");
+  }
+  int rc = launch_conv_gemm(p, BN, static_cast<cudaStream_t>(stream));
+  if (rc == 0) g_launches.fetch_add(1, std::memory_order_relaxed);
+  return rc;
+}
+
+}  // extern "C"

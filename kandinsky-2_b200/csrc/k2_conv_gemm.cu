@@ -1,0 +1,302 @@
+// k2_conv_gemm.cu -- im2col-free 3x3 / 1x1 convolution and plain GEMM on tcgen05 tensor cores.
+//
+// Replaces the cuDNN / cuBLAS call sites of the reference hot path:
+//   nn.Conv2d 3x3   kandinsky2/model/unet.py:152,180,426,562 ; vqgan/movq_modules.py:139-148,268-270
+//   nn.Conv2d 1x1   kandinsky2/model/unet.py:191 (skip_connection) ; movq_modules.py:150-157,188-199
+//   nn.Conv1d k=1   kandinsky2/model/unet.py:251,257,258 (qkv / encoder_kv / proj_out)
+//
+// Formulation: D[M = pixels, N = Cout] = sum over (segment, tap, 64-channel chunk) A_tap[M, 64] * W[N, 64]^T.
+//   * Activations are NHWC fp16. An M tile is a (TN x TH x TW) box of output pixels (<= 128 rows).
+//     For tap (dy, dx) the A operand is the SAME box shifted by (dy, dx), fetched with ONE 4-D TMA
+//     whose out-of-bounds elements are zero-filled by the hardware: conv padding costs nothing and no
+//     im2col buffer exists in HBM or smem.
+//   * Up to three A "segments" accumulate into the same TMEM tile: the 3x3 conv input plus 1x1 skip
+//     inputs (raw x, optionally split in two for the un-materialised torch.cat of the up path). This is
+//     how ResBlock's  skip_connection(x) + conv(h)  (unet.py:220) becomes a single kernel.
+//   * Weights are pre-packed [Cout][K] fp16, K = concat over segments/taps/channels, loaded by 2-D TMA.
+//   * Warp roles (256 threads): warp0 = TMA producer, warp1 = tcgen05.mma issuer, warp2 = TMEM alloc,
+//     warps4-7 = epilogue (tcgen05.ld -> +bias (+residual) -> fp16 -> global). Persistent over tiles,
+//     smem ring of STAGES (A 16 KB + B BN*128 B), TMEM accumulator double-buffered (2 x BN columns) so
+//     the epilogue of tile i overlaps the mainloop of tile i+1.
+#include <stdio.h>
+
+#include "k2_common.cuh"
+#include "k2_internal.h"
+
+namespace k2 {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 192 ? 5 : (BN >= 128 ? 6 : 8));
+  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
+};
+
+__device__ __forceinline__ void decode_m_tile(const ConvGemmParams& p, int m_idx, int& n0, int& y0,
+                                              int& x0) {
+  int tw_i = m_idx % p.tiles_w;
+  int t = m_idx / p.tiles_w;
+  int th_i = t % p.tiles_h;
+  int tn_i = t / p.tiles_h;
+  x0 = tw_i * p.TW;
+  y0 = th_i * p.TH;
+  n0 = tn_i * p.TN;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* tmem_full = empty_bar + C::STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmB);
+    for (int s = 0; s < 3; ++s)
+      if (p.seg_taps[s]) tma_prefetch_desc(&p.tmA[s]);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);  // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp_idx == 2) {
+    tmem_alloc(tmem_ptr, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int total_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp_idx == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = p.a_box_bytes + C::B_STAGE_BYTES;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_idx = tile % p.m_tiles;
+        const int n_idx = tile / p.m_tiles;
+        int n0, y0, x0;
+        decode_m_tile(p, m_idx, n0, y0, x0);
+        int kc_global = 0;
+        for (int s = 0; s < 3; ++s) {
+          const int taps = p.seg_taps[s];
+          if (taps == 0) continue;
+          const int kch = p.seg_kchunks[s];
+          for (int tap = 0; tap < taps; ++tap) {
+            const int dy = (taps == 9) ? (tap / 3 - 1) : 0;
+            const int dx = (taps == 9) ? (tap % 3 - 1) : 0;
+            for (int c = 0; c < kch; ++c) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* sA = smem + stage * C::STAGE_BYTES;
+              uint8_t* sB = sA + A_STAGE_BYTES;
+              mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+              tma_load_4d(sA, &p.tmA[s], &full_bar[stage], c * BK, x0 + dx, y0 + dy, n0);
+              tma_load_2d(sB, &p.tmB, &full_bar[stage], kc_global * BK, n_idx * BN);
+              ++kc_global;
+              if (++stage == C::STAGES) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================================== MMA issuer ========================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kc = 0; kc < p.num_k_chunks; ++kc) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint64_t adesc = make_sw128_desc(a_addr);
+          const uint64_t bdesc = make_sw128_desc(a_addr + A_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // +32 bytes (2 x 16 B units) per 16-element K step inside the 128 B swizzle row
+            umma_f16(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2),
+                     idesc, (kc | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs retire
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator ready for the epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp_idx >= 4) {
+    // ===================================== epilogue ==========================================
+    const int ew = warp_idx - 4;  // == warp_idx % 4 -> TMEM lanes [32*ew, 32*ew+32)
+    const int row = ew * 32 + lane;
+    const int thw = p.TH * p.TW;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    constexpr int CH = (BN >= 32) ? 32 : 16;  // columns per tcgen05.ld
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_idx = tile % p.m_tiles;
+      const int n_idx = tile / p.m_tiles;
+      int n0, y0, x0;
+      decode_m_tile(p, m_idx, n0, y0, x0);
+      const int tn = row / thw;
+      const int rem = row - tn * thw;
+      const int th = rem / p.TW;
+      const int tw = rem - th * p.TW;
+      const int n = n0 + tn, y = y0 + th, x = x0 + tw;
+      const bool valid = (tn < p.TN) && (n < p.NB) && (y < p.H) && (x < p.W);
+      const long long out_row = (static_cast<long long>(n) * p.H + y) * p.W + x;
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < BN / CH; ++j) {
+        const uint32_t taddr =
+            tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * BN + j * CH);
+        uint32_t r[CH];
+        if constexpr (CH == 32) {
+          tmem_ld_32x32b_x32(taddr, r);
+        } else {
+          tmem_ld_32x32b_x16(taddr, r);
+        }
+        tmem_ld_wait();
+        const int col0 = n_idx * BN + j * CH;
+        if (valid && col0 < p.Cout) {
+          if (p.out_mode == 0) {
+            __half* orow = reinterpret_cast<__half*>(p.out) + out_row * p.ldo + col0;
+            const __half* rrow = p.residual ? p.residual + out_row * p.ldr + col0 : nullptr;
+            if (col0 + CH <= p.Cout) {
+#pragma unroll
+              for (int v = 0; v < CH / 8; ++v) {
+                float f[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  f[e] = __uint_as_float(r[v * 8 + e]);
+                  if (p.bias) f[e] += __ldg(p.bias + col0 + v * 8 + e);
+                }
+                if (rrow) {
+                  uint4 rv = *reinterpret_cast<const uint4*>(rrow + v * 8);
+                  const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    float2 t = __half22float2(rh[e]);
+                    f[2 * e] += t.x;
+                    f[2 * e + 1] += t.y;
+                  }
+                }
+                uint4 ov;
+                __half2* oh = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+                *reinterpret_cast<uint4*>(orow + v * 8) = ov;
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < CH; ++e) {
+                if (col0 + e < p.Cout) {
+                  float f = __uint_as_float(r[e]);
+                  if (p.bias) f += __ldg(p.bias + col0 + e);
+                  if (rrow) f += __half2float(rrow[e]);
+                  orow[e] = __float2half_rn(f);
+                }
+              }
+            }
+          } else {
+            // fp32 NCHW (UNet / MoVQ output heads)
+            float* o = reinterpret_cast<float*>(p.out);
+#pragma unroll
+            for (int e = 0; e < CH; ++e) {
+              if (col0 + e < p.Cout) {
+                float f = __uint_as_float(r[e]);
+                if (p.bias) f += __ldg(p.bias + col0 + e);
+                o[((static_cast<long long>(n) * p.Cout + (col0 + e)) * p.H + y) * p.W + x] = f;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+template <int BN>
+int launch_bn(const ConvGemmParams& p, cudaStream_t stream) {
+  using C = Cfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    K2_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       C::SMEM_BYTES));
+    attr_set = true;
+  }
+  int total = p.m_tiles * p.n_tiles;
+  int grid = total < num_sms() ? total : num_sms();
+  conv_gemm_kernel<BN><<<grid, 256, C::SMEM_BYTES, stream>>>(p);
+  K2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+int launch_conv_gemm(const ConvGemmParams& p, int BN, cudaStream_t stream) {
+  switch (BN) {
+    case 16: return launch_bn<16>(p, stream);
+    case 64: return launch_bn<64>(p, stream);
+    case 128: return launch_bn<128>(p, stream);
+    case 192: return launch_bn<192>(p, stream);
+    case 256: return launch_bn<256>(p, stream);
+    default: return fail("conv_gemm: unsupported BN");
+  }
+}
+
+}  // namespace k2

@@ -1,0 +1,70 @@
+// k2_internal.h -- declarations shared between the kernel translation units and the C-ABI layer.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+namespace k2 {
+
+// ---- error plumbing (no exceptions cross the C ABI) ---------------------------------------------
+void set_error(const std::string& msg);
+int fail(const std::string& msg);  // records msg, returns -1
+#define K2_CHECK_CUDA(expr)                                                                 \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess)                                                                  \
+      return ::k2::fail(std::string(#expr) + ": " + cudaGetErrorString(_e));                \
+  } while (0)
+#define K2_REQUIRE(cond, msg)                                  \
+  do {                                                         \
+    if (!(cond)) return ::k2::fail(std::string("k2b200: ") + (msg)); \
+  } while (0)
+
+int num_sms();
+void count_launch(int n = 1);  // bump the library-wide kernel launch counter
+
+// ---- TMA tensor-map encoding (driver entry point fetched at run time; no libcuda link) ----------
+// fp16 tensor, rank<=4, 128B swizzle, inner box dim must be 64 elements (=128 bytes).
+int encode_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box);
+
+// ---- implicit-GEMM convolution / GEMM (k2_conv_gemm.cu) -----------------------------------------
+struct ConvGemmParams {
+  CUtensorMap tmA[3];  // activation sources, 4-D (C, W, H, N)
+  CUtensorMap tmB;     // packed weights, 2-D (Ktot, Cout_rows), K contiguous
+  int seg_taps[3];     // 9 (3x3, pad 1), 1 (1x1) or 0 (unused)
+  int seg_kchunks[3];  // 64-channel chunks per tap
+  int num_k_chunks;
+  int NB, H, W;        // output geometry
+  int TN, TH, TW;      // rows of one M tile = TN*TH*TW <= 128 (a TMA box)
+  int tiles_n, tiles_h, tiles_w;
+  int m_tiles, n_tiles;
+  int Cout;            // logical output channels
+  const float* bias;   // [Cout] or nullptr
+  const __half* residual;  // [M, ldr] or nullptr (added after bias)
+  int ldr;
+  void* out;
+  int ldo;
+  int out_mode;        // 0: fp16 [M, ldo] rows (NHWC); 1: fp32 NCHW [NB, Cout, H, W]
+  uint32_t a_box_bytes;
+};
+int launch_conv_gemm(const ConvGemmParams& p, int BN, cudaStream_t stream);
+
+// ---- fused attention, head dim 64 (k2_attention.cu) ---------------------------------------------
+struct AttnParams {
+  CUtensorMap tmQKV;   // 3-D (3C, T, B) over the qkv buffer, box (64, 128|64, 1)
+  CUtensorMap tmKV;    // same buffer, box (64, 64, 1) for K/V blocks
+  CUtensorMap tmEnc;   // 3-D (2C, Tc, B) over encoder kv, box (64, 64, 1)
+  int B, heads, T, Tc;
+  int q_stride_h, k_off, v_off;      // channel offsets inside one head's slab of the qkv row
+  int enc_stride_h, enc_k_off, enc_v_off;
+  __half* out;         // [B, T, heads*64]
+  int ldo;
+  float scale_log2e;   // softmax scale * log2(e)
+};
+int launch_attention_d64(const AttnParams& p, cudaStream_t stream);
+
+}  // namespace k2

@@ -1,0 +1,534 @@
+// k2_misc.cu -- the small kernels of the path: dense layers on tiny M, LayerNorm, timestep embedding,
+// stem im2col, the fused classifier-free-guidance + DDPM sampler step, and the MoVQ helpers.
+// Reference call sites are cited at each entry point (declared in include/k2b200.h).
+#include <math.h>
+
+#include "../../include/k2b200.h"
+#include "k2_common.cuh"
+#include "k2_internal.h"
+
+namespace k2 {
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// linear: one warp per output column, MT rows of x per pass. Weight rows are streamed once per row tile
+// with 16-byte loads (fp16) -- this is a bandwidth-bound GEMV-like op (M = 2*batch rows).
+// ------------------------------------------------------------------------------------------------
+constexpr int LIN_MT = 8;   // rows of x staged in shared memory per block
+constexpr int LIN_CB = 4;   // output columns per warp pass (register blocking over the staged x)
+
+template <bool W_HALF>
+__device__ __forceinline__ void load_w8(const void* Wv, long long off, float (&w)[8]) {
+  if (W_HALF) {
+    uint4 raw = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(Wv) + off));
+    const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float2 t = __half22float2(h2[e]);
+      w[2 * e] = t.x;
+      w[2 * e + 1] = t.y;
+    }
+  } else {
+    const float4* wp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(Wv) + off);
+    float4 a = __ldg(wp), c = __ldg(wp + 1);
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = c.x; w[5] = c.y; w[6] = c.z; w[7] = c.w;
+  }
+}
+
+template <bool W_HALF>
+__global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x, int ldx, const void* __restrict__ Wv,
+                                                     const float* __restrict__ b, const float* __restrict__ add,
+                                                     int ldadd, float* __restrict__ y, int ldy, int M, int N, int K,
+                                                     int Kp, int vec_ok, int silu_in, int silu_out) {
+  extern __shared__ float xs[];  // [LIN_MT][Kp]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * LIN_MT;
+  const int mt = min(LIN_MT, M - m0);
+  for (int idx = threadIdx.x; idx < LIN_MT * Kp; idx += blockDim.x) {
+    const int r = idx / Kp, k = idx - r * Kp;
+    float v = 0.f;
+    if (r < mt && k < K) {
+      v = x[static_cast<long long>(m0 + r) * ldx + k];
+      if (silu_in) v = silu_f(v);
+    }
+    xs[idx] = v;
+  }
+  __syncthreads();
+  const int n0 = (blockIdx.x * 8 + warp) * LIN_CB;
+  if (n0 >= N) return;
+  float acc[LIN_CB][LIN_MT];
+#pragma unroll
+  for (int cb = 0; cb < LIN_CB; ++cb)
+#pragma unroll
+    for (int i = 0; i < LIN_MT; ++i) acc[cb][i] = 0.f;
+  const int K8 = vec_ok ? (K & ~7) : 0;
+  for (int k = lane * 8; k < K8; k += 256) {
+    float w[LIN_CB][8];
+#pragma unroll
+    for (int cb = 0; cb < LIN_CB; ++cb) {
+      if (n0 + cb < N) {
+        load_w8<W_HALF>(Wv, static_cast<long long>(n0 + cb) * K + k, w[cb]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) w[cb][e] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < LIN_MT; ++i) {
+      const float4 xa = *reinterpret_cast<const float4*>(xs + i * Kp + k);
+      const float4 xb = *reinterpret_cast<const float4*>(xs + i * Kp + k + 4);
+      const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+      for (int cb = 0; cb < LIN_CB; ++cb)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[cb][i] = fmaf(xv[e], w[cb][e], acc[cb][i]);
+    }
+  }
+  for (int k = K8 + lane; k < K; k += 32) {
+#pragma unroll
+    for (int cb = 0; cb < LIN_CB; ++cb) {
+      if (n0 + cb < N) {
+        const long long off = static_cast<long long>(n0 + cb) * K + k;
+        const float w = W_HALF ? __half2float(reinterpret_cast<const __half*>(Wv)[off])
+                               : reinterpret_cast<const float*>(Wv)[off];
+#pragma unroll
+        for (int i = 0; i < LIN_MT; ++i) acc[cb][i] = fmaf(xs[i * Kp + k], w, acc[cb][i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int cb = 0; cb < LIN_CB; ++cb) {
+#pragma unroll
+    for (int i = 0; i < LIN_MT; ++i) {
+      float v = acc[cb][i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      const int n = n0 + cb;
+      if (lane == 0 && i < mt && n < N) {
+        if (b) v += b[n];
+        if (silu_out) v = silu_f(v);
+        if (add) v += add[static_cast<long long>(m0 + i) * ldadd + n];
+        y[static_cast<long long>(m0 + i) * ldy + n] = v;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g,
+                                                        const float* __restrict__ b, float* __restrict__ y, int N,
+                                                        float eps) {
+  __shared__ double sred[2][8];
+  const int m = blockIdx.x;
+  const float* xr = x + static_cast<long long>(m) * N;
+  double s = 0.0, q = 0.0;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    double v = xr[i];
+    s += v;
+    q += v * v;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sred[0][threadIdx.x >> 5] = s;
+    sred[1][threadIdx.x >> 5] = q;
+  }
+  __syncthreads();
+  s = 0.0;
+  q = 0.0;
+  for (int w = 0; w < 8; ++w) {
+    s += sred[0][w];
+    q += sred[1][w];
+  }
+  const double mean = s / N;
+  double var = q / N - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  const float fmean = static_cast<float>(mean);
+  for (int i = threadIdx.x; i < N; i += blockDim.x)
+    y[static_cast<long long>(m) * N + i] = (xr[i] - fmean) * rstd * g[i] + b[i];
+}
+
+// nn.py:101-121: [cos(t*f) | sin(t*f)], f_j = exp(-ln(max_period) * j / half), fp32
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __restrict__ out, int B, int dim,
+                                          float max_period) {
+  const int half = dim / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * dim) return;
+  const int b = i / dim, j = i % dim;
+  float v = 0.f;
+  if (j < 2 * half) {
+    const int jj = j < half ? j : j - half;
+    const float freq = expf(-logf(max_period) * static_cast<float>(jj) / static_cast<float>(half));
+    const float arg = t[b] * freq;
+    v = j < half ? cosf(arg) : sinf(arg);
+  }
+  out[i] = v;
+}
+
+__global__ void f32_to_f16_kernel(const float* __restrict__ x, __half* __restrict__ y, long long n) {
+  long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (; i < n; i += stride) y[i] = __float2half_rn(x[i]);
+}
+
+// fp32 NCHW sources -> fp16 patch rows [NB*H*W, Kpad], k = tap*Cin + c
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x, int Cx,
+                                                          const float* __restrict__ x2, int C2,
+                                                          const float* __restrict__ x3, int C3, int mul23, int NB,
+                                                          int H, int W, __half* __restrict__ out, int Kpad) {
+  const long long item = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(NB) * H * W * Kpad;
+  if (item >= total) return;
+  const int k = static_cast<int>(item % Kpad);
+  const long long pix = item / Kpad;
+  const int xx = static_cast<int>(pix % W);
+  const int yy = static_cast<int>((pix / W) % H);
+  const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
+  const int Cin = Cx + C2 + C3;
+  float v = 0.f;
+  if (k < 9 * Cin) {
+    const int tap = k / Cin, c = k % Cin;
+    const int yi = yy + tap / 3 - 1, xi = xx + tap % 3 - 1;
+    if (yi >= 0 && yi < H && xi >= 0 && xi < W) {
+      const long long sp = static_cast<long long>(yi) * W + xi;
+      if (c < Cx) {
+        v = x[(static_cast<long long>(n) * Cx + c) * H * W + sp];
+      } else if (c < Cx + C2) {
+        v = x2[(static_cast<long long>(n) * C2 + (c - Cx)) * H * W + sp];
+        if (mul23) v *= x3[static_cast<long long>(n) * C3 * H * W + sp];  // inpaint_image * inpaint_mask
+      } else {
+        v = x3[(static_cast<long long>(n) * C3 + (c - Cx - C2)) * H * W + sp];
+      }
+    }
+  }
+  out[item] = __float2half_rn(v);
+}
+
+// ------------------------------------------------------------------------------------------------
+// sampler step
+// ------------------------------------------------------------------------------------------------
+struct SamplerParams {
+  const float* model_out;  // [2B, 8, H, W]
+  float* x;                // [B, 4, H, W]
+  const float* noise;
+  const float* coef;       // device [8]
+  int B, HW;
+  float guidance;
+  int cond_first;
+  float clip;
+  int threshold_mode;
+  const float* init;       // [B,4,H,W] or null
+  const float* mask;       // [B,1,H,W] or null
+  float* x0;               // work [B*4*HW]
+  float* sval;             // work scalar (dynamic threshold s)
+};
+
+__global__ void __launch_bounds__(256) sampler_x0_kernel(const SamplerParams p) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(p.B) * 4 * p.HW;
+  if (i >= total) return;
+  const int sp = static_cast<int>(i % p.HW);
+  const int c = static_cast<int>((i / p.HW) % 4);
+  const int b = static_cast<int>(i / (4LL * p.HW));
+  const int bc = p.cond_first ? b : b + p.B;
+  const int bu = p.cond_first ? b + p.B : b;
+  const float ec = p.model_out[(static_cast<long long>(bc) * 8 + c) * p.HW + sp];
+  const float eu = p.model_out[(static_cast<long long>(bu) * 8 + c) * p.HW + sp];
+  const float eps = eu + p.guidance * (ec - eu);
+  float x0 = p.coef[0] * p.x[i] - p.coef[1] * eps;
+  x0 = fminf(fmaxf(x0, -p.clip), p.clip);
+  if (p.mask) {
+    const float m = p.mask[static_cast<long long>(b) * p.HW + sp];
+    x0 = x0 * (1.f - m) + p.init[i] * m;
+  }
+  p.x0[i] = x0;
+}
+
+// exact order statistics of |v[0..n)| (non-negative floats compare like their bit patterns):
+// 4-pass byte radix select, single block. Reproduces np.percentile(|x|, 99.5) with linear interpolation
+// (gaussian_diffusion.py:288-292) and s = max(s, 1).
+__device__ float radix_select(const float* __restrict__ v, int n, int rank, unsigned int* hist, unsigned int* sh) {
+  unsigned int prefix = 0, mask = 0;
+  int k = rank;
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const unsigned int u = __float_as_uint(fabsf(v[i]));
+      if ((u & mask) == prefix) atomicAdd(&hist[(u >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned int cum = 0;
+      int bin = 0;
+      for (; bin < 256; ++bin) {
+        if (cum + hist[bin] > static_cast<unsigned int>(k)) break;
+        cum += hist[bin];
+      }
+      sh[0] = static_cast<unsigned int>(bin);
+      sh[1] = cum;
+    }
+    __syncthreads();
+    prefix |= sh[0] << shift;
+    mask |= 255u << shift;
+    k -= static_cast<int>(sh[1]);
+    __syncthreads();
+  }
+  return __uint_as_float(prefix);
+}
+
+__global__ void __launch_bounds__(1024) sampler_percentile_kernel(const float* __restrict__ x0, int n, float* sval) {
+  __shared__ unsigned int hist[256];
+  __shared__ unsigned int sh[2];
+  const double pos = 0.995 * static_cast<double>(n - 1);
+  int lo = static_cast<int>(floor(pos));
+  const double frac = pos - lo;
+  int hi = lo + 1 < n ? lo + 1 : n - 1;
+  const float a = radix_select(x0, n, lo, hist, sh);
+  const float b = radix_select(x0, n, hi, hist, sh);
+  if (threadIdx.x == 0) {
+    // numpy _lerp: a + (b-a)*t, switched to b - (b-a)*(1-t) for t >= 0.5
+    const double da = a, db = b;
+    double r = (frac >= 0.5) ? db - (db - da) * (1.0 - frac) : da + (db - da) * frac;
+    float s = static_cast<float>(r);
+    *sval = fmaxf(s, 1.0f);
+  }
+}
+
+__global__ void __launch_bounds__(256) sampler_post_kernel(const SamplerParams p) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(p.B) * 4 * p.HW;
+  if (i >= total) return;
+  const int sp = static_cast<int>(i % p.HW);
+  const int c = static_cast<int>((i / p.HW) % 4);
+  const int b = static_cast<int>(i / (4LL * p.HW));
+  const int bc = p.cond_first ? b : b + p.B;
+  float x0 = p.x0[i];
+  if (p.threshold_mode == 1) {
+    const float s = *p.sval;
+    x0 = fminf(fmaxf(x0, -s), s) / s;
+  }
+  const float mean = p.coef[2] * x0 + p.coef[3] * p.x[i];
+  const float v = p.model_out[(static_cast<long long>(bc) * 8 + 4 + c) * p.HW + sp];
+  const float frac = (v + 1.f) * 0.5f;
+  const float logvar = frac * p.coef[5] + (1.f - frac) * p.coef[4];
+  p.x[i] = mean + p.coef[6] * expf(0.5f * logvar) * p.noise[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// MoVQ helpers
+// ------------------------------------------------------------------------------------------------
+// quntize.py:89-98: d = sum(z^2) + sum(e^2) - 2 z.e ; argmin (first minimum). dim == 4.
+__global__ void __launch_bounds__(256) vq_argmin_kernel(const float* __restrict__ z, const float* __restrict__ cb,
+                                                        long long* __restrict__ idx, int n, int n_embed) {
+  extern __shared__ float4 scb[];  // tile of the codebook
+  constexpr int TILE = 2048;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < n) zv = reinterpret_cast<const float4*>(z)[i];
+  const float zz = ((zv.x * zv.x + zv.y * zv.y) + zv.z * zv.z) + zv.w * zv.w;
+  float best = INFINITY;
+  int bi = 0;
+  for (int t0 = 0; t0 < n_embed; t0 += TILE) {
+    const int cnt = min(TILE, n_embed - t0);
+    __syncthreads();
+    for (int j = threadIdx.x; j < cnt; j += blockDim.x) scb[j] = reinterpret_cast<const float4*>(cb)[t0 + j];
+    __syncthreads();
+    for (int j = 0; j < cnt; ++j) {
+      const float4 e = scb[j];
+      const float ee = ((e.x * e.x + e.y * e.y) + e.z * e.z) + e.w * e.w;
+      const float dot = ((zv.x * e.x + zv.y * e.y) + zv.z * e.z) + zv.w * e.w;
+      const float d = (zz + ee) - 2.f * dot;
+      if (d < best) {
+        best = d;
+        bi = t0 + j;
+      }
+    }
+  }
+  if (i < n) idx[i] = bi;
+}
+
+__global__ void nchw_to_nhwc_f32_kernel(const float* __restrict__ x, float* __restrict__ y, int NB, int C, int H, int W) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(NB) * C * H * W;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % C);
+  const long long pix = i / C;
+  const int sp = static_cast<int>(pix % (static_cast<long long>(H) * W));
+  const int n = static_cast<int>(pix / (static_cast<long long>(H) * W));
+  y[i] = x[(static_cast<long long>(n) * C + c) * H * W + sp];
+}
+
+// utils.py:57-70: ((x+1)*127.5).round().clamp(0,255).uint8, NCHW -> NHWC, cropped to (crop_h, crop_w)
+__global__ void images_to_u8_kernel(const float* __restrict__ x, uint8_t* __restrict__ out, int NB, int C, int H, int W,
+                                    int ch, int cw) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(NB) * ch * cw * C;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % C);
+  const long long pix = i / C;
+  const int xx = static_cast<int>(pix % cw);
+  const int yy = static_cast<int>((pix / cw) % ch);
+  const int n = static_cast<int>(pix / (static_cast<long long>(cw) * ch));
+  float v = (x[((static_cast<long long>(n) * C + c) * H + yy) * W + xx] + 1.f) * 127.5f;
+  v = rintf(v);  // torch.round = round-half-to-even
+  v = fminf(fmaxf(v, 0.f), 255.f);
+  out[i] = static_cast<uint8_t>(v);
+}
+
+// tiny per-pixel channel mix on fp32 NCHW (MoVQ post_quant_conv 4->4, autoencoder.py:183)
+__global__ void pointwise_nchw_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                                      float* __restrict__ y, int NB, int Ci, int Co, int HW) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(NB) * Co * HW;
+  if (i >= total) return;
+  const int sp = static_cast<int>(i % HW);
+  const int o = static_cast<int>((i / HW) % Co);
+  const int n = static_cast<int>(i / (static_cast<long long>(HW) * Co));
+  float acc = b ? b[o] : 0.f;
+  for (int c = 0; c < Ci; ++c) acc = fmaf(w[o * Ci + c], x[(static_cast<long long>(n) * Ci + c) * HW + sp], acc);
+  y[i] = acc;
+}
+
+inline unsigned int blocks_for(long long total, int bs) { return static_cast<unsigned int>((total + bs - 1) / bs); }
+
+}  // namespace
+}  // namespace k2
+
+using namespace k2;
+
+extern "C" {
+
+int k2_linear(const float* x, int ldx, const void* W, int w_is_half, const float* b, const float* add, int ldadd,
+              float* y, int ldy, int M, int N, int K, int silu_in, int silu_out, k2_stream_t stream) {
+  K2_REQUIRE(x && W && y && M > 0 && N > 0 && K > 0, "linear: bad arguments");
+  const int Kp = (K + 7) & ~7;
+  const size_t smem = static_cast<size_t>(LIN_MT) * Kp * sizeof(float);
+  K2_REQUIRE(smem <= 160 * 1024, "linear: K too large for the shared-memory x tile");
+  const int vec_ok = ((K & 7) == 0) && ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
+  static bool attr_set = false;
+  if (!attr_set) {
+    K2_CHECK_CUDA(cudaFuncSetAttribute(linear_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    K2_CHECK_CUDA(cudaFuncSetAttribute(linear_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set = true;
+  }
+  dim3 grid((N + 8 * LIN_CB - 1) / (8 * LIN_CB), (M + LIN_MT - 1) / LIN_MT);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (w_is_half)
+    linear_kernel<true><<<grid, 256, smem, st>>>(x, ldx, W, b, add, ldadd, y, ldy, M, N, K, Kp, vec_ok, silu_in, silu_out);
+  else
+    linear_kernel<false><<<grid, 256, smem, st>>>(x, ldx, W, b, add, ldadd, y, ldy, M, N, K, Kp, vec_ok, silu_in, silu_out);
+  K2_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int k2_layernorm(const float* x, const float* gamma, const float* beta, float* y, int M, int N, float eps,
+                 k2_stream_t stream) {
+  K2_REQUIRE(x && gamma && beta && y && M > 0 && N > 0, "layernorm: bad arguments");
+  layernorm_kernel<<<M, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, gamma, beta, y, N, eps);
+  K2_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int k2_timestep_embedding(const float* t, float* out, int B, int dim, float max_period, k2_stream_t stream) {
+  K2_REQUIRE(t && out && B > 0 && dim > 0, "timestep_embedding: bad arguments");
+  timestep_embedding_kernel<<<blocks_for(static_cast<long long>(B) * dim, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      t, out, B, dim, max_period);
+  K2_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int k2_f32_to_f16(const float* x, void* y, long long n, k2_stream_t stream) {
+  K2_REQUIRE(x && y && n > 0, "f32_to_f16: bad arguments");
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  f32_to_f16_kernel<<<static_cast<unsigned int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, reinterpret_cast<__half*>(y), n);
+  K2_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int k2_stem_im2col(const float* x, int Cx, const float* x2, int C2, const float* x3, int C3, int mul23, int NB, int H,
+                   int W, void* out, int Kpad, k2_stream_t stream) {
+  K2_REQUIRE(x && out && Cx > 0, "stem_im2col: bad arguments");
+  K2_REQUIRE(Kpad % 64 == 0 && Kpad >= 9 * (Cx + C2 + C3), "stem_im2col: Kpad too small / not a multiple of 64");
+  K2_REQUIRE(!mul23 || (x2 && x3 && C3 == 1), "stem_im2col: mul23 needs x2 and a 1-channel x3");
+  const long long total = static_cast<long long>(NB) * H * W * Kpad;
+  stem_im2col_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, Cx, x2, C2, x3, C3, mul23, NB, H, W, reinterpret_cast<__half*>(out), Kpad);
+  K2_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int k2_sampler_step(const float* model_out, float* x, const float* noise, const float* coef, int B, int H, int W,
+                    float guidance, int cond_first, float clip, int threshold_mode, const float* inpaint_init,
+                    const float* inpaint_mask, float* work, k2_stream_t stream) {
+  K2_REQUIRE(model_out && x && noise && coef && work && B > 0, "sampler_step: bad arguments");
+  K2_REQUIRE((inpaint_init == nullptr) == (inpaint_mask == nullptr), "sampler_step: init and mask go together");
+  SamplerParams p;
+  p.model_out = model_out; p.x = x; p.noise = noise; p.coef = coef;
+  p.B = B; p.HW = H * W; p.guidance = guidance; p.cond_first = cond_first; p.clip = clip;
+  p.threshold_mode = threshold_mode; p.init = inpaint_init; p.mask = inpaint_mask;
+  p.x0 = work; p.sval = work + static_cast<long long>(B) * 4 * H * W;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long total = static_cast<long long>(B) * 4 * H * W;
+  sampler_x0_kernel<<<blocks_for(total, 256), 256, 0, st>>>(p);
+  if (threshold_mode == 1) {
+    sampler_percentile_kernel<<<1, 1024, 0, st>>>(p.x0, 4 * H * W, p.sval);
+    count_launch();
+  }
+  sampler_post_kernel<<<blocks_for(total, 256), 256, 0, st>>>(p);
+  K2_CHECK_CUDA(cudaGetLastError());
+  count_launch(2);
+  return 0;
+}
+
+int k2_vq_argmin(const float* z, const float* codebook, long long* idx, int n, int n_embed, int dim,
+                 k2_stream_t stream) {
+  K2_REQUIRE(z && codebook && idx && n > 0 && n_embed > 0, "vq_argmin: bad arguments");
+  K2_REQUIRE(dim == 4, "vq_argmin: only embed_dim 4 (MoVQ) is implemented");
+  vq_argmin_kernel<<<blocks_for(n, 256), 256, 2048 * sizeof(float4), static_cast<cudaStream_t>(stream)>>>(
+      z, codebook, idx, n, n_embed);
+  K2_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int k2_nchw_to_nhwc_f32(const float* x, float* y, int NB, int C, int H, int W, k2_stream_t stream) {
+  K2_REQUIRE(x && y, "nchw_to_nhwc: null");
+  nchw_to_nhwc_f32_kernel<<<blocks_for(static_cast<long long>(NB) * C * H * W, 256), 256, 0,
+                            static_cast<cudaStream_t>(stream)>>>(x, y, NB, C, H, W);
+  K2_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int k2_images_to_u8(const float* x_nchw, uint8_t* out_nhwc, int NB, int C, int H, int W, int crop_h, int crop_w,
+                    k2_stream_t stream) {
+  K2_REQUIRE(x_nchw && out_nhwc && crop_h <= H && crop_w <= W, "images_to_u8: bad arguments");
+  images_to_u8_kernel<<<blocks_for(static_cast<long long>(NB) * crop_h * crop_w * C, 256), 256, 0,
+                        static_cast<cudaStream_t>(stream)>>>(x_nchw, out_nhwc, NB, C, H, W, crop_h, crop_w);
+  K2_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int k2_pointwise_nchw_f32(const float* x, const float* w, const float* b, float* y, int NB, int Ci, int Co, int HW,
+                          k2_stream_t stream) {
+  K2_REQUIRE(x && w && y && Ci > 0 && Co > 0, "pointwise_nchw: bad arguments");
+  pointwise_nchw_kernel<<<blocks_for(static_cast<long long>(NB) * Co * HW, 256), 256, 0,
+                          static_cast<cudaStream_t>(stream)>>>(x, w, b, y, NB, Ci, Co, HW);
+  K2_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+}  // extern "C"

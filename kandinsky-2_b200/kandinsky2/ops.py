@@ -1,0 +1,306 @@
+"""Thin torch-tensor wrappers over the C ABI (include/k2b200.h).
+
+torch is used for device memory, streams and one-off weight re-layout only; every arithmetic op on the
+hot path is a kernel of libk2b200.so.  Activations are NHWC fp16 tensors of shape [NB, H, W, C] (a view
+may be a channel slice of a wider buffer: stride(-2) is the row stride).
+"""
+import ctypes
+
+import torch
+
+from . import _native as nat
+from ._native import K2ConvSrc, check, ptr, stream_ptr
+
+
+def _row_stride(t):
+    assert t.stride(-1) == 1, "channel dim must be contiguous"
+    ld = t.stride(-2)
+    # all leading dims must be row-contiguous w.r.t. ld
+    n = t.shape[-2]
+    for d in range(t.dim() - 3, -1, -1):
+        assert t.shape[d] == 1 or t.stride(d) == ld * n, f"not a row-strided NHWC view: {t.shape} {t.stride()}"
+        n *= t.shape[d]
+    return ld
+
+
+# ------------------------------------------------------------------------------------------------
+# weight packing (host side, once per checkpoint load)
+# ------------------------------------------------------------------------------------------------
+def _pad64(c):
+    return (c + 63) // 64 * 64
+
+
+def pack_conv_weight(w, split=None):
+    """[Cout, Cin, kh, kw] (kh=kw in {1,3}) or [Cout, Cin] / [Cout, Cin, 1] -> fp16 [Cout, taps*pad64(Cin)].
+
+    k = tap * pad64(Cin) + c with tap = ky*3+kx (k2b200.h: k2_conv_gemm).  `split=(C0, C1)` packs a 1x1
+    weight whose input is the channel concat of two sources as two independently padded segments.
+    """
+    w = w.detach()
+    if w.dim() == 2:
+        w = w[:, :, None, None]
+    elif w.dim() == 3:
+        w = w[:, :, :, None]
+    cout, cin, kh, kw = w.shape
+    taps = kh * kw
+    assert taps in (1, 9)
+    parts = [(0, cin)] if split is None else [(0, split[0]), (split[0], split[0] + split[1])]
+    segs = []
+    for lo, hi in parts:
+        c = hi - lo
+        ws = w[:, lo:hi].permute(0, 2, 3, 1).reshape(cout, taps, c)
+        if _pad64(c) != c:
+            ws = torch.nn.functional.pad(ws, (0, _pad64(c) - c))
+        segs.append(ws.reshape(cout, taps * _pad64(c)))
+    return torch.cat(segs, dim=1).to(torch.float16).contiguous()
+
+
+def pad_rows(wp, rows):
+    if wp.shape[0] >= rows:
+        return wp
+    return torch.cat([wp, wp.new_zeros(rows - wp.shape[0], wp.shape[1])], 0).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# conv / GEMM
+# ------------------------------------------------------------------------------------------------
+def conv_gemm(srcs, w_packed, cout, bias=None, residual=None, out=None, out_mode=0, geom=None):
+    """srcs: list of (tensor NHWC fp16 [NB,H,W,C], taps).  Returns fp16 [NB,H,W,cout] (out_mode 0) or
+    fp32 NCHW [NB,cout,H,W] (out_mode 1).  geom=(NB,H,W) overrides the geometry (GEMM on flat rows)."""
+    lib = nat.load()
+    t0 = srcs[0][0]
+    NB, H, W = geom if geom is not None else t0.shape[:3]
+    arr = (K2ConvSrc * len(srcs))()
+    for i, (t, taps) in enumerate(srcs):
+        assert t.dtype == torch.float16 and t.is_cuda
+        arr[i].ptr = t.data_ptr()
+        arr[i].C = t.shape[-1]
+        arr[i].ld = _row_stride(t)
+        arr[i].taps = taps
+    if out is None:
+        if out_mode == 0:
+            out = torch.empty((NB, H, W, cout), dtype=torch.float16, device=t0.device)
+        else:
+            out = torch.empty((NB, cout, H, W), dtype=torch.float32, device=t0.device)
+    ldo = _row_stride(out) if out_mode == 0 else 0
+    ldr = _row_stride(residual) if residual is not None else 0
+    assert w_packed.dtype == torch.float16 and w_packed.is_contiguous()
+    check(lib.k2_conv_gemm(arr, len(srcs), NB, H, W, ptr(w_packed), w_packed.shape[0], w_packed.shape[1], cout,
+                           ptr(bias), ptr(residual), ldr, ptr(out), ldo, out_mode, stream_ptr()))
+    return out
+
+
+def gemm_rows(x, w_packed, cout, bias=None, residual=None, out=None):
+    """x: fp16 [..., K] rows -> fp16 [..., cout]; one 1x1 'conv' over M = prod(leading dims) rows."""
+    lead = x.shape[:-1]
+    M = 1
+    for d in lead:
+        M *= d
+    x3 = x.reshape(1, 1, M, x.shape[-1]) if x.is_contiguous() else None
+    if x3 is None:
+        # row-strided view (channel slice): keep stride
+        x3 = x.as_strided((1, 1, M, x.shape[-1]), (0, 0, x.stride(-2), 1))
+    if out is None:
+        out = torch.empty(tuple(lead) + (cout,), dtype=torch.float16, device=x.device)
+    o3 = out.as_strided((1, 1, M, cout), (0, 0, out.stride(-2), 1))
+    r3 = None
+    if residual is not None:
+        r3 = residual.as_strided((1, 1, M, cout), (0, 0, residual.stride(-2), 1))
+    conv_gemm([(x3, 1)], w_packed, cout, bias=bias, residual=r3, out=o3, geom=(1, 1, M))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# GroupNorm
+# ------------------------------------------------------------------------------------------------
+_gn_scratch = {}
+
+
+def _scratch(dev, nfloats):
+    key = (dev.index, )
+    buf = _gn_scratch.get(key)
+    if buf is None or buf.numel() < nfloats:
+        buf = torch.zeros(max(nfloats, 1 << 20), dtype=torch.float32, device=dev)
+        _gn_scratch[key] = buf
+    return buf
+
+
+def gn_stats(x0, x1=None, groups=32, eps=1e-5, stats=None):
+    """Per (image, group) [mean, rstd] of the channel concat [x0 | x1]; x*: fp16 NHWC."""
+    lib = nat.load()
+    NB, H, W, C0 = x0.shape
+    C1 = x1.shape[-1] if x1 is not None else 0
+    if stats is None:
+        stats = torch.empty((NB, groups, 2), dtype=torch.float32, device=x0.device)
+    need = lib.k2_gn_scratch_floats(NB, H * W, groups)
+    scratch = _scratch(x0.device, need)
+    check(lib.k2_gn_stats(ptr(x0), C0, _row_stride(x0), ptr(x1), C1, _row_stride(x1) if x1 is not None else 0,
+                          NB, H * W, groups, eps, ptr(stats), ptr(scratch), stream_ptr()))
+    return stats
+
+
+def gn_apply(x0, x1, stats, gamma, beta, film=None, act=1, resample=0, groups=32, y=None, want_xres=False,
+             zq=None, sn_w=None):
+    """Fused normalise (+FiLM) (+SiLU) (+2x up / 2x2 avg-pool) (+concat) -> fp16 NHWC. See k2b200.h."""
+    lib = nat.load()
+    NB, H, W, C0 = x0.shape
+    C1 = x1.shape[-1] if x1 is not None else 0
+    C = C0 + C1
+    Ho, Wo = (H, W) if resample == 0 else ((H // 2, W // 2) if resample == 1 else (H * 2, W * 2))
+    if y is None:
+        y = torch.empty((NB, Ho, Wo, C), dtype=torch.float16, device=x0.device)
+    xres = None
+    if want_xres:
+        xres = torch.empty((NB, Ho, Wo, C), dtype=torch.float16, device=x0.device)
+    zh = zw = 0
+    if zq is not None:
+        zh, zw = zq.shape[1], zq.shape[2]
+    check(lib.k2_gn_apply(ptr(x0), C0, _row_stride(x0), ptr(x1), C1, _row_stride(x1) if x1 is not None else 0,
+                          NB, H, W, groups, ptr(stats), ptr(gamma), ptr(beta), ptr(film),
+                          film.stride(0) if film is not None else 0, act, resample,
+                          ptr(y), _row_stride(y), ptr(xres), _row_stride(xres) if xres is not None else 0,
+                          ptr(zq), zh, zw, ptr(sn_w), stream_ptr()))
+    return (y, xres) if want_xres else y
+
+
+# ------------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------------
+def attention_d64(qkv, heads, enc=None, scale=0.125, out=None, hs=192, q_off=0, k_off=64, v_off=128, ehs=128,
+                  ek_off=0, ev_off=64):
+    """qkv fp16 [B, T, >=heads*hs]; enc fp16 [B, Tc, heads*ehs] or None -> fp16 [B, T, heads*64]."""
+    lib = nat.load()
+    B, T = qkv.shape[:2]
+    Tc = enc.shape[1] if enc is not None else 0
+    if out is None:
+        out = torch.empty((B, T, heads * 64), dtype=torch.float16, device=qkv.device)
+    check(lib.k2_attention_d64(ptr(qkv), qkv.stride(1), hs, q_off, k_off, v_off, ptr(enc),
+                               enc.stride(1) if enc is not None else 0, ehs, ek_off, ev_off, B, heads, T, Tc,
+                               scale, ptr(out), out.stride(1), stream_ptr()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# small dense layers
+# ------------------------------------------------------------------------------------------------
+def linear(x, W, b=None, add=None, silu_in=False, silu_out=False, out=None):
+    """fp32 x [M,K] (row-strided ok) @ W[N,K]^T (+b) (+add) -> fp32 [M,N]."""
+    lib = nat.load()
+    M, K = x.shape
+    N = W.shape[0]
+    assert W.shape[1] == K and W.is_contiguous() and x.dtype == torch.float32
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    check(lib.k2_linear(ptr(x), x.stride(0), ptr(W), 1 if W.dtype == torch.float16 else 0, ptr(b), ptr(add),
+                        add.stride(0) if add is not None else 0, ptr(out), out.stride(0), M, N, K,
+                        int(silu_in), int(silu_out), stream_ptr()))
+    return out
+
+
+def layernorm(x, gamma, beta, eps=1e-5):
+    lib = nat.load()
+    M, N = x.shape
+    y = torch.empty_like(x)
+    check(lib.k2_layernorm(ptr(x), ptr(gamma), ptr(beta), ptr(y), M, N, eps, stream_ptr()))
+    return y
+
+
+def timestep_embedding(t, dim, max_period=10000.0, out=None):
+    lib = nat.load()
+    B = t.shape[0]
+    if out is None:
+        out = torch.empty((B, dim), dtype=torch.float32, device=t.device)
+    check(lib.k2_timestep_embedding(ptr(t), ptr(out), B, dim, max_period, stream_ptr()))
+    return out
+
+
+def f32_to_f16(x, out=None):
+    lib = nat.load()
+    assert x.is_contiguous() and x.dtype == torch.float32
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    check(lib.k2_f32_to_f16(ptr(x), ptr(out), x.numel(), stream_ptr()))
+    return out
+
+
+def stem_im2col(x, x2=None, x3=None, mul23=False, kpad=None, out=None):
+    """fp32 NCHW inputs -> fp16 [NB, H, W, kpad] 3x3 patches of cat([x, x2*(x3 if mul23), x3], 1)."""
+    lib = nat.load()
+    NB, Cx, H, W = x.shape
+    C2 = x2.shape[1] if x2 is not None else 0
+    C3 = x3.shape[1] if x3 is not None else 0
+    cin = Cx + C2 + C3
+    if kpad is None:
+        kpad = _pad64(9 * cin)
+    if out is None:
+        out = torch.empty((NB, H, W, kpad), dtype=torch.float16, device=x.device)
+    check(lib.k2_stem_im2col(ptr(x), Cx, ptr(x2), C2, ptr(x3), C3, int(mul23), NB, H, W, ptr(out), kpad,
+                             stream_ptr()))
+    return out
+
+
+def pack_stem_weight(w):
+    """[Cout, Cin, 3, 3] -> fp16 [Cout, pad64(9*Cin)] with k = tap*Cin + c (matches stem_im2col)."""
+    cout, cin = w.shape[:2]
+    wp = w.detach().permute(0, 2, 3, 1).reshape(cout, 9 * cin)
+    k = _pad64(9 * cin)
+    if k != 9 * cin:
+        wp = torch.nn.functional.pad(wp, (0, k - 9 * cin))
+    return wp.to(torch.float16).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# sampler / MoVQ helpers
+# ------------------------------------------------------------------------------------------------
+def sampler_step(model_out, x, noise, coef, guidance, cond_first, clip=2.0, threshold_mode=0, inpaint_init=None,
+                 inpaint_mask=None, work=None):
+    lib = nat.load()
+    B, _, H, W = x.shape
+    if work is None:
+        work = torch.empty(B * 4 * H * W + 4096, dtype=torch.float32, device=x.device)
+    check(lib.k2_sampler_step(ptr(model_out), ptr(x), ptr(noise), ptr(coef), B, H, W, float(guidance),
+                              int(cond_first), float(clip), int(threshold_mode), ptr(inpaint_init),
+                              ptr(inpaint_mask), ptr(work), stream_ptr()))
+    return x
+
+
+def vq_argmin(z, codebook):
+    """z fp32 [n, dim], codebook fp32 [n_embed, dim] -> int64 [n] (ties -> lowest index)."""
+    lib = nat.load()
+    n, dim = z.shape
+    idx = torch.empty((n,), dtype=torch.int64, device=z.device)
+    check(lib.k2_vq_argmin(ptr(z), ptr(codebook), ptr(idx), n, codebook.shape[0], dim, stream_ptr()))
+    return idx
+
+
+def pointwise_nchw_f32(x, w, b):
+    lib = nat.load()
+    NB, Ci, H, W = x.shape
+    Co = w.shape[0]
+    y = torch.empty((NB, Co, H, W), dtype=torch.float32, device=x.device)
+    check(lib.k2_pointwise_nchw_f32(ptr(x), ptr(w), ptr(b), ptr(y), NB, Ci, Co, H * W, stream_ptr()))
+    return y
+
+
+def nchw_to_nhwc_f32(x):
+    lib = nat.load()
+    NB, C, H, W = x.shape
+    y = torch.empty((NB, H, W, C), dtype=torch.float32, device=x.device)
+    check(lib.k2_nchw_to_nhwc_f32(ptr(x), ptr(y), NB, C, H, W, stream_ptr()))
+    return y
+
+
+def images_to_u8(x, crop_h, crop_w):
+    lib = nat.load()
+    NB, C, H, W = x.shape
+    out = torch.empty((NB, crop_h, crop_w, C), dtype=torch.uint8, device=x.device)
+    check(lib.k2_images_to_u8(ptr(x), ptr(out), NB, C, H, W, crop_h, crop_w, stream_ptr()))
+    return out
+
+
+def launch_count():
+    return nat.load().k2_launch_count()
+
+
+def reset_launch_count():
+    nat.load().k2_reset_launch_count()

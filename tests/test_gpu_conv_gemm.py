@@ -1,0 +1,90 @@
+"""GPU parity of k2_conv_gemm (tcgen05 implicit-GEMM conv) against torch fp32 conv2d on the same fp16 data."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_conv(x_nhwc, w, b, pad):
+    y = F.conv2d(x_nhwc.float().permute(0, 3, 1, 2), w.half().float(), b, padding=pad)
+    return y.permute(0, 2, 3, 1)
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+
+@pytest.mark.parametrize("NB,H,W,Cin,Cout", [
+    (2, 16, 16, 64, 128),     # one (16x8) box geometry, BN=128
+    (1, 96, 96, 128, 256),    # metric geometry, BN=256, multi-tile persistent loop
+    (3, 24, 24, 192, 192),    # TW=24 TH=5 partial boxes, BN=192
+    (4, 12, 12, 128, 384),    # 12x6 boxes
+    (5, 4, 4, 64, 64),        # TN>1: several images per tile, BN=64
+    (2, 8, 12, 64, 320),      # non-square, Cout not a multiple of the N tile
+])
+def test_conv3x3(NB, H, W, Cin, Cout):
+    from kandinsky2 import ops
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(NB, H, W, Cin, device="cuda", generator=g).half()
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) / (3 * Cin ** 0.5)
+    b = torch.randn(Cout, device="cuda", generator=g)
+    y = ops.conv_gemm([(x, 9)], ops.pack_conv_weight(w), Cout, bias=b)
+    torch.cuda.synchronize()
+    ref = _ref_conv(x, w, b, 1)
+    err = (y.float() - ref).abs().max().item()
+    assert err < 2e-2 * max(1.0, ref.abs().max().item()) / 4, f"max abs err {err}"
+    # fp16 output rounding only: relative error of the bulk must be ~1e-3
+    rel = ((y.float() - ref).norm() / ref.norm()).item()
+    assert rel < 1e-3, rel
+
+
+def test_gemm_rows_bias_residual():
+    from kandinsky2 import ops
+    g = torch.Generator(device="cuda").manual_seed(1)
+    M, K, N = 1000, 256, 384
+    x = torch.randn(M, K, device="cuda", generator=g).half()
+    w = torch.randn(N, K, device="cuda", generator=g) / K ** 0.5
+    b = torch.randn(N, device="cuda", generator=g)
+    r = torch.randn(M, N, device="cuda", generator=g).half()
+    y = ops.gemm_rows(x, ops.pack_conv_weight(w), N, bias=b, residual=r)
+    torch.cuda.synchronize()
+    ref = x.float() @ w.half().float().t() + b + r.float()
+    rel = ((y.float() - ref).norm() / ref.norm()).item()
+    assert rel < 1e-3, rel
+
+
+def test_conv_plus_skip_segments():
+    """3x3 conv of h plus 1x1 skip of the (virtual) concat [xa | xb] accumulated in one kernel, + residual-free."""
+    from kandinsky2 import ops
+    g = torch.Generator(device="cuda").manual_seed(2)
+    NB, H, W, Ch, Ca, Cb, Cout = 2, 16, 16, 128, 64, 128, 256
+    h = torch.randn(NB, H, W, Ch, device="cuda", generator=g).half()
+    buf = torch.randn(NB, H, W, Ca + Cb + 64, device="cuda", generator=g).half()
+    xa, xb = buf[..., :Ca], buf[..., Ca:Ca + Cb]            # channel-slice views (row stride > C)
+    w3 = torch.randn(Cout, Ch, 3, 3, device="cuda", generator=g) / (3 * Ch ** 0.5)
+    w1 = torch.randn(Cout, Ca + Cb, 1, 1, device="cuda", generator=g) / (Ca + Cb) ** 0.5
+    b = torch.randn(Cout, device="cuda", generator=g)
+    wp = torch.cat([ops.pack_conv_weight(w3), ops.pack_conv_weight(w1, split=(Ca, Cb))], 1).contiguous()
+    y = ops.conv_gemm([(h, 9), (xa, 1), (xb, 1)], wp, Cout, bias=b)
+    torch.cuda.synchronize()
+    ref = _ref_conv(h, w3, b, 1) + _ref_conv(torch.cat([xa, xb], -1), w1, None, 0)
+    rel = ((y.float() - ref).norm() / ref.norm()).item()
+    assert rel < 1e-3, rel
+
+
+def test_head_fp32_nchw():
+    from kandinsky2 import ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    NB, H, W, Cin, Cout = 2, 32, 32, 128, 8
+    x = torch.randn(NB, H, W, Cin, device="cuda", generator=g).half()
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) / (3 * Cin ** 0.5)
+    b = torch.randn(Cout, device="cuda", generator=g)
+    wp = ops.pad_rows(ops.pack_conv_weight(w), 16)
+    y = ops.conv_gemm([(x, 9)], wp, Cout, bias=b, out_mode=1)
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.half().float(), b, padding=1)
+    assert y.shape == ref.shape and y.dtype == torch.float32
+    assert (y - ref).abs().max().item() < 2e-3
