@@ -69,7 +69,8 @@ int k2_conv_gemm(const K2ConvSrc* srcs, int nsrc, int NB, int H, int W, const vo
  *
  * k2_gn_stats: per (image, group) mean and rstd of the channel-concatenation [src0 | src1]
  *   (src1 may be NULL); stats is fp32 [NB, groups, 2]; scratch is fp32 workspace of
- *   k2_gn_scratch_floats(NB, HW, groups) floats plus one int counter array (see .cu); deterministic.
+ *   k2_gn_scratch_floats(NB, HW, groups) floats that the caller ZEROES once at allocation (its first
+ *   1024 words are self-resetting arrival counters); deterministic.
  * k2_gn_apply: y = act( ((x-mean)*rstd*gamma+beta) * (1+scale[n,c]) + shift[n,c] ), written as fp16
  *   rows of the concatenated tensor, optionally resampled:
  *     resample 0: same size; 1: 2x2 average pool of y (and of raw x into xres); 2: nearest 2x upsample.

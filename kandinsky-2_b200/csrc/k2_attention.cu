@@ -1,0 +1,358 @@
+// k2_attention.cu -- fused softmax(Q K^T) V for head dim 64 on tcgen05 tensor cores (flash-style, no
+// [T, Tkv] score matrix in HBM).
+//
+// Replaces QKVAttention.forward (kandinsky2/model/unet.py:286-340): the two torch.einsum calls (:335,:339),
+// the fp32 softmax (:338), the torch.cat that prepends the encoder K/V (:300-302) and the optional
+// flash-attn path (:303-332).  Keys/values are read from TWO buffers -- encoder tokens first, then the
+// spatial tokens -- so the concat never exists.
+//
+// One CTA = one (batch, head, 128-query tile).  Per 128-key block j:
+//     S_j = Q K_j^T            tcgen05.mma  M128 N128 K64   -> TMEM  (S double-buffered, 2 x 128 columns)
+//     P_j = exp2(S_j*c - m)    4 softmax warps, one query row per thread: tcgen05.ld -> registers ->
+//                              fp16 -> shared memory in the 128B-swizzled K-major layout the MMA reads
+//     O_j = P_j V_j            tcgen05.mma  M128 N64 K128   -> TMEM  (O double-buffered, 2 x 64 columns)
+//     acc = acc*alpha + O_j    in registers (fp32), normalised by the row sum at the end.
+// V tiles are used as an MN-major B operand exactly as TMA lands them ([key][64 d] rows), so V is never
+// transposed.  Warp roles: warp0 TMA producer (Q once, K/V ring of 3 stages), warp1 MMA issuer, warp2 TMEM
+// allocator, warps4-7 softmax/epilogue.  S_{j+1} is issued before P_j is consumed, so the tensor core
+// works on the next scores while the softmax warps exponentiate the current ones.
+#include <string.h>
+
+#include <algorithm>
+
+#include "../../include/k2b200.h"
+#include "k2_common.cuh"
+#include "k2_internal.h"
+
+namespace k2 {
+namespace {
+
+constexpr int BQ = 128;         // queries per CTA
+constexpr int BKV = 128;        // keys per block
+constexpr int HD = 64;          // head dim
+constexpr int TILE_BYTES = 128 * HD * 2;  // 16 KB: one Q / K / V tile
+constexpr int KV_STAGES = 3;
+constexpr int P_BYTES = BQ * BKV * 2;     // 32 KB
+constexpr int SMEM_Q = 0;
+constexpr int SMEM_KV = SMEM_Q + TILE_BYTES;
+constexpr int SMEM_P = SMEM_KV + KV_STAGES * 2 * TILE_BYTES;
+constexpr int SMEM_BAR = SMEM_P + 2 * P_BYTES;
+constexpr int SMEM_TOTAL = SMEM_BAR + 256 + 1024;
+constexpr int TMEM_COLS = 512;  // S: 2 x 128, O: 2 x 64 -> 384, rounded to a power of two
+constexpr int TM_S = 0;
+constexpr int TM_O = 256;
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(256, 1) attention_d64_kernel(const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_BAR);
+  uint64_t* q_full = bars;                 // 1
+  uint64_t* kv_full = bars + 1;            // KV_STAGES
+  uint64_t* kv_empty = kv_full + KV_STAGES;
+  uint64_t* s_full = kv_empty + KV_STAGES; // 2
+  uint64_t* p_full = s_full + 2;           // 2
+  uint64_t* o_full = p_full + 2;           // 2
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + 2);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * BQ;
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int nctx = (p.Tc + BKV - 1) / BKV;
+  const int nsp = (p.T + BKV - 1) / BKV;
+  const int nblk = nctx + nsp;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmQKV);
+    if (p.Tc > 0) tma_prefetch_desc(&p.tmEnc);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < KV_STAGES; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);  // one arrival per softmax warp
+      mbar_init(&o_full[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp_idx == 2) {
+    tmem_alloc(tmem_ptr, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp_idx == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, TILE_BYTES);
+      tma_load_3d(smem + SMEM_Q, &p.tmQKV, q_full, head * p.hs + p.q_off, q0, b);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < nblk; ++j) {
+        mbar_wait(&kv_empty[stage], phase ^ 1);
+        uint8_t* sK = smem + SMEM_KV + stage * 2 * TILE_BYTES;
+        uint8_t* sV = sK + TILE_BYTES;
+        mbar_arrive_expect_tx(&kv_full[stage], 2 * TILE_BYTES);
+        if (j < nctx) {
+          tma_load_3d(sK, &p.tmEnc, &kv_full[stage], head * p.ehs + p.ek_off, j * BKV, b);
+          tma_load_3d(sV, &p.tmEnc, &kv_full[stage], head * p.ehs + p.ev_off, j * BKV, b);
+        } else {
+          const int kv0 = (j - nctx) * BKV;
+          tma_load_3d(sK, &p.tmQKV, &kv_full[stage], head * p.hs + p.k_off, kv0, b);
+          tma_load_3d(sV, &p.tmQKV, &kv_full[stage], head * p.hs + p.v_off, kv0, b);
+        }
+        if (++stage == KV_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================================== MMA issuer ========================================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_f16(BQ, BKV, 0, 0);  // Q (K-major) x K (K-major)
+      constexpr uint32_t idesc_o = make_idesc_f16(BQ, HD, 0, 1);   // P (K-major) x V (MN-major)
+      const uint32_t q_addr = smem_u32(smem + SMEM_Q);
+      auto issue_s = [&](int j, int stage) {
+        const uint32_t k_addr = smem_u32(smem + SMEM_KV + stage * 2 * TILE_BYTES);
+        const uint64_t adesc = make_sw128_desc(q_addr);
+        const uint64_t bdesc = make_sw128_desc(k_addr);
+        const uint32_t d = tmem_base + TM_S + (j & 1) * BKV;
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_f16(d, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc_s, k != 0);
+        umma_commit(&s_full[j & 1]);
+      };
+      mbar_wait(q_full, 0);
+      int stage = 0;        // stage of block j
+      uint32_t phase = 0;   // phase of block j's stage
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      issue_s(0, 0);
+      for (int j = 0; j < nblk; ++j) {
+        int nstage = stage + 1;
+        uint32_t nphase = phase;
+        if (nstage == KV_STAGES) {
+          nstage = 0;
+          nphase ^= 1;
+        }
+        if (j + 1 < nblk) {
+          mbar_wait(&kv_full[nstage], nphase);
+          tc_fence_after();
+          issue_s(j + 1, nstage);
+        }
+        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+        tc_fence_after();
+        {
+          const uint32_t p_addr = smem_u32(smem + SMEM_P + (j & 1) * P_BYTES);
+          const uint32_t v_addr = smem_u32(smem + SMEM_KV + stage * 2 * TILE_BYTES + TILE_BYTES);
+          const uint32_t d = tmem_base + TM_O + (j & 1) * HD;
+#pragma unroll
+          for (int k = 0; k < BKV / 16; ++k) {
+            // A: P row-major [128 q][128 keys] as two 64-key swizzle atoms of 16 KB; 32 B per 16-key step
+            const uint64_t adesc = make_sw128_desc(p_addr + (k >> 2) * TILE_BYTES) + static_cast<uint64_t>((k & 3) * 2);
+            // B: V [128 keys][64 d] (MN-major): 16 keys = 16 rows of 128 B = 2048 B per step
+            const uint64_t bdesc = make_sw128_desc(v_addr + k * 2048);
+            umma_f16(d, adesc, bdesc, idesc_o, k != 0);
+          }
+        }
+        umma_commit(&kv_empty[stage]);
+        umma_commit(&o_full[j & 1]);
+        stage = nstage;
+        phase = nphase;
+      }
+    }
+  } else if (warp_idx >= 4) {
+    // ===================================== softmax + epilogue =================================
+    const int ew = warp_idx - 4;
+    const int row = ew * 32 + lane;  // query row in the tile == TMEM lane
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
+    float acc[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) acc[d] = 0.f;
+    float m_run = -INFINITY;  // running max of the scaled (log2 domain) scores
+    float l_run = 0.f;
+    const float c = p.scale_log2e;
+
+    for (int j = 0; j < nblk; ++j) {
+      const int valid = (j < nctx) ? min(BKV, p.Tc - j * BKV) : min(BKV, p.T - (j - nctx) * BKV);
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t s_addr = lane_addr + TM_S + (j & 1) * BKV;
+      // pass 1: row max
+      float m_blk = -INFINITY;
+#pragma unroll 1
+      for (int ch = 0; ch < BKV / 32; ++ch) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(s_addr + ch * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e)
+          if (ch * 32 + e < valid) m_blk = fmaxf(m_blk, __uint_as_float(r[e]));
+      }
+      const float m_new = fmaxf(m_run, m_blk * c);
+      const float alpha = ex2(m_run - m_new);  // 0 on the first block (m_run = -inf)
+      // pass 2: P = exp2(S*c - m_new) -> fp16 -> swizzled shared memory; row sum
+      uint8_t* p_row = smem + SMEM_P + (j & 1) * P_BYTES + row * 128;
+      float l_blk = 0.f;
+#pragma unroll 1
+      for (int ch = 0; ch < BKV / 32; ++ch) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(s_addr + ch * 32, r);
+        tmem_ld_wait();
+        uint32_t packed[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          float p0 = (ch * 32 + e < valid) ? ex2(fmaf(__uint_as_float(r[e]), c, -m_new)) : 0.f;
+          float p1 = (ch * 32 + e + 1 < valid) ? ex2(fmaf(__uint_as_float(r[e + 1]), c, -m_new)) : 0.f;
+          __half2 h = __floats2half2_rn(p0, p1);
+          // the row sum uses the fp16-rounded probabilities that the PV product actually sees
+          float2 hf = __half22float2(h);
+          l_blk += hf.x + hf.y;
+          packed[e >> 1] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        // 32 keys = 4 chunks of 16 B; key block ch -> atom (ch>>1), chunks (ch&1)*4 .. +3
+        uint8_t* atom = p_row + (ch >> 1) * TILE_BYTES;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int cc = (ch & 1) * 4 + q;
+          *reinterpret_cast<uint4*>(atom + ((cc ^ (row & 7)) << 4)) =
+              make_uint4(packed[q * 4], packed[q * 4 + 1], packed[q * 4 + 2], packed[q * 4 + 3]);
+        }
+      }
+      l_run = l_run * alpha + l_blk;
+      m_run = m_new;
+      // P_j visible to the async proxy, S_j reads retired -> let the MMA warp go
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[j & 1]);
+
+      // fold the PREVIOUS block's O into the accumulator (it was computed against m of block j-1)
+      if (j > 0) {
+        mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);
+        tc_fence_after();
+        const uint32_t o_addr = lane_addr + TM_O + ((j - 1) & 1) * HD;
+#pragma unroll
+        for (int ch = 0; ch < HD / 32; ++ch) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(o_addr + ch * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) acc[ch * 32 + e] += __uint_as_float(r[e]);
+        }
+      }
+#pragma unroll
+      for (int d = 0; d < HD; ++d) acc[d] *= alpha;
+    }
+    // last block
+    {
+      const int j = nblk - 1;
+      mbar_wait(&o_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t o_addr = lane_addr + TM_O + (j & 1) * HD;
+#pragma unroll
+      for (int ch = 0; ch < HD / 32; ++ch) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(o_addr + ch * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) acc[ch * 32 + e] += __uint_as_float(r[e]);
+      }
+    }
+    const int q = q0 + row;
+    if (q < p.T) {
+      const float inv = 1.f / l_run;
+      __half* orow = p.out + (static_cast<long long>(b) * p.T + q) * p.ldo + head * HD;
+#pragma unroll
+      for (int v = 0; v < HD / 8; ++v) {
+        uint4 ov;
+        __half2* oh = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(acc[v * 8 + 2 * e] * inv, acc[v * 8 + 2 * e + 1] * inv);
+        *reinterpret_cast<uint4*>(orow + v * 8) = ov;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+}  // namespace
+
+int launch_attention_d64(const AttnParams& p, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    K2_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    attr_set = true;
+  }
+  dim3 grid((p.T + BQ - 1) / BQ, p.heads, p.B);
+  attention_d64_kernel<<<grid, 256, SMEM_TOTAL, stream>>>(p);
+  K2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace k2
+
+using namespace k2;
+
+extern "C" int k2_attention_d64(const void* qkv, int ldq, int hs, int q_off, int k_off, int v_off, const void* enc,
+                                int lde, int ehs, int ek_off, int ev_off, int B, int heads, int T, int Tc, float scale,
+                                void* out, int ldo, k2_stream_t stream) {
+  K2_REQUIRE(qkv && out && B > 0 && heads > 0 && T > 0, "attention_d64: bad arguments");
+  K2_REQUIRE(ldq % 8 == 0 && ldo % 8 == 0 && hs % 8 == 0 && q_off % 8 == 0 && k_off % 8 == 0 && v_off % 8 == 0,
+             "attention_d64: strides/offsets must be multiples of 8 elements");
+  K2_REQUIRE((enc != nullptr) == (Tc > 0), "attention_d64: enc and Tc go together");
+  K2_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+             "attention_d64: 16-byte alignment");
+  AttnParams p;
+  memset(&p, 0, sizeof p);
+  {
+    const int width = (heads - 1) * hs + std::max(std::max(q_off, k_off), v_off) + 64;
+    K2_REQUIRE(width <= ldq, "attention_d64: qkv row narrower than heads*hs");
+    uint64_t dims[3] = {static_cast<uint64_t>(width), static_cast<uint64_t>(T), static_cast<uint64_t>(B)};
+    uint64_t str[2] = {static_cast<uint64_t>(ldq) * 2, static_cast<uint64_t>(ldq) * 2 * T};
+    uint32_t box[3] = {64, 128, 1};
+    if (encode_tmap_f16(&p.tmQKV, qkv, 3, dims, str, box)) return -1;
+  }
+  if (Tc > 0) {
+    K2_REQUIRE(lde % 8 == 0 && ehs % 8 == 0 && ek_off % 8 == 0 && ev_off % 8 == 0 &&
+                   (reinterpret_cast<uintptr_t>(enc) & 15) == 0,
+               "attention_d64: encoder strides/alignment");
+    const int width = (heads - 1) * ehs + std::max(ek_off, ev_off) + 64;
+    K2_REQUIRE(width <= lde, "attention_d64: encoder row narrower than heads*ehs");
+    uint64_t dims[3] = {static_cast<uint64_t>(width), static_cast<uint64_t>(Tc), static_cast<uint64_t>(B)};
+    uint64_t str[2] = {static_cast<uint64_t>(lde) * 2, static_cast<uint64_t>(lde) * 2 * Tc};
+    uint32_t box[3] = {64, 128, 1};
+    if (encode_tmap_f16(&p.tmEnc, enc, 3, dims, str, box)) return -1;
+  }
+  p.B = B; p.heads = heads; p.T = T; p.Tc = Tc;
+  p.hs = hs; p.q_off = q_off; p.k_off = k_off; p.v_off = v_off;
+  p.ehs = ehs; p.ek_off = ek_off; p.ev_off = ev_off;
+  p.out = reinterpret_cast<__half*>(out);
+  p.ldo = ldo;
+  p.scale_log2e = scale * 1.4426950408889634f;
+  int rc = launch_attention_d64(p, static_cast<cudaStream_t>(stream));
+  if (rc == 0) count_launch();
+  return rc;
+}

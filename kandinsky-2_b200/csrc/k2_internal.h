@@ -55,13 +55,12 @@ int launch_conv_gemm(const ConvGemmParams& p, int BN, cudaStream_t stream);
 
 // ---- fused attention, head dim 64 (k2_attention.cu) ---------------------------------------------
 struct AttnParams {
-  CUtensorMap tmQKV;   // 3-D (3C, T, B) over the qkv buffer, box (64, 128|64, 1)
-  CUtensorMap tmKV;    // same buffer, box (64, 64, 1) for K/V blocks
-  CUtensorMap tmEnc;   // 3-D (2C, Tc, B) over encoder kv, box (64, 64, 1)
+  CUtensorMap tmQKV;   // 3-D (channels, T, B) over the qkv rows, box (64, 128, 1)
+  CUtensorMap tmEnc;   // 3-D (channels, Tc, B) over the encoder kv rows, box (64, 128, 1)
   int B, heads, T, Tc;
-  int q_stride_h, k_off, v_off;      // channel offsets inside one head's slab of the qkv row
-  int enc_stride_h, enc_k_off, enc_v_off;
-  __half* out;         // [B, T, heads*64]
+  int hs, q_off, k_off, v_off;       // head h owns channels [h*hs, (h+1)*hs); q/k/v at these offsets
+  int ehs, ek_off, ev_off;           // same for the encoder kv rows
+  __half* out;         // [B, T, ldo], channel h*64+d
   int ldo;
   float scale_log2e;   // softmax scale * log2(e)
 };

@@ -306,12 +306,13 @@ using namespace k2;
 extern "C" {
 
 long long k2_gn_scratch_floats(int NB, int HW, int groups) {
-  // partials for the worst-case chunk count + one counter per image (+ padding)
+  // [0, 1024): one arrival counter per image (fixed location: they must stay zero between launches
+  // whatever geometry the previous launch had); then the partials for the worst-case chunk count
   int maxc = (HW + 63) / 64;
   long long c = 4LL * 160;
   if (c > maxc) c = maxc;
   if (c < 1) c = 1;
-  return static_cast<long long>(NB) * c * groups * 2 + NB + 64;
+  return 1024 + static_cast<long long>(NB) * c * groups * 2;
 }
 
 int k2_gn_stats(const void* src0, int C0, int ld0, const void* src1, int C1, int ld1, int NB, int HW, int groups,
@@ -322,12 +323,11 @@ int k2_gn_stats(const void* src0, int C0, int ld0, const void* src1, int C1, int
   K2_REQUIRE(groups <= 256, "gn_stats: at most 256 groups");
   K2_REQUIRE(src1 || C1 == 0, "gn_stats: src1 null with C1 > 0");
   const int chunks = stats_chunks(NB, HW);
-  float* partial = scratch;
+  K2_REQUIRE(NB <= 1024, "gn_stats: at most 1024 images per launch");
+  float* partial = scratch + 1024;
   long long partial_floats = static_cast<long long>(NB) * chunks * groups * 2;
-  K2_REQUIRE(partial_floats + NB <= k2_gn_scratch_floats(NB, HW, groups), "gn_stats: scratch too small");
-  // counters live after the worst-case partial area
-  unsigned int* counters =
-      reinterpret_cast<unsigned int*>(scratch + (k2_gn_scratch_floats(NB, HW, groups) - NB - 64) + 32);
+  K2_REQUIRE(1024 + partial_floats <= k2_gn_scratch_floats(NB, HW, groups), "gn_stats: scratch too small");
+  unsigned int* counters = reinterpret_cast<unsigned int*>(scratch);  // zero-initialised by the caller, self-resetting
   dim3 grid(chunks, NB);
   size_t smem = (ST_PY * ST_VX * 16 + ST_VX * 8 * 2 + groups * 2) * sizeof(float);
   gn_stats_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(

@@ -140,7 +140,7 @@ def gn_stats(x0, x1=None, groups=32, eps=1e-5, stats=None):
 
 
 def gn_apply(x0, x1, stats, gamma, beta, film=None, act=1, resample=0, groups=32, y=None, want_xres=False,
-             zq=None, sn_w=None):
+             zq=None, sn_w=None, xres=None):
     """Fused normalise (+FiLM) (+SiLU) (+2x up / 2x2 avg-pool) (+concat) -> fp16 NHWC. See k2b200.h."""
     lib = nat.load()
     NB, H, W, C0 = x0.shape
@@ -149,8 +149,9 @@ def gn_apply(x0, x1, stats, gamma, beta, film=None, act=1, resample=0, groups=32
     Ho, Wo = (H, W) if resample == 0 else ((H // 2, W // 2) if resample == 1 else (H * 2, W * 2))
     if y is None:
         y = torch.empty((NB, Ho, Wo, C), dtype=torch.float16, device=x0.device)
-    xres = None
-    if want_xres:
+    if xres is not None:
+        want_xres = True
+    elif want_xres:
         xres = torch.empty((NB, Ho, Wo, C), dtype=torch.float16, device=x0.device)
     zh = zw = 0
     if zq is not None:
