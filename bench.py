@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json metric: UNet denoising steps/sec @ 768x768, 4 images (UNet batch 8 under CFG),
+Kandinsky-2.2 decoder configuration (1.22 B-parameter UNet, 32 context tokens, guidance 4, DDPM learned-range).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+One "step" = one classifier-free-guidance-doubled UNet forward + guidance combine + scheduler update for the
+batch.  Own arm: the C-ABI kernels of libk2b200.so replayed as a CUDA graph; one process per
+GPU, each rank denoises its own 4 images (weak scaling, the only collective is one NCCL broadcast of the
+conditioning embeddings before step 0).  `value` times K steps with the latents resident in HBM; `e2e` times
+the same K steps through the module boundary with the latents coming from / returning to pinned host memory
+every step.  `--impl reference` times the reference algorithm's CPU path (the oracle port of the reference
+modules -- /root/reference itself is Python and absent on the GPU box) on the host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "kandinsky-2_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+METRIC = "unet_denoising_steps_per_sec"
+UNIT = "steps/s"
+UNET_CFG = dict(model_dim=768, image_encoder_in_dim=1280, text_encoder_in_dim1=1024, text_encoder_in_dim2=768,
+                num_image_embs=32, pooling_type="from_model", in_channels=4, model_channels=384, out_channels=8,
+                num_res_blocks=3, attention_resolutions=(2, 4, 8), channel_mult=(1, 2, 3, 4), use_fp16=True,
+                num_heads=1, num_head_channels=64, use_scale_shift_norm=True, resblock_updown=True,
+                cond_version="2.2")
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return dict(tflops_burst=d.get("bf16_tflops"), tflops_sustained=d.get("bf16_tflops_sustained"),
+                    hbm_gbs=d.get("hbm_gbs"), source="MEASURED_PEAKS.json")
+    return dict(tflops_burst=1590.0, tflops_sustained=1400.0, hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.f = None
+
+    def start(self):
+        try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if not sm:
+            return None
+        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), samples=len(sm), reasons=sorted(reasons))
+
+
+def dist_setup(n_gpus):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return world, rank, local
+
+
+def cpu_oracle_sample(images, lat_h, lat_w, threads, reps=1, warm=0, budget_s=200.0):
+    """Times the oracle (torch fp32 restatement of the reference modules) on the host: one CFG-doubled UNet
+    forward of `images` of the 4 images at full model size.  Returns seconds per forward (list)."""
+    from oracle import unet_oracle as uo
+    torch.set_num_threads(threads)
+    cfg = uo.CONFIG_2_2
+    g = torch.Generator().manual_seed(0)
+    sd = {}
+    for k, shape in uo.unet_param_spec(cfg):  # cheap init: values do not change the arithmetic cost
+        t = torch.empty(shape)
+        if len(shape) == 1:
+            t.fill_(1.0 if k.endswith("weight") else 0.0)
+        else:
+            fan = 1
+            for d in shape[1:]:
+                fan *= d
+            t.uniform_(-1.0, 1.0, generator=g).mul_((3.0 / fan) ** 0.5)
+        sd[k] = t
+    N = 2 * images
+    x = torch.randn(N, 4, lat_h, lat_w, generator=g)
+    t = torch.full((N,), 980.0)
+    img = torch.randn(N, cfg["image_encoder_in_dim"], generator=g)
+    times = []
+    t_begin = time.perf_counter()
+    with torch.no_grad():
+        for i in range(warm + reps):
+            t0 = time.perf_counter()
+            uo.unet_forward(sd, cfg, x, t, image_emb=img)
+            dt = time.perf_counter() - t0
+            if i >= warm:
+                times.append(dt)
+            if times and time.perf_counter() - t_begin > budget_s:
+                break  # keep the whole run within a few minutes (reported as steps_timed)
+    return times
+
+
+def run_reference(args):
+    """Reference arm: the reference algorithm's CPU implementation on this box's host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = int(os.environ.get('K2_CPU_THREADS', 0)) or min(os.cpu_count() or 1, 32)
+    lat_h, lat_w = args.height // 8, args.width // 8
+    # bounded sample: 1 of the 4 images (UNet batch 2 of 8) per step; a full step is 4 such forwards
+    times = cpu_oracle_sample(1, lat_h, lat_w, threads, reps=args.steps, warm=args.warmup)
+    per_fwd = sum(times) / len(times)
+    ms_per_step = per_fwd * args.batch * 1e3
+    value = 1e3 / ms_per_step
+    sample = (f"each timed step = one CFG-doubled fp32 forward of 1 of the {args.batch} images (UNet batch 2 of "
+              f"{2 * args.batch}) at {lat_h}x{lat_w}, full 1.22B model, oracle port of the reference modules; "
+              f"step time scaled x{args.batch}")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "steps_timed": len(times)}))
+
+
+def workload_config(args, world):
+    return {"workload": f"Kandinsky-2.2 text2img {args.height}x{args.width}, batch {args.batch} per GPU, 50-step "
+                        f"DDPM schedule, CFG 4 (BASELINE configs[1])",
+            "latent": [args.height // 8, args.width // 8], "images_per_gpu": args.batch,
+            "unet_batch_per_gpu": 2 * args.batch, "global_images": args.batch * world, "context_tokens": 32,
+            "unet_params": 1228661768 + 0, "parallelism": f"dp{world} (replicas, one conditioning broadcast)",
+            "l2": "per-step working set (2.5 GB weights + activations) exceeds the 126 MB L2; no explicit flush"}
+
+
+def run_k2(args):
+    from kandinsky2 import ops
+    from kandinsky2.model.gaussian_diffusion import FusedStep, create_ddpm_v22
+    from kandinsky2.model.unet import Text2ImUNet
+    world, rank, local = dist_setup(args.gpus)
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    B, H, W = args.batch, args.height // 8, args.width // 8
+
+    model = Text2ImUNet(**UNET_CFG, device=dev, param_dtype=torch.float16)
+    model.init_synthetic_(seed=0)
+    model.finalize(release_params=True)
+
+    # conditioning: rank 0 draws the image embeddings for the whole job, ONE broadcast, each rank keeps its rows
+    emb = torch.empty(world, 2 * B, 1280, device=dev)
+    if rank == 0:
+        emb.copy_(torch.randn(world, 2 * B, 1280, generator=torch.Generator().manual_seed(1234)).to(dev))
+    if world > 1:
+        import torch.distributed as dist
+        dist.broadcast(emb, src=0)
+    image_emb = emb[rank].contiguous()
+
+    diffusion = create_ddpm_v22(50)
+    coef, ts = diffusion._tables(dev)
+    step = FusedStep(model, B, H, W, dict(image_emb=image_emb), guidance_scale=4.0, cond_first=False,
+                     clip_range=2.0, threshold_mode=0)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x = torch.randn(B, 4, H, W, device=dev, generator=g)
+    order = list(range(diffusion.num_timesteps))[::-1]
+
+    def one_step(n):
+        i = order[n % len(order)]
+        step.noise.normal_(generator=g)
+        step.run(x, ts[i], coef[i])
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for n in range(k):
+            fn(n)
+        e.record()
+        barrier()
+        ms = torch.tensor([s.elapsed_time(e)], device=dev)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    # kernels per step, counted by the library during one eager (un-graphed) step
+    model.use_cuda_graph = False
+    ops.reset_launch_count()
+    one_step(0)
+    torch.cuda.synchronize()
+    launches_per_step = int(ops.launch_count())
+    model.use_cuda_graph = True
+    x.copy_(torch.randn(B, 4, H, W, device=dev, generator=g))
+
+    for n in range(max(args.warmup, 3)):
+        one_step(n)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms = timed(one_step, args.steps)
+    clocks = sampler.stop()
+    ms_per_step = ms / args.steps
+    value = world * 1e3 / ms_per_step
+
+    # e2e: same steps through the module boundary with HOST latents (pinned), H2D + D2H every step
+    x_host = torch.randn(B, 4, H, W).pin_memory()
+    out_host = torch.empty(B, 4, H, W).pin_memory()
+
+    def e2e_step(n):
+        x.copy_(x_host, non_blocking=True)
+        one_step(n)
+        out_host.copy_(x, non_blocking=True)
+
+    for n in range(3):
+        e2e_step(n)
+    e2e_ms = timed(e2e_step, args.steps) / args.steps
+    nbytes = x_host.numel() * 4
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f16", "data": "synthetic (random-init 1.22B UNet, N(0,1) latents/embeddings)",
+        "config": workload_config(args, world),
+        "e2e": {"value": world * 1e3 / e2e_ms, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+                "ms_per_step": e2e_ms},
+        "gpu_launches": launches_per_step * args.steps,
+        "clocks": clocks,
+    }
+
+    if rank == 0 and not args.no_profile:
+        peaks = measured_peaks()
+        if args.detail:
+            det = step.plan.profile_detail(reps=3)
+            with open(args.detail, "w") as f:
+                json.dump([dict(i=i, kind=k, gflop=fl / 1e9, us=ms * 1e3, tflops=(fl / (ms * 1e-3) / 1e12 if ms > 0 else 0))
+                           for i, (k, fl, ms) in enumerate(det)], f)
+        prof = step.plan.profile(reps=2)
+        total_ms = sum(v["ms"] for v in prof.values())
+        conv = prof["conv_gemm"]
+        achieved = conv["flops"] / (conv["ms"] * 1e-3) / 1e12
+        peak = peaks["tflops_sustained"] or peaks["tflops_burst"]
+        from oracle import unet_oracle as uo  # FLOP accounting of the reference graph only (checker-side helper)
+        step_flops = uo.algorithmic_flops(uo.CONFIG_2_2, 2 * B, H, W, 32)
+        line["roofline"] = {
+            "bound": "tensor", "kernel": "conv_gemm_kernel (3x3 / 1x1 / Conv1d implicit GEMM, tcgen05)",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step); burst "
+                           f"{peaks['tflops_burst']}",
+            "launches_per_step": conv["launches"], "kernel_ms_per_step": conv["ms"],
+            "share_of_step": conv["ms"] / total_ms,
+            "step_algorithmic_tflop": step_flops / 1e12,
+            "step_tflops_achieved": step_flops / (ms_per_step * 1e-3) / 1e12,
+            "step_frac_of_peak": step_flops / (ms_per_step * 1e-3) / 1e12 / peak,
+            "per_kind_ms": {k: round(v["ms"], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
+            "attention_tflops": prof["attention"]["flops"] / (prof["attention"]["ms"] * 1e-3) / 1e12,
+        }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = int(os.environ.get('K2_CPU_THREADS', 0)) or min(os.cpu_count() or 1, 32)
+        t = cpu_oracle_sample(1, H, W, threads, reps=1, warm=0)[0]
+        v = 1.0 / (t * B)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"one CFG-doubled fp32 oracle forward of 1 of the {B} images at {H}x{W} "
+                                          f"({t:.1f} s), step time scaled x{B}"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="k2", choices=["k2", "reference"])
+    ap.add_argument("--batch", type=int, default=4)
+    ap.add_argument("--height", type=int, default=768)
+    ap.add_argument("--width", type=int, default=768)
+    ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--detail", default=None, help="write per-launch timings of one eager step to this JSON file")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_k2(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -69,7 +69,7 @@ int k2_conv_gemm(const K2ConvSrc* srcs, int nsrc, int NB, int H, int W, const vo
  *
  * k2_gn_stats: per (image, group) mean and rstd of the channel-concatenation [src0 | src1]
  *   (src1 may be NULL); stats is fp32 [NB, groups, 2]; scratch is fp32 workspace of
- *   k2_gn_scratch_floats(NB, HW, groups) floats that the caller ZEROES once at allocation (its first
+ *   k2_gn_scratch_floats(NB, HW, C0+C1) floats that the caller ZEROES once at allocation (its first
  *   1024 words are self-resetting arrival counters); deterministic.
  * k2_gn_apply: y = act( ((x-mean)*rstd*gamma+beta) * (1+scale[n,c]) + shift[n,c] ), written as fp16
  *   rows of the concatenated tensor, optionally resampled:
@@ -78,7 +78,7 @@ int k2_conv_gemm(const K2ConvSrc* srcs, int nsrc, int NB, int H, int W, const vo
  *   spatial (MoVQ): if zq != NULL, y = GN(x) * (Wy.zq + by) + (Wb.zq + bb) with zq fp32 NHWC
  *   [NB, zh, zw, 4] nearest-resized to (H, W); sn_w is fp32 [C, 10] = (Wy[4], by, Wb[4], bb).
  * ------------------------------------------------------------------------------------------- */
-long long k2_gn_scratch_floats(int NB, int HW, int groups);
+long long k2_gn_scratch_floats(int NB, int HW, int C);
 int k2_gn_stats(const void* src0, int C0, int ld0, const void* src1, int C1, int ld1, int NB, int HW,
                 int groups, float eps, float* stats, float* scratch, k2_stream_t stream);
 int k2_gn_apply(const void* src0, int C0, int ld0, const void* src1, int C1, int ld1, int NB, int H, int W,

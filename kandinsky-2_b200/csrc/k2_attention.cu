@@ -187,46 +187,72 @@ __global__ void __launch_bounds__(256, 1) attention_d64_kernel(const __grid_cons
     for (int d = 0; d < HD; ++d) acc[d] = 0.f;
     float m_run = -INFINITY;  // running max of the scaled (log2 domain) scores
     float l_run = 0.f;
+    float alpha_prev = 0.f;   // rescale factor that moves acc from the max of block j-2 to that of block j-1
     const float c = p.scale_log2e;
+
+    // acc = acc * alpha + O_blk  (O_blk was computed against the running max that alpha moves acc to)
+    auto fold_o = [&](int jb, float alpha) {
+      mbar_wait(&o_full[jb & 1], (jb >> 1) & 1);
+      tc_fence_after();
+      const uint32_t o_addr = lane_addr + TM_O + (jb & 1) * HD;
+      uint32_t r0[32], r1[32];
+      tmem_ld_32x32b_x32(o_addr, r0);
+      tmem_ld_32x32b_x32(o_addr + 32, r1);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        acc[e] = fmaf(acc[e], alpha, __uint_as_float(r0[e]));
+        acc[32 + e] = fmaf(acc[32 + e], alpha, __uint_as_float(r1[e]));
+      }
+    };
 
     for (int j = 0; j < nblk; ++j) {
       const int valid = (j < nctx) ? min(BKV, p.Tc - j * BKV) : min(BKV, p.T - (j - nctx) * BKV);
       mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
       const uint32_t s_addr = lane_addr + TM_S + (j & 1) * BKV;
-      // pass 1: row max
-      float m_blk = -INFINITY;
-#pragma unroll 1
-      for (int ch = 0; ch < BKV / 32; ++ch) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(s_addr + ch * 32, r);
-        tmem_ld_wait();
+      // the whole score row of this thread: 4 TMEM loads in flight, one wait
+      uint32_t s0[32], s1[32], s2[32], s3[32];
+      tmem_ld_32x32b_x32(s_addr, s0);
+      tmem_ld_32x32b_x32(s_addr + 32, s1);
+      tmem_ld_32x32b_x32(s_addr + 64, s2);
+      tmem_ld_32x32b_x32(s_addr + 96, s3);
+      tmem_ld_wait();
+      if (valid < BKV) {  // ragged tail / short encoder block (block-uniform branch): masked scores -> -inf
+        const uint32_t ninf = __float_as_uint(-INFINITY);
 #pragma unroll
-        for (int e = 0; e < 32; ++e)
-          if (ch * 32 + e < valid) m_blk = fmaxf(m_blk, __uint_as_float(r[e]));
+        for (int e = 0; e < 32; ++e) {
+          if (e >= valid) s0[e] = ninf;
+          if (32 + e >= valid) s1[e] = ninf;
+          if (64 + e >= valid) s2[e] = ninf;
+          if (96 + e >= valid) s3[e] = ninf;
+        }
       }
-      const float m_new = fmaxf(m_run, m_blk * c);
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        mx0 = fmaxf(mx0, __uint_as_float(s0[e]));
+        mx1 = fmaxf(mx1, __uint_as_float(s1[e]));
+        mx2 = fmaxf(mx2, __uint_as_float(s2[e]));
+        mx3 = fmaxf(mx3, __uint_as_float(s3[e]));
+      }
+      const float m_new = fmaxf(m_run, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * c);
       const float alpha = ex2(m_run - m_new);  // 0 on the first block (m_run = -inf)
-      // pass 2: P = exp2(S*c - m_new) -> fp16 -> swizzled shared memory; row sum
+      // P = exp2(S*c - m_new) -> fp16 -> swizzled shared memory (K-major A operand of the PV product)
       uint8_t* p_row = smem + SMEM_P + (j & 1) * P_BYTES + row * 128;
-      float l_blk = 0.f;
-#pragma unroll 1
-      for (int ch = 0; ch < BKV / 32; ++ch) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(s_addr + ch * 32, r);
-        tmem_ld_wait();
+      float l0 = 0.f, l1 = 0.f;
+      auto emit = [&](const uint32_t (&sv)[32], int ch) {
         uint32_t packed[16];
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
-          float p0 = (ch * 32 + e < valid) ? ex2(fmaf(__uint_as_float(r[e]), c, -m_new)) : 0.f;
-          float p1 = (ch * 32 + e + 1 < valid) ? ex2(fmaf(__uint_as_float(r[e + 1]), c, -m_new)) : 0.f;
+          const float p0 = ex2(fmaf(__uint_as_float(sv[e]), c, -m_new));
+          const float p1 = ex2(fmaf(__uint_as_float(sv[e + 1]), c, -m_new));
+          l0 += p0;
+          l1 += p1;
           __half2 h = __floats2half2_rn(p0, p1);
-          // the row sum uses the fp16-rounded probabilities that the PV product actually sees
-          float2 hf = __half22float2(h);
-          l_blk += hf.x + hf.y;
           packed[e >> 1] = *reinterpret_cast<uint32_t*>(&h);
         }
-        // 32 keys = 4 chunks of 16 B; key block ch -> atom (ch>>1), chunks (ch&1)*4 .. +3
+        // 32 keys = 4 chunks of 16 B; key group ch -> swizzle atom (ch>>1), chunks (ch&1)*4 .. +3
         uint8_t* atom = p_row + (ch >> 1) * TILE_BYTES;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -234,8 +260,12 @@ __global__ void __launch_bounds__(256, 1) attention_d64_kernel(const __grid_cons
           *reinterpret_cast<uint4*>(atom + ((cc ^ (row & 7)) << 4)) =
               make_uint4(packed[q * 4], packed[q * 4 + 1], packed[q * 4 + 2], packed[q * 4 + 3]);
         }
-      }
-      l_run = l_run * alpha + l_blk;
+      };
+      emit(s0, 0);
+      emit(s1, 1);
+      emit(s2, 2);
+      emit(s3, 3);
+      l_run = fmaf(l_run, alpha, l0 + l1);
       m_run = m_new;
       // P_j visible to the async proxy, S_j reads retired -> let the MMA warp go
       fence_proxy_async_smem();
@@ -243,38 +273,10 @@ __global__ void __launch_bounds__(256, 1) attention_d64_kernel(const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[j & 1]);
 
-      // fold the PREVIOUS block's O into the accumulator (it was computed against m of block j-1)
-      if (j > 0) {
-        mbar_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);
-        tc_fence_after();
-        const uint32_t o_addr = lane_addr + TM_O + ((j - 1) & 1) * HD;
-#pragma unroll
-        for (int ch = 0; ch < HD / 32; ++ch) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(o_addr + ch * 32, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < 32; ++e) acc[ch * 32 + e] += __uint_as_float(r[e]);
-        }
-      }
-#pragma unroll
-      for (int d = 0; d < HD; ++d) acc[d] *= alpha;
+      if (j > 0) fold_o(j - 1, alpha_prev);  // overlaps with the tensor core working on P_j V_j
+      alpha_prev = alpha;
     }
-    // last block
-    {
-      const int j = nblk - 1;
-      mbar_wait(&o_full[j & 1], (j >> 1) & 1);
-      tc_fence_after();
-      const uint32_t o_addr = lane_addr + TM_O + (j & 1) * HD;
-#pragma unroll
-      for (int ch = 0; ch < HD / 32; ++ch) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(o_addr + ch * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 32; ++e) acc[ch * 32 + e] += __uint_as_float(r[e]);
-      }
-    }
+    fold_o(nblk - 1, alpha_prev);
     const int q = q0 + row;
     if (q < p.T) {
       const float inv = 1.f / l_run;

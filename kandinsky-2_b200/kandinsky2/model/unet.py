@@ -151,6 +151,24 @@ class Text2ImUNet(nn.Module):
             P("add_embedding.image_proj.weight", temb, image_encoder_in_dim); P("add_embedding.image_proj.bias", temb)
             P("add_embedding.image_norm.weight", temb); P("add_embedding.image_norm.bias", temb)
 
+    @torch.no_grad()
+    def init_synthetic_(self, seed=0):
+        """Random weights of this architecture, drawn on the parameters' own device (benchmarks: there are no
+        checkpoints offline).  Fan-in scaled so activations stay O(1); the reference's zero_module() tensors are
+        filled too (a zero-initialised UNet outputs exact zeros, nn.py:73-79)."""
+        dev = self._param("time_embed.0.weight").device
+        g = torch.Generator(device=dev).manual_seed(seed)
+        for name, prm in self.named_parameters():
+            if name.endswith("bias"):
+                prm.normal_(0.0, 0.05, generator=g)
+            elif prm.dim() == 1:
+                prm.normal_(0.0, 0.1, generator=g).add_(1.0)
+            else:
+                fan_in = prm[0].numel()
+                prm.normal_(0.0, fan_in ** -0.5, generator=g)
+        self._invalidate()
+        return self
+
     # ---------------------------------------------------------------- reference surface
     def convert_to_fp16(self):
         """Reference: casts the conv torso to fp16 (fp16_util.py:9-16). Here activations and conv weights are
@@ -381,7 +399,7 @@ class _Plan:
     # program -----------------------------------------------------------------------------------
     def _build(self):
         m, pk, N = self.m, self.m._packed, self.N
-        S = self.steps.append
+        S = self._add
         mc = m.model_channels
         temb = 4 * mc
         f32 = dict(device=self.dev, dtype=torch.float32)
@@ -389,10 +407,10 @@ class _Plan:
         e1 = torch.empty(N, temb, **f32)
         emb = torch.empty(N, temb, **f32)
         film = torch.empty(N, pk["film_total"], **f32)
-        S(lambda: ops.timestep_embedding(self.t_in, mc, out=e0))
-        S(lambda: ops.linear(e0, pk["te0_w"], pk["te0_b"], silu_out=True, out=e1))
-        S(lambda: ops.linear(e1, pk["te2_w"], pk["te2_b"], add=self.xf_proj, out=emb))
-        S(lambda: ops.linear(emb, pk["film_w"], pk["film_b"], silu_in=True, out=film))
+        S(lambda: ops.timestep_embedding(self.t_in, mc, out=e0), "timestep_embedding")
+        S(lambda: ops.linear(e0, pk["te0_w"], pk["te0_b"], silu_out=True, out=e1), "linear")
+        S(lambda: ops.linear(e1, pk["te2_w"], pk["te2_b"], add=self.xf_proj, out=emb), "linear")
+        S(lambda: ops.linear(emb, pk["film_w"], pk["film_b"], silu_in=True, out=film), "linear")
         self.film = film
 
         H, W = self.H, self.W
@@ -403,10 +421,11 @@ class _Plan:
         patches = self._new(N, H, W, kpad)
         h = self._new(N, H, W, inp[0][0][2])
         if m._inpainting:
-            S(lambda: ops.stem_im2col(self.x_in, self.img_in, self.mask_in, mul23=True, kpad=kpad, out=patches))
+            S(lambda: ops.stem_im2col(self.x_in, self.img_in, self.mask_in, mul23=True, kpad=kpad, out=patches), "stem_im2col")
         else:
-            S(lambda: ops.stem_im2col(self.x_in, kpad=kpad, out=patches))
-        S(lambda h=h: ops.gemm_rows(patches, pk["stem_w"], h.shape[-1], bias=pk["stem_b"], out=h))
+            S(lambda: ops.stem_im2col(self.x_in, kpad=kpad, out=patches), "stem_im2col")
+        S(lambda h=h: ops.gemm_rows(patches, pk["stem_w"], h.shape[-1], bias=pk["stem_b"], out=h), "conv_gemm",
+          2 * N * H * W * h.shape[-1] * 9 * cin)
         hs = [h]
         for bi, blk in enumerate(inp[1:], start=1):
             for li, layer in enumerate(blk):
@@ -421,12 +440,13 @@ class _Plan:
         # head: GN32 + SiLU + conv3x3 -> fp32 NCHW (unet.py:559-563; text2im_model2_1.py:101-102)
         st = self._new(N, 32, 2, dtype=torch.float32)
         hn = self._tmp("h1", *h.shape)
-        S(lambda h=h: ops.gn_stats(h, None, stats=st))
-        S(lambda h=h: ops.gn_apply(h, None, st, pk["out_g"], pk["out_b"], act=1, y=hn))
-        S(lambda: ops.conv_gemm([(hn, 9)], pk["out_w"], m.out_channels, bias=pk["out_c"], out=self.out, out_mode=1))
+        S(lambda h=h: ops.gn_stats(h, None, stats=st), "gn_stats")
+        S(lambda h=h: ops.gn_apply(h, None, st, pk["out_g"], pk["out_b"], act=1, y=hn), "gn_apply")
+        S(lambda: ops.conv_gemm([(hn, 9)], pk["out_w"], m.out_channels, bias=pk["out_c"], out=self.out, out_mode=1),
+          "conv_gemm", 2 * N * H * W * m.out_channels * 9 * h.shape[-1])
 
     def _layer(self, p, layer, a, b):
-        pk, N, S = self.m._packed, self.N, self.steps.append
+        pk, N, S = self.m._packed, self.N, self._add
         if layer[0] == "res":
             _, cin, cout, updown = layer
             d = pk["res"][p]
@@ -439,22 +459,23 @@ class _Plan:
             h3 = self._tmp("h3", N, Ho, Wo, cout)
             o = self._new(N, Ho, Wo, cout)
             film = self.film[:, d["film_off"]:d["film_off"] + 2 * cout]
-            S(lambda: ops.gn_stats(a, b, stats=st1))
+            S(lambda: ops.gn_stats(a, b, stats=st1), "gn_stats")
             if updown is None:
                 xres = None
-                S(lambda: ops.gn_apply(a, b, st1, d["g1"], d["b1"], act=1, y=h1))
+                S(lambda: ops.gn_apply(a, b, st1, d["g1"], d["b1"], act=1, y=h1), "gn_apply")
             else:
                 xres = self._tmp("xres", N, Ho, Wo, cin)
                 S(lambda: ops.gn_apply(a, b, st1, d["g1"], d["b1"], act=1, resample=1 if updown == "down" else 2,
                                             y=h1, xres=xres))
-            S(lambda: ops.conv_gemm([(h1, 9)], d["w1"], cout, bias=d["c1"], out=h2))
-            S(lambda: ops.gn_stats(h2, None, stats=st2))
-            S(lambda: ops.gn_apply(h2, None, st2, d["g2"], d["b2"], film=film, act=1, y=h3))
+            S(lambda: ops.conv_gemm([(h1, 9)], d["w1"], cout, bias=d["c1"], out=h2), "conv_gemm", 2 * N * Ho * Wo * cout * 9 * cin)
+            S(lambda: ops.gn_stats(h2, None, stats=st2), "gn_stats")
+            S(lambda: ops.gn_apply(h2, None, st2, d["g2"], d["b2"], film=film, act=1, y=h3), "gn_apply")
             if cin == cout:
                 if b is not None:
                     raise NotImplementedError("identity skip over a concatenated input")
                 res = xres if xres is not None else a
-                S(lambda: ops.conv_gemm([(h3, 9)], d["w2"], cout, bias=d["c2"], residual=res, out=o))
+                S(lambda: ops.conv_gemm([(h3, 9)], d["w2"], cout, bias=d["c2"], residual=res, out=o), "conv_gemm",
+                  2 * N * Ho * Wo * cout * 9 * cout)
             else:
                 if updown is not None:
                     raise NotImplementedError("resampling ResBlock with a channel change")
@@ -462,7 +483,8 @@ class _Plan:
                 c1 = b.shape[-1] if b is not None else 0
                 wcat = self.m._skip_weight(d, c0, c1)
                 srcs = [(h3, 9), (a, 1)] + ([(b, 1)] if b is not None else [])
-                S(lambda: ops.conv_gemm(srcs, wcat, cout, bias=d["c2"], out=o))
+                S(lambda: ops.conv_gemm(srcs, wcat, cout, bias=d["c2"], out=o), "conv_gemm",
+                  2 * N * Ho * Wo * cout * (9 * cout + cin))
             return o
         # attention
         ch = layer[1]
@@ -478,17 +500,64 @@ class _Plan:
         ctx = self.m.cache["xf_out"].shape[1]
         enc = self._new(N, ctx, 2 * ch)
         self.enc_kv[p] = enc
-        S(lambda: ops.gn_stats(a, None, stats=st))
-        S(lambda: ops.gn_apply(a, None, st, d["g"], d["b"], act=0, y=xn))
-        S(lambda: ops.gemm_rows(xn.view(N, T, ch), d["wqkv"], 3 * ch, bias=d["bqkv"], out=qkv))
-        S(lambda: ops.attention_d64(qkv, heads, enc, out=att))
-        S(lambda: ops.gemm_rows(att, d["wproj"], ch, bias=d["bproj"], residual=a.view(N, T, ch), out=o.view(N, T, ch)))
+        S(lambda: ops.gn_stats(a, None, stats=st), "gn_stats")
+        S(lambda: ops.gn_apply(a, None, st, d["g"], d["b"], act=0, y=xn), "gn_apply")
+        S(lambda: ops.gemm_rows(xn.view(N, T, ch), d["wqkv"], 3 * ch, bias=d["bqkv"], out=qkv), "conv_gemm", 2 * N * T * 3 * ch * ch)
+        S(lambda: ops.attention_d64(qkv, heads, enc, out=att), "attention", 4 * N * T * (T + ctx) * ch)
+        S(lambda: ops.gemm_rows(att, d["wproj"], ch, bias=d["bproj"], residual=a.view(N, T, ch), out=o.view(N, T, ch)),
+          "conv_gemm", 2 * N * T * ch * ch)
         return o
+
+    def _add(self, fn, kind="misc", flops=0):
+        self.steps.append((fn, kind, flops))
 
     # execution ---------------------------------------------------------------------------------
     def launch(self):
-        for fn in self.steps:
+        for fn, _, _ in self.steps:
             fn()
+
+    def profile_detail(self, reps=3):
+        """[(kind, flops, ms)] per launch, averaged over `reps` eager passes (same method as profile())."""
+        acc = [0.0] * len(self.steps)
+        for _ in range(reps):
+            evs = []
+            torch.cuda.synchronize()
+            torch.cuda._sleep(int(4e7))
+            for fn, kind, flops in self.steps:
+                s = torch.cuda.Event(enable_timing=True)
+                e = torch.cuda.Event(enable_timing=True)
+                s.record()
+                fn()
+                e.record()
+                evs.append((s, e))
+            torch.cuda.synchronize()
+            for i, (s, e) in enumerate(evs):
+                acc[i] += s.elapsed_time(e) / reps
+        return [(k, f, ms) for (_, k, f), ms in zip(self.steps, acc)]
+
+    def profile(self, reps=3):
+        """Per-kernel-family device time of one eager pass (CUDA events around every launch; a long sleep kernel
+        is queued first so the host runs ahead and the events are not skewed by launch latency).
+        -> {kind: dict(ms=..., launches=..., flops=...)} averaged over `reps` passes."""
+        agg = {}
+        for _ in range(reps):
+            evs = []
+            torch.cuda.synchronize()
+            torch.cuda._sleep(int(4e7))
+            for fn, kind, flops in self.steps:
+                s = torch.cuda.Event(enable_timing=True)
+                e = torch.cuda.Event(enable_timing=True)
+                s.record()
+                fn()
+                e.record()
+                evs.append((s, e, kind, flops))
+            torch.cuda.synchronize()
+            for s, e, kind, flops in evs:
+                a = agg.setdefault(kind, dict(ms=0.0, launches=0, flops=0))
+                a["ms"] += s.elapsed_time(e) / reps
+                a["launches"] += 1.0 / reps
+                a["flops"] += flops / reps
+        return agg
 
     def run(self, use_graph):
         if not use_graph:

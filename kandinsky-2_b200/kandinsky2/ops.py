@@ -116,12 +116,17 @@ def gemm_rows(x, w_packed, cout, bias=None, residual=None, out=None):
 _gn_scratch = {}
 
 
+_GN_SCRATCH_FLOATS = 1 << 23  # 32 MB, fixed: its address is baked into captured CUDA graphs
+
+
 def _scratch(dev, nfloats):
     key = (dev.index, )
     buf = _gn_scratch.get(key)
-    if buf is None or buf.numel() < nfloats:
-        buf = torch.zeros(max(nfloats, 1 << 20), dtype=torch.float32, device=dev)
+    if buf is None:
+        buf = torch.zeros(_GN_SCRATCH_FLOATS, dtype=torch.float32, device=dev)
         _gn_scratch[key] = buf
+    if nfloats > buf.numel():
+        raise nat.K2Error(f"gn_stats scratch of {buf.numel()} floats is too small for this geometry ({nfloats})")
     return buf
 
 
@@ -132,7 +137,7 @@ def gn_stats(x0, x1=None, groups=32, eps=1e-5, stats=None):
     C1 = x1.shape[-1] if x1 is not None else 0
     if stats is None:
         stats = torch.empty((NB, groups, 2), dtype=torch.float32, device=x0.device)
-    need = lib.k2_gn_scratch_floats(NB, H * W, groups)
+    need = lib.k2_gn_scratch_floats(NB, H * W, C0 + C1)
     scratch = _scratch(x0.device, need)
     check(lib.k2_gn_stats(ptr(x0), C0, _row_stride(x0), ptr(x1), C1, _row_stride(x1) if x1 is not None else 0,
                           NB, H * W, groups, eps, ptr(stats), ptr(scratch), stream_ptr()))
