@@ -48,6 +48,8 @@ int k2_set_tuning(int key, int value);
  * [w_rows >= Cout][Ktot], K contiguous, k ordered source-major, then tap (ky*3+kx), then channel, each
  * source's channel count padded to a multiple of 64 (zero weights for the padding).
  * out_mode 0: fp16 rows [M, ldo]; out_mode 1: fp32 NCHW [NB, Cout, H, W] (output heads).
+ * ldw is the row stride of Wp in elements (0 = Ktot); a strided Wp lets an ACTIVATION matrix be the B operand
+ * (MoVQ attention: scores = q k^T with k rows as "weights").
  * A plain GEMM [M,K]x[K,N] is the call with NB=1, H=1, W=M, one source with taps=1.
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
@@ -58,7 +60,7 @@ typedef struct {
 } K2ConvSrc;
 
 int k2_conv_gemm(const K2ConvSrc* srcs, int nsrc, int NB, int H, int W, const void* w_packed, int w_rows,
-                 int Ktot, int Cout, const float* bias, const void* residual, int ldr, void* out, int ldo,
+                 int Ktot, int ldw, int Cout, const float* bias, const void* residual, int ldr, void* out, int ldo,
                  int out_mode, k2_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
@@ -150,6 +152,10 @@ int k2_vq_argmin(const float* z, const float* codebook, long long* idx, int n, i
 /* y[n,o,:] = b[o] + sum_i w[o,i] x[n,i,:] on fp32 NCHW (MoVQ post_quant_conv 4->4, autoencoder.py:183) */
 int k2_pointwise_nchw_f32(const float* x, const float* w, const float* b, float* y, int NB, int Ci, int Co, int HW,
                           k2_stream_t stream);
+/* nearest 2x upsample of fp16 NHWC rows (movq_modules.py:93-97 F.interpolate before the conv) */
+int k2_upsample2x_nhwc(const void* x, int ldx, void* y, int ldy, int NB, int H, int W, int C, k2_stream_t stream);
+/* y[r, :] = softmax(scale * x[r, :]) over n columns, fp16 in/out, fp32 math (movq_modules.py:213-215) */
+int k2_softmax_rows(const void* x, int ldx, void* y, int ldy, long long rows, int n, float scale, k2_stream_t stream);
 int k2_nchw_to_nhwc_f32(const float* x, float* y, int NB, int C, int H, int W, k2_stream_t stream);
 int k2_images_to_u8(const float* x_nchw, uint8_t* out_nhwc, int NB, int C, int H, int W, int crop_h,
                     int crop_w, k2_stream_t stream);

@@ -136,12 +136,15 @@ int k2_set_tuning(int key, int value) {
 }
 
 int k2_conv_gemm(const K2ConvSrc* srcs, int nsrc, int NB, int H, int W, const void* w_packed, int w_rows,
-                 int Ktot, int Cout, const float* bias, const void* residual, int ldr, void* out, int ldo,
+                 int Ktot, int ldw, int Cout, const float* bias, const void* residual, int ldr, void* out, int ldo,
                  int out_mode, k2_stream_t stream) {
   K2_REQUIRE(nsrc >= 1 && nsrc <= 3, "conv_gemm: 1..3 sources");
   K2_REQUIRE(NB > 0 && H > 0 && W > 0 && Cout > 0, "conv_gemm: bad geometry");
   K2_REQUIRE(w_rows >= Cout, "conv_gemm: w_rows < Cout");
   K2_REQUIRE(Ktot % 64 == 0, "conv_gemm: Ktot must be a multiple of 64");
+  if (ldw == 0) ldw = Ktot;
+  K2_REQUIRE(ldw >= Ktot && ldw % 8 == 0 && (reinterpret_cast<uintptr_t>(w_packed) & 15) == 0,
+             "conv_gemm: weight row stride / alignment");
   ConvGemmParams p;
   memset(&p, 0, sizeof p);
   p.NB = NB;
@@ -185,7 +188,7 @@ int k2_conv_gemm(const K2ConvSrc* srcs, int nsrc, int NB, int H, int W, const vo
   p.Cout = Cout;
   {
     uint64_t dims[2] = {static_cast<uint64_t>(Ktot), static_cast<uint64_t>(w_rows)};
-    uint64_t str[1] = {static_cast<uint64_t>(Ktot) * 2};
+    uint64_t str[1] = {static_cast<uint64_t>(ldw) * 2};
     uint32_t box[2] = {64, static_cast<uint32_t>(BN)};
     if (encode_tmap_f16(&p.tmB, w_packed, 2, dims, str, box)) return -1;
   }

@@ -52,6 +52,89 @@ __device__ __forceinline__ void decode_m_tile(const ConvGemmParams& p, int m_idx
   n0 = tn_i * p.TN;
 }
 
+// Epilogue of one (128-row x BN-column) accumulator tile held in this CTA's TMEM at column `acc_col`:
+// tcgen05.ld -> + bias (+ residual) -> fp16 rows (out_mode 0) or fp32 NCHW (out_mode 1).
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t tmem_base, int acc_col, int ew, int lane,
+                                          int n0, int y0, int x0, int n_idx) {
+  const int row = ew * 32 + lane;
+  const int thw = p.TH * p.TW;
+  constexpr int CH = (BN >= 32) ? 32 : 16;  // columns per tcgen05.ld
+      const int tn = row / thw;
+      const int rem = row - tn * thw;
+      const int th = rem / p.TW;
+      const int tw = rem - th * p.TW;
+      const int n = n0 + tn, y = y0 + th, x = x0 + tw;
+      const bool valid = (tn < p.TN) && (n < p.NB) && (y < p.H) && (x < p.W);
+      const long long out_row = (static_cast<long long>(n) * p.H + y) * p.W + x;
+#pragma unroll 1
+      for (int j = 0; j < BN / CH; ++j) {
+        const uint32_t taddr =
+            tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc_col + j * CH);
+        uint32_t r[CH];
+        if constexpr (CH == 32) {
+          tmem_ld_32x32b_x32(taddr, r);
+        } else {
+          tmem_ld_32x32b_x16(taddr, r);
+        }
+        tmem_ld_wait();
+        const int col0 = n_idx * BN + j * CH;
+        if (valid && col0 < p.Cout) {
+          if (p.out_mode == 0) {
+            __half* orow = reinterpret_cast<__half*>(p.out) + out_row * p.ldo + col0;
+            const __half* rrow = p.residual ? p.residual + out_row * p.ldr + col0 : nullptr;
+            if (col0 + CH <= p.Cout) {
+#pragma unroll
+              for (int v = 0; v < CH / 8; ++v) {
+                float f[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  f[e] = __uint_as_float(r[v * 8 + e]);
+                  if (p.bias) f[e] += __ldg(p.bias + col0 + v * 8 + e);
+                }
+                if (rrow) {
+                  uint4 rv = *reinterpret_cast<const uint4*>(rrow + v * 8);
+                  const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    float2 t = __half22float2(rh[e]);
+                    f[2 * e] += t.x;
+                    f[2 * e + 1] += t.y;
+                  }
+                }
+                uint4 ov;
+                __half2* oh = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+                *reinterpret_cast<uint4*>(orow + v * 8) = ov;
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < CH; ++e) {
+                if (col0 + e < p.Cout) {
+                  float f = __uint_as_float(r[e]);
+                  if (p.bias) f += __ldg(p.bias + col0 + e);
+                  if (rrow) f += __half2float(rrow[e]);
+                  orow[e] = __float2half_rn(f);
+                }
+              }
+            }
+          } else {
+            // fp32 NCHW (UNet / MoVQ output heads)
+            float* o = reinterpret_cast<float*>(p.out);
+#pragma unroll
+            for (int e = 0; e < CH; ++e) {
+              if (col0 + e < p.Cout) {
+                float f = __uint_as_float(r[e]);
+                if (p.bias) f += __ldg(p.bias + col0 + e);
+                o[((static_cast<long long>(n) * p.Cout + (col0 + e)) * p.H + y) * p.W + x] = f;
+              }
+            }
+          }
+        }
+      }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   using C = Cfg<BN>;
@@ -168,92 +251,16 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
   } else if (warp_idx >= 4) {
     // ===================================== epilogue ==========================================
     const int ew = warp_idx - 4;  // == warp_idx % 4 -> TMEM lanes [32*ew, 32*ew+32)
-    const int row = ew * 32 + lane;
-    const int thw = p.TH * p.TW;
     int acc = 0;
     uint32_t acc_phase = 0;
-    constexpr int CH = (BN >= 32) ? 32 : 16;  // columns per tcgen05.ld
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_idx = tile % p.m_tiles;
       const int n_idx = tile / p.m_tiles;
       int n0, y0, x0;
       decode_m_tile(p, m_idx, n0, y0, x0);
-      const int tn = row / thw;
-      const int rem = row - tn * thw;
-      const int th = rem / p.TW;
-      const int tw = rem - th * p.TW;
-      const int n = n0 + tn, y = y0 + th, x = x0 + tw;
-      const bool valid = (tn < p.TN) && (n < p.NB) && (y < p.H) && (x < p.W);
-      const long long out_row = (static_cast<long long>(n) * p.H + y) * p.W + x;
-
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-#pragma unroll 1
-      for (int j = 0; j < BN / CH; ++j) {
-        const uint32_t taddr =
-            tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc * BN + j * CH);
-        uint32_t r[CH];
-        if constexpr (CH == 32) {
-          tmem_ld_32x32b_x32(taddr, r);
-        } else {
-          tmem_ld_32x32b_x16(taddr, r);
-        }
-        tmem_ld_wait();
-        const int col0 = n_idx * BN + j * CH;
-        if (valid && col0 < p.Cout) {
-          if (p.out_mode == 0) {
-            __half* orow = reinterpret_cast<__half*>(p.out) + out_row * p.ldo + col0;
-            const __half* rrow = p.residual ? p.residual + out_row * p.ldr + col0 : nullptr;
-            if (col0 + CH <= p.Cout) {
-#pragma unroll
-              for (int v = 0; v < CH / 8; ++v) {
-                float f[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  f[e] = __uint_as_float(r[v * 8 + e]);
-                  if (p.bias) f[e] += __ldg(p.bias + col0 + v * 8 + e);
-                }
-                if (rrow) {
-                  uint4 rv = *reinterpret_cast<const uint4*>(rrow + v * 8);
-                  const __half2* rh = reinterpret_cast<const __half2*>(&rv);
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    float2 t = __half22float2(rh[e]);
-                    f[2 * e] += t.x;
-                    f[2 * e + 1] += t.y;
-                  }
-                }
-                uint4 ov;
-                __half2* oh = reinterpret_cast<__half2*>(&ov);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
-                *reinterpret_cast<uint4*>(orow + v * 8) = ov;
-              }
-            } else {
-#pragma unroll
-              for (int e = 0; e < CH; ++e) {
-                if (col0 + e < p.Cout) {
-                  float f = __uint_as_float(r[e]);
-                  if (p.bias) f += __ldg(p.bias + col0 + e);
-                  if (rrow) f += __half2float(rrow[e]);
-                  orow[e] = __float2half_rn(f);
-                }
-              }
-            }
-          } else {
-            // fp32 NCHW (UNet / MoVQ output heads)
-            float* o = reinterpret_cast<float*>(p.out);
-#pragma unroll
-            for (int e = 0; e < CH; ++e) {
-              if (col0 + e < p.Cout) {
-                float f = __uint_as_float(r[e]);
-                if (p.bias) f += __ldg(p.bias + col0 + e);
-                o[((static_cast<long long>(n) * p.Cout + (col0 + e)) * p.H + y) * p.W + x] = f;
-              }
-            }
-          }
-        }
-      }
+      epilogue_tile<BN>(p, tmem_base, acc * BN, ew, lane, n0, y0, x0, n_idx);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);

@@ -393,6 +393,86 @@ __global__ void pointwise_nchw_kernel(const float* __restrict__ x, const float* 
   y[i] = acc;
 }
 
+// nearest 2x upsample of NHWC fp16 rows: one 16-byte vector per thread, each written to its 4 output pixels
+__global__ void __launch_bounds__(256) upsample2x_kernel(const __half* __restrict__ x, int ldx, __half* __restrict__ y, int ldy,
+                                                         int NB, int H, int W, int CV) {
+  const long long item = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(NB) * H * W * CV;
+  if (item >= total) return;
+  const int v = static_cast<int>(item % CV);
+  const long long pix = item / CV;
+  const int xx = static_cast<int>(pix % W);
+  const int yy = static_cast<int>((pix / W) % H);
+  const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
+  const uint4 val = __ldg(reinterpret_cast<const uint4*>(x + pix * ldx + v * 8));
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      const long long orow = (static_cast<long long>(n) * 2 * H + (2 * yy + dy)) * (2 * W) + (2 * xx + dx);
+      *reinterpret_cast<uint4*>(y + orow * ldy + v * 8) = val;
+    }
+}
+
+// row softmax, fp16 in/out, fp32 math; one block per row, 16-byte vectors
+__global__ void __launch_bounds__(256) softmax_rows_kernel(const __half* __restrict__ x, int ldx, __half* __restrict__ y,
+                                                           int ldy, int n, float scale_log2e) {
+  __shared__ float red[8];
+  const long long r = blockIdx.x;
+  const __half* xr = x + r * ldx;
+  __half* yr = y + r * ldy;
+  const int nv = n / 8;
+  float mx = -INFINITY;
+  for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(xr + v * 8));
+    const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __half22float2(h2[e]);
+      mx = fmaxf(mx, fmaxf(f.x, f.y));
+    }
+  }
+  for (int i = nv * 8 + threadIdx.x; i < n; i += blockDim.x) mx = fmaxf(mx, __half2float(xr[i]));
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+  __syncthreads();
+  const float mo = mx * scale_log2e;
+  float sum = 0.f;
+  for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(xr + v * 8));
+    const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __half22float2(h2[e]);
+      sum += exp2f(fmaf(f.x, scale_log2e, -mo)) + exp2f(fmaf(f.y, scale_log2e, -mo));
+    }
+  }
+  for (int i = nv * 8 + threadIdx.x; i < n; i += blockDim.x) sum += exp2f(fmaf(__half2float(xr[i]), scale_log2e, -mo));
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int w = 0; w < 8; ++w) sum += red[w];
+  const float inv = 1.f / sum;
+  for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(xr + v * 8));
+    const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+    uint4 ov;
+    __half2* oh = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __half22float2(h2[e]);
+      oh[e] = __floats2half2_rn(exp2f(fmaf(f.x, scale_log2e, -mo)) * inv, exp2f(fmaf(f.y, scale_log2e, -mo)) * inv);
+    }
+    *reinterpret_cast<uint4*>(yr + v * 8) = ov;
+  }
+  for (int i = nv * 8 + threadIdx.x; i < n; i += blockDim.x)
+    yr[i] = __float2half_rn(exp2f(fmaf(__half2float(xr[i]), scale_log2e, -mo)) * inv);
+}
+
 inline unsigned int blocks_for(long long total, int bs) { return static_cast<unsigned int>((total + bs - 1) / bs); }
 
 }  // namespace
@@ -488,6 +568,26 @@ int k2_sampler_step(const float* model_out, float* x, const float* noise, const 
   sampler_post_kernel<<<blocks_for(total, 256), 256, 0, st>>>(p);
   K2_CHECK_CUDA(cudaGetLastError());
   count_launch(2);
+  return 0;
+}
+
+int k2_upsample2x_nhwc(const void* x, int ldx, void* y, int ldy, int NB, int H, int W, int C, k2_stream_t stream) {
+  K2_REQUIRE(x && y && C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "upsample2x: channels / strides must be multiples of 8");
+  const long long total = static_cast<long long>(NB) * H * W * (C / 8);
+  upsample2x_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half*>(x), ldx, reinterpret_cast<__half*>(y), ldy, NB, H, W, C / 8);
+  K2_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int k2_softmax_rows(const void* x, int ldx, void* y, int ldy, long long rows, int n, float scale, k2_stream_t stream) {
+  K2_REQUIRE(x && y && rows > 0 && n > 0 && ldx % 8 == 0 && ldy % 8 == 0, "softmax_rows: bad arguments");
+  K2_REQUIRE(rows < (1LL << 31), "softmax_rows: too many rows");
+  softmax_rows_kernel<<<static_cast<unsigned int>(rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half*>(x), ldx, reinterpret_cast<__half*>(y), ldy, n, scale * 1.4426950408889634f);
+  K2_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return 0;
 }
 

@@ -108,14 +108,17 @@ class SpacedDiffusion:
     @torch.no_grad()
     def p_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, model_kwargs=None,
                       device=None, progress=False, init_step=None, *, guidance_scale=1.0, cond_first=True,
-                      clip_range=2.0, inpaint_init=None, inpaint_mask=None, step_noise=None, callback=None):
+                      clip_range=2.0, inpaint_init=None, inpaint_mask=None, step_noise=None, callback=None,
+                      sample_generators=None):
         """Reference signature (gaussian_diffusion.py:384-425) with `model` being the k2b200 UNet module itself:
         the CFG closure, the clamp of denoised_fun and the optional inpainting blend are fused into the step
         kernel and selected by the keyword-only arguments.  shape = (2*B, 4, h, w) as in the reference (CFG
         doubled); returns [2*B, 4, h, w] whose two halves both hold the B samples.
         clip_denoised=True reproduces the reference's per-step dynamic threshold (sample 0's 99.5 percentile
         applied to the whole batch, :284-294); False keeps only the +-clip_range clamp (Kandinsky 2.2 DDPM).
-        step_noise: optional fp32 [num_steps, B, 4, h, w] injected instead of torch.randn (parity tests)."""
+        step_noise: optional fp32 [num_steps, B, 4, h, w] injected instead of torch.randn (parity tests).
+        sample_generators: optional list of B torch.Generator (device of the model), one per sample, so that the
+        noise stream of an image does not depend on which rank / batch position it runs at."""
         if denoised_fn is not None:
             raise K2Error("denoised_fn closures are fused: pass clip_range / inpaint_init / inpaint_mask instead")
         model_kwargs = dict(model_kwargs or {})
@@ -141,6 +144,9 @@ class SpacedDiffusion:
         for n, i in enumerate(indices):
             if step_noise is not None:
                 step.noise.copy_(step_noise[n])
+            elif sample_generators is not None:
+                for b, gen in enumerate(sample_generators):
+                    step.noise[b].normal_(generator=gen)
             else:
                 step.noise.normal_()
             step.run(x, ts[i], coef[i])

@@ -240,7 +240,9 @@ class Text2ImUNet(nn.Module):
                             wqkv=ops.pack_conv_weight(self._param(p + "qkv.weight")), bqkv=f32(p + "qkv.bias"),
                             wenc=ops.pack_conv_weight(self._param(p + "encoder_kv.weight")), benc=f32(p + "encoder_kv.bias"),
                             wproj=ops.pack_conv_weight(self._param(p + "proj_out.weight")), bproj=f32(p + "proj_out.bias"))
-        pk["film_w"] = torch.cat(film_w, 0).contiguous()
+        # all 2*Cout x temb emb_layers of the network as ONE weight (one GEMV-like launch per step), stored fp16:
+        # it is the only per-step weight stream that is pure bandwidth (the reference keeps it fp32, fp16_util.py:13)
+        pk["film_w"] = torch.cat(film_w, 0).to(torch.float16).contiguous()
         pk["film_b"] = torch.cat(film_b, 0).contiguous()
         pk["film_total"] = off
         pk["te0_w"], pk["te0_b"] = f32("time_embed.0.weight"), f32("time_embed.0.bias")

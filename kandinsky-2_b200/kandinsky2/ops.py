@@ -84,8 +84,9 @@ def conv_gemm(srcs, w_packed, cout, bias=None, residual=None, out=None, out_mode
             out = torch.empty((NB, cout, H, W), dtype=torch.float32, device=t0.device)
     ldo = _row_stride(out) if out_mode == 0 else 0
     ldr = _row_stride(residual) if residual is not None else 0
-    assert w_packed.dtype == torch.float16 and w_packed.is_contiguous()
-    check(lib.k2_conv_gemm(arr, len(srcs), NB, H, W, ptr(w_packed), w_packed.shape[0], w_packed.shape[1], cout,
+    assert w_packed.dtype == torch.float16 and w_packed.stride(1) == 1
+    check(lib.k2_conv_gemm(arr, len(srcs), NB, H, W, ptr(w_packed), w_packed.shape[0], w_packed.shape[1],
+                           w_packed.stride(0), cout,
                            ptr(bias), ptr(residual), ldr, ptr(out), ldo, out_mode, stream_ptr()))
     return out
 
@@ -286,6 +287,26 @@ def pointwise_nchw_f32(x, w, b):
     y = torch.empty((NB, Co, H, W), dtype=torch.float32, device=x.device)
     check(lib.k2_pointwise_nchw_f32(ptr(x), ptr(w), ptr(b), ptr(y), NB, Ci, Co, H * W, stream_ptr()))
     return y
+
+
+def upsample2x(x, out=None):
+    """fp16 NHWC [NB,H,W,C] -> nearest 2x [NB,2H,2W,C]."""
+    lib = nat.load()
+    NB, H, W, C = x.shape
+    if out is None:
+        out = torch.empty((NB, 2 * H, 2 * W, C), dtype=torch.float16, device=x.device)
+    check(lib.k2_upsample2x_nhwc(ptr(x), _row_stride(x), ptr(out), _row_stride(out), NB, H, W, C, stream_ptr()))
+    return out
+
+
+def softmax_rows(x, scale, out=None):
+    """fp16 [rows, n] (row-strided) -> softmax(scale * x) fp16."""
+    lib = nat.load()
+    rows, n = x.shape
+    if out is None:
+        out = torch.empty((rows, n), dtype=torch.float16, device=x.device)
+    check(lib.k2_softmax_rows(ptr(x), x.stride(0), ptr(out), out.stride(0), rows, n, float(scale), stream_ptr()))
+    return out
 
 
 def nchw_to_nhwc_f32(x):

@@ -77,7 +77,118 @@ def main():
         extra()
 
 
-EXTRA = []
+def golden_movq(name, dd, B, h, w, wseed, iseed, n_embed=64):
+    import contextlib
+    import io
+    from oracle import movq_oracle as mo
+    with ref_shim.reference_modules() as R:
+        ae = R.load("vqgan.autoencoder")
+        with contextlib.redirect_stdout(io.StringIO()):  # the reference ctor prints (movq_modules.py:261-265)
+            m = ae.MOVQ(dict(dd, double_z=False, dropout=0.0), n_embed=n_embed, embed_dim=4).eval()
+    spec = mo.movq_decoder_param_spec(dd, 4, n_embed)
+    ref = {k: tuple(v.shape) for k, v in m.state_dict().items()
+           if k.startswith(("decoder.", "post_quant_conv.", "quantize."))}
+    assert ref == {k: tuple(s) for k, s in spec}, "oracle MoVQ parameter spec != reference state_dict"
+    sd = synth.synth_state_dict(spec, seed=wseed)
+    m.load_state_dict(sd, strict=False)
+    g = torch.Generator().manual_seed(iseed)
+    z = torch.randn(B, 4, h, w, generator=g)
+    with torch.no_grad():
+        y_ref = m.decode(z)
+        y_orc = mo.movq_decode(sd, dd, z)
+        zf = z.permute(0, 2, 3, 1).reshape(-1, 4)
+        # VectorQuantizer.forward's distance/argmin lines (quntize.py:89-98) on the same z
+        emb = m.quantize.embedding.weight
+        d = torch.sum(zf ** 2, dim=1, keepdim=True) + torch.sum(emb ** 2, dim=1) - 2 * torch.einsum("bd,dn->bn", zf, emb.t())
+        idx_ref = torch.argmin(d, dim=1)
+        idx_orc = mo.vq_indices(zf, sd["quantize.embedding.weight"])
+    err = (y_ref - y_orc).abs().max().item()
+    assert err <= 1e-5 and torch.equal(idx_ref, idx_orc), f"{name}: MoVQ oracle deviates ({err})"
+    torch.save(dict(dd=dd, n_embed=n_embed, weight_seed=wseed, z=z, out=y_ref, indices=idx_ref),
+               os.path.join(GOLD, name + ".pt"))
+    print(f"{name}: reference out std {y_ref.std():.4f}, oracle-vs-reference max abs {err:.2e}")
+
+
+def golden_trajectory(name, cfg, B, H, W, ntext, steps, guidance, wseed, iseed):
+    """Reference SpacedDiffusion.p_sample_loop (p_sampler path of Kandinsky2_1.generate_img) on the tiny reference
+    UNet with the CFG closure of kandinsky2_1_model.py:222-233 and injected noise."""
+    from oracle import diffusion_oracle as do
+    model = build_ref_unet(cfg)
+    spec = uo.unet_param_spec(cfg)
+    sd = synth.synth_state_dict(spec, seed=wseed)
+    model.load_state_dict(sd, strict=True)
+    inp = unet_inputs(cfg, 2 * B, H, W, ntext, iseed)
+    g = torch.Generator().manual_seed(iseed + 100)
+    x_T = torch.randn(2 * B, 4, H, W, generator=g)
+    step_noise = torch.randn(steps, 2 * B, 4, H, W, generator=g)
+    kw = dict(full_emb=inp["full_emb"], pooled_emb=inp["pooled_emb"], image_emb=inp["image_emb"])
+    with ref_shim.reference_modules() as R:
+        mc = R.load("model.model_creation")
+        gdm = R.load("model.gaussian_diffusion")
+        diffusion = mc.create_gaussian_diffusion(steps=1000, learn_sigma=True, sigma_small=False, noise_schedule="linear",
+                                                 use_kl=False, predict_xstart=False, rescale_timesteps=True,
+                                                 rescale_learned_sigmas=True, timestep_respacing=str(steps),
+                                                 linear_start=0.00085, linear_end=0.012)
+
+        def model_fn(x_t, ts, **kwargs):  # kandinsky2_1_model.py:222-233, sampler == "p_sampler"
+            half = x_t[: len(x_t) // 2]
+            combined = torch.cat([half, half], dim=0)
+            model_out = model(combined, ts, **kwargs)
+            eps, rest = model_out[:, :4], model_out[:, 4:]
+            cond_eps, uncond_eps = torch.split(eps, len(eps) // 2, dim=0)
+            half_eps = uncond_eps + guidance * (cond_eps - uncond_eps)
+            eps = torch.cat([half_eps, half_eps], dim=0)
+            return torch.cat([eps, rest], dim=1)
+
+        it = iter(step_noise)
+        orig = gdm.th.randn_like
+        gdm.th.randn_like = lambda x: next(it)
+        try:
+            model.del_cache()
+            with torch.no_grad():
+                out = diffusion.p_sample_loop(model_fn, (2 * B, 4, H, W), device="cpu", noise=x_T, progress=False,
+                                              model_kwargs=kw, denoised_fn=lambda x: x.clamp(-2, 2))[:B]
+        finally:
+            gdm.th.randn_like = orig
+        tables = dict(betas=diffusion.betas.copy(), timestep_map=list(diffusion.timestep_map),
+                      post_logvar=diffusion.posterior_log_variance_clipped.copy(),
+                      coef1=diffusion.posterior_mean_coef1.copy(), coef2=diffusion.posterior_mean_coef2.copy())
+    # the oracle restatement on the same inputs
+    tab = do.Tables(do.linear_betas(), do.space_timesteps(1000, steps))
+    assert tab.timestep_map == tables["timestep_map"] and np.allclose(tab.betas, tables["betas"], rtol=0, atol=0)
+    assert np.array_equal(tab.post_logvar, tables["post_logvar"]) and np.array_equal(tab.coef1, tables["coef1"])
+    with torch.no_grad():
+        orc = do.p_sample_loop(lambda xx, tt: uo.unet_forward(sd, cfg, xx, tt, **kw), tab, x_T[:B], step_noise[:, :B], guidance)
+    err = (out - orc).abs().max().item()
+    assert err <= 1e-4, f"{name}: oracle trajectory deviates from the reference by {err}"
+    torch.save(dict(cfg=cfg, weight_seed=wseed, cond=kw, x_T=x_T[:B].clone(), step_noise=step_noise[:, :B].clone(),
+                    steps=steps, guidance=guidance, out=out, tables=tables), os.path.join(GOLD, name + ".pt"))
+    print(f"{name}: final latent std {out.std():.4f}, oracle-vs-reference max abs {err:.2e}")
+
+
+def golden_schedule():
+    """Known-answer constants of the reference schedule code."""
+    with ref_shim.reference_modules() as R:
+        mc = R.load("model.model_creation")
+        rs = R.load("model.respace")
+        nn_ = R.load("model.nn")
+        d50 = mc.create_gaussian_diffusion(steps=1000, learn_sigma=True, noise_schedule="linear", rescale_timesteps=True,
+                                           rescale_learned_sigmas=True, timestep_respacing="50", linear_start=0.00085,
+                                           linear_end=0.012)
+        kat = dict(space50=sorted(rs.space_timesteps(1000, "50")), space20=sorted(rs.space_timesteps(1000, "20")),
+                   betas50=d50.betas.copy(), post_logvar50=d50.posterior_log_variance_clipped.copy(),
+                   coef1_50=d50.posterior_mean_coef1.copy(), coef2_50=d50.posterior_mean_coef2.copy(),
+                   sqrt_recip50=d50.sqrt_recip_alphas_cumprod.copy(), sqrt_recipm1_50=d50.sqrt_recipm1_alphas_cumprod.copy(),
+                   temb=nn_.timestep_embedding(torch.tensor([999.0, 0.0, 500.5]), 384))
+    torch.save(kat, os.path.join(GOLD, "schedule_kat.pt"))
+    print("schedule_kat: betas50[:3]", kat["betas50"][:3])
+
+
+EXTRA = [
+    lambda: golden_movq("movq_tiny", __import__("oracle.movq_oracle", fromlist=["x"]).DDCONFIG_TINY, 2, 8, 8, wseed=4, iseed=3),
+    lambda: golden_trajectory("traj_tiny", uo.CONFIG_TINY, 2, 16, 16, 7, steps=5, guidance=4.0, wseed=1, iseed=21),
+    golden_schedule,
+]
 
 if __name__ == "__main__":
     main()

@@ -1,0 +1,99 @@
+"""CPU: the oracle restatement against the committed golden vectors (written by oracle/make_golden.py from the
+reference's own code), the schedule known-answer constants, and the host-side schedule code of the product."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _load(name):
+    return torch.load(os.path.join(GOLD, name + ".pt"), weights_only=False)
+
+
+@pytest.mark.parametrize("name", ["unet_tiny", "unet_tiny_inpaint"])
+def test_unet_oracle_matches_reference_golden(name):
+    from oracle import synth, unet_oracle as uo
+    fx = _load(name)
+    sd = synth.synth_state_dict(uo.unet_param_spec(fx["cfg"]), seed=fx["weight_seed"])
+    assert abs(float(sum(v.double().sum() for v in sd.values())) - fx["weight_checksum"]) < 1e-6
+    inp = fx["inputs"]
+    kw = {k: v for k, v in inp.items() if k not in ("x", "t")}
+    with torch.no_grad():
+        y = uo.unet_forward(sd, fx["cfg"], inp["x"], inp["t"], **kw)
+    assert (y - fx["out"]).abs().max().item() <= 1e-5
+
+
+def test_movq_oracle_matches_reference_golden():
+    from oracle import movq_oracle as mo, synth
+    fx = _load("movq_tiny")
+    sd = synth.synth_state_dict(mo.movq_decoder_param_spec(fx["dd"], 4, fx["n_embed"]), seed=fx["weight_seed"])
+    with torch.no_grad():
+        y = mo.movq_decode(sd, fx["dd"], fx["z"])
+    assert (y - fx["out"]).abs().max().item() <= 1e-5
+    zf = fx["z"].permute(0, 2, 3, 1).reshape(-1, 4)
+    assert torch.equal(mo.vq_indices(zf, sd["quantize.embedding.weight"]), fx["indices"])  # bit-exact indices
+
+
+def test_trajectory_oracle_matches_reference_golden():
+    from oracle import diffusion_oracle as do, synth, unet_oracle as uo
+    fx = _load("traj_tiny")
+    sd = synth.synth_state_dict(uo.unet_param_spec(fx["cfg"]), seed=fx["weight_seed"])
+    tab = do.Tables(do.linear_betas(), do.space_timesteps(1000, fx["steps"]))
+    with torch.no_grad():
+        out = do.p_sample_loop(lambda xx, tt: uo.unet_forward(sd, fx["cfg"], xx, tt, **fx["cond"]), tab, fx["x_T"],
+                               fx["step_noise"], fx["guidance"])
+    assert (out - fx["out"]).abs().max().item() <= 1e-4
+
+
+def test_schedule_known_answers():
+    """Constants obtained by running the reference + the product's host schedule code."""
+    from oracle import diffusion_oracle as do
+    kat = _load("schedule_kat")
+    b = do.linear_betas()
+    assert b[0] == 0.00085 and abs(b[999] - 0.012) < 1e-15
+    ac = np.cumprod(1 - b)
+    assert abs(ac[0] - 0.99915) < 1e-12 and abs(ac[499] - 0.1618121459134018) < 1e-12
+    assert abs(ac[999] - 0.0015789629305514416) < 1e-14
+    assert do.space_timesteps(1000, 50) == kat["space50"] and do.space_timesteps(1000, 20) == kat["space20"]
+    assert kat["space20"][:6] == [0, 53, 105, 158, 210, 263] and kat["space50"][-3:] == [958, 979, 999]
+    tab = do.Tables(b, kat["space50"])
+    assert np.array_equal(tab.betas, kat["betas50"]) and np.array_equal(tab.post_logvar, kat["post_logvar50"])
+    assert np.allclose(kat["betas50"][:3], [0.00085, 0.01916717422017, 0.02481784056427294], rtol=1e-12)
+    assert abs(kat["post_logvar50"][0] + 7.1128514473284525) < 1e-12
+    # product host code (no GPU needed: numpy tables only)
+    from kandinsky2.model.gaussian_diffusion import create_gaussian_diffusion, create_ddpm_v22, space_timesteps
+    assert sorted(space_timesteps(1000, "50")) == kat["space50"]
+    d = create_gaussian_diffusion(steps=1000, learn_sigma=True, noise_schedule="linear", rescale_timesteps=True,
+                                  rescale_learned_sigmas=True, timestep_respacing="50", linear_start=0.00085,
+                                  linear_end=0.012)
+    assert np.array_equal(d.betas, kat["betas50"])
+    coef = d.coef_table()
+    assert np.array_equal(coef[:, 0], kat["sqrt_recip50"].astype(np.float32))
+    assert np.array_equal(coef[:, 1], kat["sqrt_recipm1_50"].astype(np.float32))
+    assert np.array_equal(coef[:, 2], kat["coef1_50"].astype(np.float32))
+    assert np.array_equal(coef[:, 3], kat["coef2_50"].astype(np.float32))
+    assert np.array_equal(coef[:, 4], kat["post_logvar50"].astype(np.float32))
+    assert d.model_timestep(49) == 999.0 and d.model_timestep(1) == 20.0
+    v22 = create_ddpm_v22(50)
+    assert v22.timestep_map[:3] == [0, 20, 40] and v22.timestep_map[-1] == 980 and v22.num_timesteps == 50
+    # timestep embedding known answers (cos first)
+    from oracle import unet_oracle as uo
+    te = uo.timestep_embedding(torch.tensor([999.0, 0.0, 500.5]), 384)
+    assert torch.equal(te, kat["temb"])
+    assert abs(te[0, 0].item() - 0.99964982) < 1e-6 and abs(te[0, 192].item() + 0.02646075) < 1e-6
+
+
+def test_param_counts_and_flops():
+    from oracle import movq_oracle as mo, unet_oracle as uo
+    n = sum(int(np.prod(s)) for _, s in uo.unet_param_spec(uo.CONFIG_2_1))
+    assert n == 1228661768  # CONFIG_2_1 UNet parameter count
+    f = uo.algorithmic_flops(uo.CONFIG_2_2, 8, 96, 96, 32)
+    assert abs(f / 1e12 - 15.940) < 0.02  # 15.940 TFLOP per cfg-2 step
+    assert abs(uo.algorithmic_flops(uo.CONFIG_2_1, 2, 32, 32, 87) / 1e12 - 0.433) < 0.002
+    fm = mo.decode_flops(mo.DDCONFIG_2_1, 4, 96, 96)
+    assert abs(fm / 1e12 - 19.54) < 0.3  # 19.542 TFLOP per B=4 768^2 decode
