@@ -33,7 +33,8 @@ int k2_version(void);
 /* Number of kernels launched by this library in this process since the last reset (bench evidence). */
 long long k2_launch_count(void);
 void k2_reset_launch_count(void);
-/* Tuning knobs: key 0 = force conv/GEMM N tile (0 = auto). */
+/* Tuning knobs: key 0 = force conv/GEMM N tile (0 = auto); key 1 = split-K (0 auto, 1 off, n>1 forced);
+ * key 2 = CTA-pair kernel (0 auto, 1 off, 2 on). */
 int k2_set_tuning(int key, int value);
 
 /* ---------------------------------------------------------------------------------------------
@@ -50,6 +51,9 @@ int k2_set_tuning(int key, int value);
  * out_mode 0: fp16 rows [M, ldo]; out_mode 1: fp32 NCHW [NB, Cout, H, W] (output heads).
  * ldw is the row stride of Wp in elements (0 = Ktot); a strided Wp lets an ACTIVATION matrix be the B operand
  * (MoVQ attention: scores = q k^T with k rows as "weights").
+ * workspace (may be NULL): caller-owned scratch for split-K.  When the tile count would leave SMs idle (small M, huge K:
+ * the bottom of the U) K is split over several CTAs that write fp32 partial tiles [split][M][Cout] there, and a second
+ * launch sums them in a fixed order (+bias, +residual) -- deterministic, no atomics.
  * A plain GEMM [M,K]x[K,N] is the call with NB=1, H=1, W=M, one source with taps=1.
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
@@ -61,7 +65,7 @@ typedef struct {
 
 int k2_conv_gemm(const K2ConvSrc* srcs, int nsrc, int NB, int H, int W, const void* w_packed, int w_rows,
                  int Ktot, int ldw, int Cout, const float* bias, const void* residual, int ldr, void* out, int ldo,
-                 int out_mode, k2_stream_t stream);
+                 int out_mode, void* workspace, long long workspace_bytes, k2_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * GroupNorm (32 groups in the UNet) statistics + fused apply.

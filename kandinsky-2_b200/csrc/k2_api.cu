@@ -3,6 +3,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <mutex>
 
@@ -14,6 +15,9 @@ namespace k2 {
 static thread_local std::string g_err;
 static std::atomic<long long> g_launches{0};
 static int g_force_bn = 0;
+static int g_force_split = 0;  // 0 auto, 1 off, n>1 forced
+static int g_force_2cta = 0;   // 0 auto, 1 off, 2 on
+
 
 void set_error(const std::string& msg) { g_err = msg; }
 int fail(const std::string& msg) {
@@ -132,12 +136,21 @@ int k2_set_tuning(int key, int value) {
     g_force_bn = value;
     return 0;
   }
+  if (key == 1) {
+    g_force_split = value;
+    return 0;
+  }
+  if (key == 2) {
+    g_force_2cta = value;
+    return 0;
+  }
+
   return fail("k2_set_tuning: unknown key");
 }
 
 int k2_conv_gemm(const K2ConvSrc* srcs, int nsrc, int NB, int H, int W, const void* w_packed, int w_rows,
                  int Ktot, int ldw, int Cout, const float* bias, const void* residual, int ldr, void* out, int ldo,
-                 int out_mode, k2_stream_t stream) {
+                 int out_mode, void* workspace, long long workspace_bytes, k2_stream_t stream) {
   K2_REQUIRE(nsrc >= 1 && nsrc <= 3, "conv_gemm: 1..3 sources");
   K2_REQUIRE(NB > 0 && H > 0 && W > 0 && Cout > 0, "conv_gemm: bad geometry");
   K2_REQUIRE(w_rows >= Cout, "conv_gemm: w_rows < Cout");
@@ -176,20 +189,50 @@ int k2_conv_gemm(const K2ConvSrc* srcs, int nsrc, int NB, int H, int W, const vo
   K2_REQUIRE(kchunks * 64 == Ktot, "conv_gemm: Ktot does not match the sources (taps * ceil(C/64)*64 summed)");
   p.num_k_chunks = kchunks;
 
+  // Tile shape and split-K factor from a cycle model of one SM: a K chunk costs max(MMA time, smem traffic time);
+  // the launch costs (waves of tiles) x (chunks per tile) x chunk cost + per-tile epilogue (+ the split-K second pass).
+  // Tile shape, CTA-pair mode and split-K factor.  Fitted to the B200 sweep in profiles/conv_sweep_r1.txt: the kernel
+  // is bound by L2->SM operand bandwidth (~64 B/clk/SM), so the CTA-pair kernel (half of the weight tile per CTA) with
+  // the widest N tile wins everywhere it applies; N = 192 only where it divides Cout and 256 would waste a third of a
+  // tile; K is split 2-3 ways when the tile count would leave most SM pairs idle (levels 2-3 of the U).
   int BN = g_force_bn;
+  int splits = 1;
+  int two_cta = (Cout > 64 && g_force_2cta != 1) ? 1 : 0;
+  if (g_force_2cta == 2 && Cout > 64) two_cta = 1;
   if (BN == 0) {
     if (Cout <= 16) BN = 16;
     else if (Cout <= 64) BN = 64;
-    else if (Cout % 256 == 0) BN = 256;
-    else if (Cout % 192 == 0) BN = 192;
-    else BN = 128;
+    else if (Cout <= 128) BN = 128;
+    else if (Cout <= 384 && Cout % 192 == 0) BN = 192;
+    else BN = 256;
   }
+  if (two_cta && BN < 128) two_cta = 0;
+  {
+    const long long M_total = static_cast<long long>(NB) * H * W;
+    const int nt = (Cout + BN - 1) / BN;
+    const long long units = static_cast<long long>(two_cta ? (p.m_tiles + 1) / 2 : p.m_tiles) * nt;
+    const int slots = two_cta ? num_sms() / 2 : num_sms();
+    int want = 1;
+    if (units * 5 < slots * 3 && kchunks >= 48) want = 3;        // < 60 % of the machine
+    else if (units * 2 < slots * 3 && kchunks >= 64) want = 2;   // < 1.5 waves
+    if (g_force_split > 0) want = g_force_split;
+    const bool can = workspace && out_mode == 0 && Cout % 8 == 0;
+    if (want > 1 && can) {
+      const int kps = (kchunks + want - 1) / want;
+      if ((want - 1) * kps < kchunks && static_cast<long long>(want) * M_total * Cout * 4 <= workspace_bytes) splits = want;
+    }
+  }
+  p.two_cta = two_cta;
+  p.splits = splits;
+  p.k_per_split = (kchunks + splits - 1) / splits;
+  p.M_total = static_cast<long long>(NB) * H * W;
+  p.ws = reinterpret_cast<float*>(workspace);
   p.n_tiles = (Cout + BN - 1) / BN;
   p.Cout = Cout;
   {
     uint64_t dims[2] = {static_cast<uint64_t>(Ktot), static_cast<uint64_t>(w_rows)};
     uint64_t str[1] = {static_cast<uint64_t>(ldw) * 2};
-    uint32_t box[2] = {64, static_cast<uint32_t>(BN)};
+    uint32_t box[2] = {64, static_cast<uint32_t>(two_cta ? BN / 2 : BN)};
     if (encode_tmap_f16(&p.tmB, w_packed, 2, dims, str, box)) return -1;
   }
   p.bias = bias;
@@ -197,7 +240,7 @@ int k2_conv_gemm(const K2ConvSrc* srcs, int nsrc, int NB, int H, int W, const vo
   p.ldr = ldr;
   p.out = out;
   p.ldo = ldo;
-  p.out_mode = out_mode;
+  p.out_mode = (splits > 1) ? 2 : out_mode;
   if (out_mode == 0) {
     K2_REQUIRE(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "conv_gemm: out alignment");
     if (residual)
@@ -205,6 +248,11 @@ int k2_conv_gemm(const K2ConvSrc* srcs, int nsrc, int NB, int H, int W, const vo
   }
   int rc = launch_conv_gemm(p, BN, static_cast<cudaStream_t>(stream));
   if (rc == 0) g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (rc == 0 && splits > 1) {
+    rc = launch_splitk_finalize(p.ws, splits, p.M_total, Cout, bias, p.residual, ldr, reinterpret_cast<__half*>(out), ldo,
+                                static_cast<cudaStream_t>(stream));
+    if (rc == 0) g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
   return rc;
 }
 

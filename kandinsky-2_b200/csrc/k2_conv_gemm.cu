@@ -56,7 +56,7 @@ __device__ __forceinline__ void decode_m_tile(const ConvGemmParams& p, int m_idx
 // tcgen05.ld -> + bias (+ residual) -> fp16 rows (out_mode 0) or fp32 NCHW (out_mode 1).
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t tmem_base, int acc_col, int ew, int lane,
-                                          int n0, int y0, int x0, int n_idx) {
+                                              int n0, int y0, int x0, int n_idx, int split) {
   const int row = ew * 32 + lane;
   const int thw = p.TH * p.TW;
   constexpr int CH = (BN >= 32) ? 32 : 16;  // columns per tcgen05.ld
@@ -80,7 +80,19 @@ __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t 
         tmem_ld_wait();
         const int col0 = n_idx * BN + j * CH;
         if (valid && col0 < p.Cout) {
-          if (p.out_mode == 0) {
+          if (p.out_mode == 2) {
+            // split-K: raw fp32 partial sums [split][M][Cout] into the workspace (bias/residual in the finalize pass)
+            float* w = p.ws + (static_cast<long long>(split) * p.M_total + out_row) * p.Cout + col0;
+            if (col0 + CH <= p.Cout) {
+#pragma unroll
+              for (int v = 0; v < CH / 4; ++v)
+                *reinterpret_cast<uint4*>(w + v * 4) = make_uint4(r[v * 4], r[v * 4 + 1], r[v * 4 + 2], r[v * 4 + 3]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < CH; ++e)
+                if (col0 + e < p.Cout) w[e] = __uint_as_float(r[e]);
+            }
+          } else if (p.out_mode == 0) {
             __half* orow = reinterpret_cast<__half*>(p.out) + out_row * p.ldo + col0;
             const __half* rrow = p.residual ? p.residual + out_row * p.ldr + col0 : nullptr;
             if (col0 + CH <= p.Cout) {
@@ -175,7 +187,7 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
 
   if (warp_idx == 0) {
     // ===================================== TMA producer =====================================
@@ -185,29 +197,39 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
       const uint32_t tx_bytes = p.a_box_bytes + C::B_STAGE_BYTES;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m_idx = tile % p.m_tiles;
-        const int n_idx = tile / p.m_tiles;
+        const int n_idx = (tile / p.m_tiles) % p.n_tiles;
+        const int split = tile / (p.m_tiles * p.n_tiles);
         int n0, y0, x0;
         decode_m_tile(p, m_idx, n0, y0, x0);
-        int kc_global = 0;
-        for (int s = 0; s < 3; ++s) {
+        const int k0 = split * p.k_per_split;
+        const int k1 = min(p.num_k_chunks, k0 + p.k_per_split);
+        // position (segment, tap, channel chunk) of flattened K chunk k0
+        int s = 0, rem = k0;
+        while (rem >= p.seg_taps[s] * p.seg_kchunks[s]) {
+          rem -= p.seg_taps[s] * p.seg_kchunks[s];
+          ++s;
+        }
+        int tap = rem / p.seg_kchunks[s];
+        int c = rem - tap * p.seg_kchunks[s];
+        for (int kc = k0; kc < k1; ++kc) {
           const int taps = p.seg_taps[s];
-          if (taps == 0) continue;
-          const int kch = p.seg_kchunks[s];
-          for (int tap = 0; tap < taps; ++tap) {
-            const int dy = (taps == 9) ? (tap / 3 - 1) : 0;
-            const int dx = (taps == 9) ? (tap % 3 - 1) : 0;
-            for (int c = 0; c < kch; ++c) {
-              mbar_wait(&empty_bar[stage], phase ^ 1);
-              uint8_t* sA = smem + stage * C::STAGE_BYTES;
-              uint8_t* sB = sA + A_STAGE_BYTES;
-              mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
-              tma_load_4d(sA, &p.tmA[s], &full_bar[stage], c * BK, x0 + dx, y0 + dy, n0);
-              tma_load_2d(sB, &p.tmB, &full_bar[stage], kc_global * BK, n_idx * BN);
-              ++kc_global;
-              if (++stage == C::STAGES) {
-                stage = 0;
-                phase ^= 1;
-              }
+          const int dy = (taps == 9) ? (tap / 3 - 1) : 0;
+          const int dx = (taps == 9) ? (tap % 3 - 1) : 0;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * C::STAGE_BYTES;
+          uint8_t* sB = sA + A_STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+          tma_load_4d(sA, &p.tmA[s], &full_bar[stage], c * BK, x0 + dx, y0 + dy, n0);
+          tma_load_2d(sB, &p.tmB, &full_bar[stage], kc * BK, n_idx * BN);
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+          if (++c == p.seg_kchunks[s]) {
+            c = 0;
+            if (++tap == taps) {
+              tap = 0;
+              ++s;
             }
           }
         }
@@ -225,7 +247,9 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
-        for (int kc = 0; kc < p.num_k_chunks; ++kc) {
+        const int split = tile / (p.m_tiles * p.n_tiles);
+        const int nk = min(p.num_k_chunks, (split + 1) * p.k_per_split) - split * p.k_per_split;
+        for (int kc = 0; kc < nk; ++kc) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * C::STAGE_BYTES);
@@ -255,12 +279,13 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_idx = tile % p.m_tiles;
-      const int n_idx = tile / p.m_tiles;
+      const int n_idx = (tile / p.m_tiles) % p.n_tiles;
+      const int split = tile / (p.m_tiles * p.n_tiles);
       int n0, y0, x0;
       decode_m_tile(p, m_idx, n0, y0, x0);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      epilogue_tile<BN>(p, tmem_base, acc * BN, ew, lane, n0, y0, x0, n_idx);
+      epilogue_tile<BN>(p, tmem_base, acc * BN, ew, lane, n0, y0, x0, n_idx, split);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -277,6 +302,235 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// 2-CTA variant (tcgen05 cta_group::2): a CTA PAIR of one cluster computes a (256 pixel x BN channel) tile.
+// CTA r of the pair owns M tile 2*pair+r: it loads ITS 128-row A box and HALF of the weight tile (BN/2 rows) per
+// K chunk, so the pair pulls 32 KB + BN*128 B per chunk from L2 instead of 2 x (16 KB + BN*128 B) -- the 1-CTA
+// kernel is L2->SM bandwidth bound at ~96 B/clk/SM.  The leader CTA (rank 0) issues the M=256 MMAs, which read both
+// CTAs' shared memory and write each CTA's own TMEM; every TMA of the pair signals the LEADER's full barrier; the
+// MMA commit multicasts the "stage free" / "accumulator ready" arrivals to both CTAs; the peer's epilogue warps arrive
+// remotely on the leader's "accumulator drained" barrier.
+// ------------------------------------------------------------------------------------------------
+template <int BN>
+struct Cfg2 {
+  static constexpr int B_STAGE_BYTES = (BN / 2) * BK * 2;   // this CTA's half of the weight tile
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (BN >= 256) ? 6 : (BN >= 192 ? 7 : 8);
+  static constexpr int TMEM_COLS = 512;                      // 2 accumulator buffers at columns 0 and 256
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p) {
+  using C = Cfg2<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* tmem_full = empty_bar + C::STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmB);
+    for (int s = 0; s < 3; ++s)
+      if (p.seg_taps[s]) tma_prefetch_desc(&p.tmA[s]);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);   // leader: one arrive.expect_tx covering BOTH CTAs' bytes
+      mbar_init(&empty_bar[i], 1);  // one multicast commit per use
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 8);  // 4 epilogue warps x 2 CTAs (only the leader's copy is waited on)
+    }
+    fence_barrier_init();
+  }
+  if (warp_idx == 2) {
+    tmem_alloc2(tmem_ptr, C::TMEM_COLS);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // barriers of both CTAs initialised before any remote arrival / multicast
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int m_pairs = (p.m_tiles + 1) >> 1;
+  const int total_tiles = m_pairs * p.n_tiles * p.splits;
+
+  if (warp_idx == 0) {
+    // ===================================== TMA producer (both CTAs) ==========================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = 2u * (p.a_box_bytes + C::B_STAGE_BYTES);
+      for (int tile = pair; tile < total_tiles; tile += num_pairs) {
+        const int m_idx = (tile % m_pairs) * 2 + static_cast<int>(rank);
+        const int n_idx = (tile / m_pairs) % p.n_tiles;
+        const int split = tile / (m_pairs * p.n_tiles);
+        int n0, y0, x0;
+        decode_m_tile(p, m_idx, n0, y0, x0);  // m_idx == m_tiles (odd tail): n0 >= NB -> the box is all zero-fill
+        const int k0 = split * p.k_per_split;
+        const int k1 = min(p.num_k_chunks, k0 + p.k_per_split);
+        int s = 0, rem = k0;
+        while (rem >= p.seg_taps[s] * p.seg_kchunks[s]) {
+          rem -= p.seg_taps[s] * p.seg_kchunks[s];
+          ++s;
+        }
+        int tap = rem / p.seg_kchunks[s];
+        int c = rem - tap * p.seg_kchunks[s];
+        for (int kc = k0; kc < k1; ++kc) {
+          const int taps = p.seg_taps[s];
+          const int dy = (taps == 9) ? (tap / 3 - 1) : 0;
+          const int dx = (taps == 9) ? (tap % 3 - 1) : 0;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * C::STAGE_BYTES;
+          uint8_t* sB = sA + A_STAGE_BYTES;
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+          tma2_load_4d(sA, &p.tmA[s], &full_bar[stage], c * BK, x0 + dx, y0 + dy, n0);
+          tma2_load_2d(sB, &p.tmB, &full_bar[stage], kc * BK, n_idx * BN + static_cast<int>(rank) * (BN / 2));
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+          if (++c == p.seg_kchunks[s]) {
+            c = 0;
+            if (++tap == taps) {
+              tap = 0;
+              ++s;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================================== MMA issuer (leader CTA only) ======================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(256, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < total_tiles; tile += num_pairs) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 256);
+        const int split = tile / (m_pairs * p.n_tiles);
+        const int nk = min(p.num_k_chunks, (split + 1) * p.k_per_split) - split * p.k_per_split;
+        for (int kc = 0; kc < nk; ++kc) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint64_t adesc = make_sw128_desc(a_addr);
+          const uint64_t bdesc = make_sw128_desc(a_addr + A_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma2_f16(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+                      (kc | k) != 0 ? 1u : 0u);
+          umma2_commit_mc(&empty_bar[stage], 0x3);  // the stage is free in BOTH CTAs once these MMAs retire
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma2_commit_mc(&tmem_full[acc], 0x3);  // each CTA's accumulator half is ready for its epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp_idx >= 4) {
+    // ===================================== epilogue (both CTAs, own TMEM) ====================
+    const int ew = warp_idx - 4;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const uint32_t leader_empty0 = mapa_u32(smem_u32(&tmem_empty[0]), 0);
+    const uint32_t leader_empty1 = mapa_u32(smem_u32(&tmem_empty[1]), 0);
+    for (int tile = pair; tile < total_tiles; tile += num_pairs) {
+      const int m_idx = (tile % m_pairs) * 2 + static_cast<int>(rank);
+      const int n_idx = (tile / m_pairs) % p.n_tiles;
+      const int split = tile / (m_pairs * p.n_tiles);
+      int n0, y0, x0;
+      decode_m_tile(p, m_idx, n0, y0, x0);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      epilogue_tile<BN>(p, tmem_base, acc * 256, ew, lane, n0, y0, x0, n_idx, split);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(acc ? leader_empty1 : leader_empty0);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // the peer's smem / TMEM must outlive every MMA of the pair
+  if (warp_idx == 2) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, C::TMEM_COLS);
+  }
+}
+
+template <int BN>
+int launch_bn2(const ConvGemmParams& p, cudaStream_t stream) {
+  using C = Cfg2<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    K2_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int m_pairs = (p.m_tiles + 1) / 2;
+  const int total = m_pairs * p.n_tiles * p.splits;
+  const int max_pairs = num_sms() / 2;
+  const int pairs = total < max_pairs ? total : max_pairs;
+  conv_gemm2_kernel<BN><<<2 * pairs, 256, C::SMEM_BYTES, stream>>>(p);
+  K2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// split-K second pass: out[m, n] = fp16( sum_s ws[s][m][n] (fixed order) + bias[n] + residual[m, n] )
+__global__ void __launch_bounds__(256) splitk_finalize_kernel(const float* __restrict__ ws, int splits, long long M,
+                                                              int Cout, const float* __restrict__ bias,
+                                                              const __half* __restrict__ residual, int ldr,
+                                                              __half* __restrict__ out, int ldo) {
+  const int cv = Cout / 8;
+  const long long item = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (item >= M * cv) return;
+  const long long m = item / cv;
+  const int c0 = static_cast<int>(item - m * cv) * 8;
+  float f[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) f[e] = bias ? __ldg(bias + c0 + e) : 0.f;
+  for (int s = 0; s < splits; ++s) {
+    const float4* w = reinterpret_cast<const float4*>(ws + (static_cast<long long>(s) * M + m) * Cout + c0);
+    const float4 a = __ldcs(w), b = __ldcs(w + 1);
+    f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w; f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
+  }
+  if (residual) {
+    const uint4 rv = __ldg(reinterpret_cast<const uint4*>(residual + m * ldr + c0));
+    const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 t = __half22float2(rh[e]);
+      f[2 * e] += t.x;
+      f[2 * e + 1] += t.y;
+    }
+  }
+  uint4 ov;
+  __half2* oh = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+  *reinterpret_cast<uint4*>(out + m * ldo + c0) = ov;
+}
+
 template <int BN>
 int launch_bn(const ConvGemmParams& p, cudaStream_t stream) {
   using C = Cfg<BN>;
@@ -286,7 +540,7 @@ int launch_bn(const ConvGemmParams& p, cudaStream_t stream) {
                                        C::SMEM_BYTES));
     attr_set = true;
   }
-  int total = p.m_tiles * p.n_tiles;
+  int total = p.m_tiles * p.n_tiles * p.splits;
   int grid = total < num_sms() ? total : num_sms();
   conv_gemm_kernel<BN><<<grid, 256, C::SMEM_BYTES, stream>>>(p);
   K2_CHECK_CUDA(cudaGetLastError());
@@ -295,7 +549,24 @@ int launch_bn(const ConvGemmParams& p, cudaStream_t stream) {
 
 }  // namespace
 
+int launch_splitk_finalize(const float* ws, int splits, long long M, int Cout, const float* bias, const __half* residual,
+                           int ldr, __half* out, int ldo, cudaStream_t stream) {
+  const long long items = M * (Cout / 8);
+  splitk_finalize_kernel<<<static_cast<unsigned int>((items + 255) / 256), 256, 0, stream>>>(ws, splits, M, Cout, bias,
+                                                                                             residual, ldr, out, ldo);
+  K2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int launch_conv_gemm(const ConvGemmParams& p, int BN, cudaStream_t stream) {
+  if (p.two_cta) {
+    switch (BN) {
+      case 128: return launch_bn2<128>(p, stream);
+      case 192: return launch_bn2<192>(p, stream);
+      case 256: return launch_bn2<256>(p, stream);
+      default: return fail("conv_gemm: unsupported BN for the 2-CTA kernel");
+    }
+  }
   switch (BN) {
     case 16: return launch_bn<16>(p, stream);
     case 64: return launch_bn<64>(p, stream);

@@ -48,10 +48,17 @@ struct ConvGemmParams {
   int ldr;
   void* out;
   int ldo;
-  int out_mode;        // 0: fp16 [M, ldo] rows (NHWC); 1: fp32 NCHW [NB, Cout, H, W]
+  int out_mode;        // 0: fp16 [M, ldo] rows (NHWC); 1: fp32 NCHW [NB, Cout, H, W]; 2: split-K fp32 partials -> ws
   uint32_t a_box_bytes;
+  int splits;          // split-K factor (1 = off)
+  int k_per_split;     // K chunks per split
+  float* ws;           // [splits][M_total][Cout] fp32 partial sums (out_mode 2)
+  long long M_total;
+  int two_cta;         // 1: CTA-pair kernel (cta_group::2, 256-row tiles)
 };
 int launch_conv_gemm(const ConvGemmParams& p, int BN, cudaStream_t stream);
+int launch_splitk_finalize(const float* ws, int splits, long long M, int Cout, const float* bias, const __half* residual,
+                           int ldr, __half* out, int ldo, cudaStream_t stream);
 
 // ---- fused attention, head dim 64 (k2_attention.cu) ---------------------------------------------
 struct AttnParams {

@@ -64,6 +64,18 @@ def pad_rows(wp, rows):
 # ------------------------------------------------------------------------------------------------
 # conv / GEMM
 # ------------------------------------------------------------------------------------------------
+_CONV_WS_BYTES = 256 << 20  # split-K partial tiles; fixed size and address (baked into captured CUDA graphs)
+_conv_ws = {}
+
+
+def _workspace(dev):
+    buf = _conv_ws.get(dev.index)
+    if buf is None:
+        buf = torch.empty(_CONV_WS_BYTES, dtype=torch.uint8, device=dev)
+        _conv_ws[dev.index] = buf
+    return buf
+
+
 def conv_gemm(srcs, w_packed, cout, bias=None, residual=None, out=None, out_mode=0, geom=None):
     """srcs: list of (tensor NHWC fp16 [NB,H,W,C], taps).  Returns fp16 [NB,H,W,cout] (out_mode 0) or
     fp32 NCHW [NB,cout,H,W] (out_mode 1).  geom=(NB,H,W) overrides the geometry (GEMM on flat rows)."""
@@ -85,9 +97,10 @@ def conv_gemm(srcs, w_packed, cout, bias=None, residual=None, out=None, out_mode
     ldo = _row_stride(out) if out_mode == 0 else 0
     ldr = _row_stride(residual) if residual is not None else 0
     assert w_packed.dtype == torch.float16 and w_packed.stride(1) == 1
+    ws = _workspace(t0.device)
     check(lib.k2_conv_gemm(arr, len(srcs), NB, H, W, ptr(w_packed), w_packed.shape[0], w_packed.shape[1],
                            w_packed.stride(0), cout,
-                           ptr(bias), ptr(residual), ldr, ptr(out), ldo, out_mode, stream_ptr()))
+                           ptr(bias), ptr(residual), ldr, ptr(out), ldo, out_mode, ptr(ws), ws.numel(), stream_ptr()))
     return out
 
 
@@ -323,6 +336,11 @@ def images_to_u8(x, crop_h, crop_w):
     out = torch.empty((NB, crop_h, crop_w, C), dtype=torch.uint8, device=x.device)
     check(lib.k2_images_to_u8(ptr(x), ptr(out), NB, C, H, W, crop_h, crop_w, stream_ptr()))
     return out
+
+
+def set_tuning(key, value):
+    """k2_set_tuning: key 0 = force conv N tile, key 1 = split-K (0 auto, 1 off, n forced)."""
+    check(nat.load().k2_set_tuning(int(key), int(value)))
 
 
 def launch_count():

@@ -88,3 +88,34 @@ def test_head_fp32_nchw():
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.half().float(), b, padding=1)
     assert y.shape == ref.shape and y.dtype == torch.float32
     assert (y - ref).abs().max().item() < 2e-3
+
+
+@pytest.mark.parametrize("split", [0, 1, 3, 5])
+def test_splitk_small_m(split):
+    """Bottom-of-the-U geometry (M = 8*12*12 rows, K = 9*1536): split-K partials + deterministic finalize, with bias,
+    residual and a second (1x1 skip) K segment; split 0 = automatic choice, 1 = off, n = forced."""
+    from kandinsky2 import ops
+    g = torch.Generator(device="cuda").manual_seed(4)
+    NB, H, W, Cin, Cs, Cout = 8, 12, 12, 1536, 192, 768
+    h = torch.randn(NB, H, W, Cin, device="cuda", generator=g).half()
+    xs = torch.randn(NB, H, W, Cs, device="cuda", generator=g).half()
+    res = torch.randn(NB, H, W, Cout, device="cuda", generator=g).half()
+    w3 = torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) / (3 * Cin ** 0.5)
+    w1 = torch.randn(Cout, Cs, 1, 1, device="cuda", generator=g) / Cs ** 0.5
+    b = torch.randn(Cout, device="cuda", generator=g)
+    wp = torch.cat([ops.pack_conv_weight(w3), ops.pack_conv_weight(w1)], 1).contiguous()
+    ops.set_tuning(1, split)
+    try:
+        ops.reset_launch_count()
+        y = ops.conv_gemm([(h, 9), (xs, 1)], wp, Cout, bias=b, residual=res)
+        y2 = ops.conv_gemm([(h, 9), (xs, 1)], wp, Cout, bias=b, residual=res)
+        launches = ops.launch_count()
+    finally:
+        ops.set_tuning(1, 0)
+    torch.cuda.synchronize()
+    assert torch.equal(y, y2), "split-K reduction must be deterministic"
+    if split > 1:
+        assert launches == 4  # (conv + finalize) x 2
+    ref = _ref_conv(h, w3, b, 1) + _ref_conv(xs, w1, None, 0) + res.float()
+    rel = ((y.float() - ref).norm() / ref.norm()).item()
+    assert rel < 1e-3, rel
