@@ -54,6 +54,12 @@ int k2_set_tuning(int key, int value);
  * workspace (may be NULL): caller-owned scratch for split-K.  When the tile count would leave SMs idle (small M, huge K:
  * the bottom of the U) K is split over several CTAs that write fp32 partial tiles [split][M][Cout] there, and a second
  * launch sums them in a fixed order (+bias, +residual) -- deterministic, no atomics.
+ * gn_partial (may be NULL): fp32 [m_tiles*4][Cout][2]; when given and the launch qualifies (no split-K, a tile lies
+ * inside one image, fp16 output, Cout % 32 == 0) the epilogue also emits per-32-row (sum, sum of squares) of the rounded
+ * output, which k2_gn_finalize turns into GroupNorm statistics -- the consumer's statistics pass disappears.
+ * With split-K the second pass emits them instead (16-row groups).  gn_partial must hold max(M tiles*4, M/16)*Cout*2 floats.
+ * info (HOST pointer, may be NULL): int[7] = {N tile, CTA-pair mode, split-K factor, M tiles, images per tile,
+ * gn_partial written (0 no / 1 epilogue / 2 split-K pass), row groups written in total}.
  * A plain GEMM [M,K]x[K,N] is the call with NB=1, H=1, W=M, one source with taps=1.
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
@@ -65,7 +71,8 @@ typedef struct {
 
 int k2_conv_gemm(const K2ConvSrc* srcs, int nsrc, int NB, int H, int W, const void* w_packed, int w_rows,
                  int Ktot, int ldw, int Cout, const float* bias, const void* residual, int ldr, void* out, int ldo,
-                 int out_mode, void* workspace, long long workspace_bytes, k2_stream_t stream);
+                 int out_mode, void* workspace, long long workspace_bytes, float* gn_partial, int* info,
+                 k2_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * GroupNorm (32 groups in the UNet) statistics + fused apply.
@@ -87,6 +94,10 @@ int k2_conv_gemm(const K2ConvSrc* srcs, int nsrc, int NB, int H, int W, const vo
 long long k2_gn_scratch_floats(int NB, int HW, int C);
 int k2_gn_stats(const void* src0, int C0, int ld0, const void* src1, int C1, int ld1, int NB, int HW,
                 int groups, float eps, float* stats, float* scratch, k2_stream_t stream);
+/* statistics from the partials k2_conv_gemm wrote (one or two channel-concatenated sources of the same image size);
+ * rg0 / rg1 = row groups per image of each source (info[6] / NB of the producing call). */
+int k2_gn_finalize(const float* part0, int C0, int rg0, const float* part1, int C1, int rg1, int NB, int HW, int groups,
+                   float eps, float* stats, k2_stream_t stream);
 int k2_gn_apply(const void* src0, int C0, int ld0, const void* src1, int C1, int ld1, int NB, int H, int W,
                 int groups, const float* stats, const float* gamma, const float* beta, const float* film,
                 int film_ld, int act, int resample, void* y, int ldy, void* xres, int ldx, const float* zq, int zh,

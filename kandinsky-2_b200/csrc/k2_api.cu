@@ -150,7 +150,8 @@ int k2_set_tuning(int key, int value) {
 
 int k2_conv_gemm(const K2ConvSrc* srcs, int nsrc, int NB, int H, int W, const void* w_packed, int w_rows,
                  int Ktot, int ldw, int Cout, const float* bias, const void* residual, int ldr, void* out, int ldo,
-                 int out_mode, void* workspace, long long workspace_bytes, k2_stream_t stream) {
+                 int out_mode, void* workspace, long long workspace_bytes, float* gn_partial, int* info,
+                 k2_stream_t stream) {
   K2_REQUIRE(nsrc >= 1 && nsrc <= 3, "conv_gemm: 1..3 sources");
   K2_REQUIRE(NB > 0 && H > 0 && W > 0 && Cout > 0, "conv_gemm: bad geometry");
   K2_REQUIRE(w_rows >= Cout, "conv_gemm: w_rows < Cout");
@@ -241,6 +242,24 @@ int k2_conv_gemm(const K2ConvSrc* srcs, int nsrc, int NB, int H, int W, const vo
   p.out = out;
   p.ldo = ldo;
   p.out_mode = (splits > 1) ? 2 : out_mode;
+  // fused GroupNorm partial statistics: only when a tile never straddles two images and the tile holds final values
+  // (split-K launches produce them in the second pass instead, as 16-row groups of the flat pixel order)
+  const long long HWl = static_cast<long long>(H) * W;
+  int fuse_stats = 0, row_groups = 0;
+  if (gn_partial && out_mode == 0 && Cout % 8 == 0) {
+    if (splits == 1 && p.TN == 1 && BN >= 32 && Cout % 32 == 0) {
+      fuse_stats = 1;
+      row_groups = p.m_tiles * 4;
+    } else if (splits > 1 && HWl % 16 == 0) {
+      fuse_stats = 2;
+      row_groups = static_cast<int>(p.M_total / 16);
+    }
+  }
+  p.gn_part = (fuse_stats == 1) ? reinterpret_cast<float2*>(gn_partial) : nullptr;
+  if (info) {
+    info[0] = BN; info[1] = two_cta; info[2] = splits; info[3] = p.m_tiles; info[4] = p.TN; info[5] = fuse_stats;
+    info[6] = row_groups;
+  }
   if (out_mode == 0) {
     K2_REQUIRE(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "conv_gemm: out alignment");
     if (residual)
@@ -250,6 +269,7 @@ int k2_conv_gemm(const K2ConvSrc* srcs, int nsrc, int NB, int H, int W, const vo
   if (rc == 0) g_launches.fetch_add(1, std::memory_order_relaxed);
   if (rc == 0 && splits > 1) {
     rc = launch_splitk_finalize(p.ws, splits, p.M_total, Cout, bias, p.residual, ldr, reinterpret_cast<__half*>(out), ldo,
+                                fuse_stats == 2 ? reinterpret_cast<float2*>(gn_partial) : nullptr,
                                 static_cast<cudaStream_t>(stream));
     if (rc == 0) g_launches.fetch_add(1, std::memory_order_relaxed);
   }

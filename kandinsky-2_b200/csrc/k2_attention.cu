@@ -6,7 +6,8 @@
 // flash-attn path (:303-332).  Keys/values are read from TWO buffers -- encoder tokens first, then the
 // spatial tokens -- so the concat never exists.
 //
-// One CTA = one (batch, head, 128-query tile).  Per 128-key block j:
+// One CTA = one (batch, head, 2 x 128-query tiles): two softmax warpgroups ping-pong on the tensor core, K/V tiles are
+// shared by both.  Per query tile and 128-key block j:
 //     S_j = Q K_j^T            tcgen05.mma  M128 N128 K64   -> TMEM  (S double-buffered, 2 x 128 columns)
 //     P_j = exp2(S_j*c - m)    4 softmax warps, one query row per thread: tcgen05.ld -> registers ->
 //                              fp16 -> shared memory in the 128B-swizzled K-major layout the MMA reads
@@ -27,20 +28,22 @@
 namespace k2 {
 namespace {
 
-constexpr int BQ = 128;         // queries per CTA
+constexpr int BQ = 128;         // queries per softmax warpgroup (one query tile)
+constexpr int QT = 2;           // query tiles per CTA
 constexpr int BKV = 128;        // keys per block
 constexpr int HD = 64;          // head dim
 constexpr int TILE_BYTES = 128 * HD * 2;  // 16 KB: one Q / K / V tile
 constexpr int KV_STAGES = 3;
 constexpr int P_BYTES = BQ * BKV * 2;     // 32 KB
 constexpr int SMEM_Q = 0;
-constexpr int SMEM_KV = SMEM_Q + TILE_BYTES;
+constexpr int SMEM_KV = SMEM_Q + QT * TILE_BYTES;
 constexpr int SMEM_P = SMEM_KV + KV_STAGES * 2 * TILE_BYTES;
-constexpr int SMEM_BAR = SMEM_P + 2 * P_BYTES;
+constexpr int SMEM_BAR = SMEM_P + QT * P_BYTES;
 constexpr int SMEM_TOTAL = SMEM_BAR + 256 + 1024;
 constexpr int TMEM_COLS = 512;  // S: 2 x 128, O: 2 x 64 -> 384, rounded to a power of two
-constexpr int TM_S = 0;
-constexpr int TM_O = 256;
+constexpr int TM_S = 0;         // S of tile t at TM_S + t*128
+constexpr int TM_O = 256;       // O of tile t at TM_O + t*64
+constexpr float RESCALE_GAP = 8.f;  // log2 units the running max may lag before O is rescaled (P <= 2^8 in fp16)
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -48,27 +51,30 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-__global__ void __launch_bounds__(256, 1) attention_d64_kernel(const __grid_constant__ AttnParams p) {
+// 384 threads: warp0 TMA producer, warp1 MMA issuer, warp2 TMEM allocator, warp3 idle,
+// warps 4-7 softmax warpgroup of query tile 0, warps 8-11 softmax warpgroup of query tile 1.
+__global__ void __launch_bounds__(384, 1) attention_d64_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_BAR);
-  uint64_t* q_full = bars;                 // 1
-  uint64_t* kv_full = bars + 1;            // KV_STAGES
-  uint64_t* kv_empty = kv_full + KV_STAGES;
-  uint64_t* s_full = kv_empty + KV_STAGES; // 2
-  uint64_t* p_full = s_full + 2;           // 2
-  uint64_t* o_full = p_full + 2;           // 2
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + 2);
+  uint64_t* q_full = bars;                   // 1
+  uint64_t* kv_full = bars + 1;              // KV_STAGES
+  uint64_t* kv_empty = kv_full + KV_STAGES;  // KV_STAGES
+  uint64_t* s_full = kv_empty + KV_STAGES;   // QT
+  uint64_t* p_full = s_full + QT;            // QT
+  uint64_t* o_full = p_full + QT;            // QT
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + QT);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * BQ;
+  const int q0 = blockIdx.x * (QT * BQ);
   const int head = blockIdx.y;
   const int b = blockIdx.z;
   const int nctx = (p.Tc + BKV - 1) / BKV;
   const int nsp = (p.T + BKV - 1) / BKV;
   const int nblk = nctx + nsp;
+  const int ntile = (q0 + BQ < p.T) ? 2 : 1;  // the second query tile may not exist
 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmQKV);
@@ -80,9 +86,9 @@ __global__ void __launch_bounds__(256, 1) attention_d64_kernel(const __grid_cons
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < QT; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 4);  // one arrival per softmax warp
+      mbar_init(&p_full[i], 4);  // one arrival per softmax warp of the tile
       mbar_init(&o_full[i], 1);
     }
     fence_barrier_init();
@@ -99,8 +105,9 @@ __global__ void __launch_bounds__(256, 1) attention_d64_kernel(const __grid_cons
   if (warp_idx == 0) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, TILE_BYTES);
-      tma_load_3d(smem + SMEM_Q, &p.tmQKV, q_full, head * p.hs + p.q_off, q0, b);
+      mbar_arrive_expect_tx(q_full, ntile * TILE_BYTES);
+      for (int t = 0; t < ntile; ++t)
+        tma_load_3d(smem + SMEM_Q + t * TILE_BYTES, &p.tmQKV, q_full, head * p.hs + p.q_off, q0 + t * BQ, b);
       int stage = 0;
       uint32_t phase = 0;
       for (int j = 0; j < nblk; ++j) {
@@ -124,170 +131,184 @@ __global__ void __launch_bounds__(256, 1) attention_d64_kernel(const __grid_cons
     }
   } else if (warp_idx == 1) {
     // ===================================== MMA issuer ========================================
+    // program order per key block j:  for each tile t: [P_t(j-1) V(j-1) -> O_t]  then  [Q_t K(j)^T -> S_t]
+    // so the tensor core works on one tile's products while the other tile's warpgroup exponentiates.
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_f16(BQ, BKV, 0, 0);  // Q (K-major) x K (K-major)
       constexpr uint32_t idesc_o = make_idesc_f16(BQ, HD, 0, 1);   // P (K-major) x V (MN-major)
-      const uint32_t q_addr = smem_u32(smem + SMEM_Q);
-      auto issue_s = [&](int j, int stage) {
-        const uint32_t k_addr = smem_u32(smem + SMEM_KV + stage * 2 * TILE_BYTES);
-        const uint64_t adesc = make_sw128_desc(q_addr);
-        const uint64_t bdesc = make_sw128_desc(k_addr);
-        const uint32_t d = tmem_base + TM_S + (j & 1) * BKV;
+      auto issue_pv = [&](int t, int jb, int stage_b) {
+        const uint32_t p_addr = smem_u32(smem + SMEM_P + t * P_BYTES);
+        const uint32_t v_addr = smem_u32(smem + SMEM_KV + stage_b * 2 * TILE_BYTES + TILE_BYTES);
+        const uint32_t d = tmem_base + TM_O + t * HD;
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k) {
+          // A: P [128 q][128 keys] as two 64-key swizzle atoms of 16 KB, 32 B per 16-key step
+          const uint64_t adesc = make_sw128_desc(p_addr + (k >> 2) * TILE_BYTES) + static_cast<uint64_t>((k & 3) * 2);
+          // B: V [128 keys][64 d] (MN-major): 16 keys = 16 rows of 128 B = 2048 B per step
+          const uint64_t bdesc = make_sw128_desc(v_addr + k * 2048);
+          umma_f16(d, adesc, bdesc, idesc_o, (jb > 0 || k > 0) ? 1u : 0u);
+        }
+      };
+      auto issue_s = [&](int t, int stage_b) {
+        const uint64_t adesc = make_sw128_desc(smem_u32(smem + SMEM_Q + t * TILE_BYTES));
+        const uint64_t bdesc = make_sw128_desc(smem_u32(smem + SMEM_KV + stage_b * 2 * TILE_BYTES));
+        const uint32_t d = tmem_base + TM_S + t * BKV;
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
           umma_f16(d, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc_s, k != 0);
-        umma_commit(&s_full[j & 1]);
+        umma_commit(&s_full[t]);
       };
       mbar_wait(q_full, 0);
-      int stage = 0;        // stage of block j
-      uint32_t phase = 0;   // phase of block j's stage
-      mbar_wait(&kv_full[0], 0);
-      tc_fence_after();
-      issue_s(0, 0);
+      int stage = 0, pstage = 0;
+      uint32_t phase = 0;
       for (int j = 0; j < nblk; ++j) {
-        int nstage = stage + 1;
-        uint32_t nphase = phase;
-        if (nstage == KV_STAGES) {
-          nstage = 0;
-          nphase ^= 1;
-        }
-        if (j + 1 < nblk) {
-          mbar_wait(&kv_full[nstage], nphase);
-          tc_fence_after();
-          issue_s(j + 1, nstage);
-        }
-        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+        mbar_wait(&kv_full[stage], phase);
         tc_fence_after();
-        {
-          const uint32_t p_addr = smem_u32(smem + SMEM_P + (j & 1) * P_BYTES);
-          const uint32_t v_addr = smem_u32(smem + SMEM_KV + stage * 2 * TILE_BYTES + TILE_BYTES);
-          const uint32_t d = tmem_base + TM_O + (j & 1) * HD;
-#pragma unroll
-          for (int k = 0; k < BKV / 16; ++k) {
-            // A: P row-major [128 q][128 keys] as two 64-key swizzle atoms of 16 KB; 32 B per 16-key step
-            const uint64_t adesc = make_sw128_desc(p_addr + (k >> 2) * TILE_BYTES) + static_cast<uint64_t>((k & 3) * 2);
-            // B: V [128 keys][64 d] (MN-major): 16 keys = 16 rows of 128 B = 2048 B per step
-            const uint64_t bdesc = make_sw128_desc(v_addr + k * 2048);
-            umma_f16(d, adesc, bdesc, idesc_o, k != 0);
+        for (int t = 0; t < ntile; ++t) {
+          if (j > 0) {
+            mbar_wait(&p_full[t], (j - 1) & 1);
+            tc_fence_after();
+            issue_pv(t, j - 1, pstage);
+            if (t == ntile - 1) umma_commit(&kv_empty[pstage]);
           }
+          issue_s(t, stage);
         }
-        umma_commit(&kv_empty[stage]);
-        umma_commit(&o_full[j & 1]);
-        stage = nstage;
-        phase = nphase;
+        pstage = stage;
+        if (++stage == KV_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      for (int t = 0; t < ntile; ++t) {
+        mbar_wait(&p_full[t], (nblk - 1) & 1);
+        tc_fence_after();
+        issue_pv(t, nblk - 1, pstage);
+        umma_commit(&o_full[t]);
       }
     }
   } else if (warp_idx >= 4) {
-    // ===================================== softmax + epilogue =================================
-    const int ew = warp_idx - 4;
-    const int row = ew * 32 + lane;  // query row in the tile == TMEM lane
-    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
-    float acc[HD];
-#pragma unroll
-    for (int d = 0; d < HD; ++d) acc[d] = 0.f;
-    float m_run = -INFINITY;  // running max of the scaled (log2 domain) scores
-    float l_run = 0.f;
-    float alpha_prev = 0.f;   // rescale factor that moves acc from the max of block j-2 to that of block j-1
-    const float c = p.scale_log2e;
+    // ===================================== softmax warpgroups + epilogue ======================
+    const int t = (warp_idx - 4) >> 2;           // query tile of this warpgroup
+    const int ew = warp_idx & 3;                  // TMEM lane quarter
+    const int row = ew * 32 + lane;               // query row in the tile == TMEM lane
+    if (t < ntile) {
+      const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
+      const uint32_t s_addr = lane_addr + TM_S + t * BKV;
+      const uint32_t o_addr = lane_addr + TM_O + t * HD;
+      uint8_t* p_row = smem + SMEM_P + t * P_BYTES + row * 128;
+      float m_used = 0.f;   // the (possibly stale) maximum the exponentials are taken against, log2 domain
+      float l_run = 0.f;
+      const float c = p.scale_log2e;
 
-    // acc = acc * alpha + O_blk  (O_blk was computed against the running max that alpha moves acc to)
-    auto fold_o = [&](int jb, float alpha) {
-      mbar_wait(&o_full[jb & 1], (jb >> 1) & 1);
-      tc_fence_after();
-      const uint32_t o_addr = lane_addr + TM_O + (jb & 1) * HD;
-      uint32_t r0[32], r1[32];
-      tmem_ld_32x32b_x32(o_addr, r0);
-      tmem_ld_32x32b_x32(o_addr + 32, r1);
-      tmem_ld_wait();
+      for (int j = 0; j < nblk; ++j) {
+        const int valid = (j < nctx) ? min(BKV, p.Tc - j * BKV) : min(BKV, p.T - (j - nctx) * BKV);
+        mbar_wait(&s_full[t], j & 1);
+        tc_fence_after();
+        uint32_t s0[32], s1[32], s2[32], s3[32];
+        tmem_ld_32x32b_x32(s_addr, s0);
+        tmem_ld_32x32b_x32(s_addr + 32, s1);
+        tmem_ld_32x32b_x32(s_addr + 64, s2);
+        tmem_ld_32x32b_x32(s_addr + 96, s3);
+        tmem_ld_wait();
+        if (valid < BKV) {  // ragged tail / short encoder block (block-uniform branch): masked scores -> -inf
+          const uint32_t ninf = __float_as_uint(-INFINITY);
 #pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        acc[e] = fmaf(acc[e], alpha, __uint_as_float(r0[e]));
-        acc[32 + e] = fmaf(acc[32 + e], alpha, __uint_as_float(r1[e]));
-      }
-    };
-
-    for (int j = 0; j < nblk; ++j) {
-      const int valid = (j < nctx) ? min(BKV, p.Tc - j * BKV) : min(BKV, p.T - (j - nctx) * BKV);
-      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
-      tc_fence_after();
-      const uint32_t s_addr = lane_addr + TM_S + (j & 1) * BKV;
-      // the whole score row of this thread: 4 TMEM loads in flight, one wait
-      uint32_t s0[32], s1[32], s2[32], s3[32];
-      tmem_ld_32x32b_x32(s_addr, s0);
-      tmem_ld_32x32b_x32(s_addr + 32, s1);
-      tmem_ld_32x32b_x32(s_addr + 64, s2);
-      tmem_ld_32x32b_x32(s_addr + 96, s3);
-      tmem_ld_wait();
-      if (valid < BKV) {  // ragged tail / short encoder block (block-uniform branch): masked scores -> -inf
-        const uint32_t ninf = __float_as_uint(-INFINITY);
+          for (int e = 0; e < 32; ++e) {
+            if (e >= valid) s0[e] = ninf;
+            if (32 + e >= valid) s1[e] = ninf;
+            if (64 + e >= valid) s2[e] = ninf;
+            if (96 + e >= valid) s3[e] = ninf;
+          }
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
         for (int e = 0; e < 32; ++e) {
-          if (e >= valid) s0[e] = ninf;
-          if (32 + e >= valid) s1[e] = ninf;
-          if (64 + e >= valid) s2[e] = ninf;
-          if (96 + e >= valid) s3[e] = ninf;
+          mx0 = fmaxf(mx0, __uint_as_float(s0[e]));
+          mx1 = fmaxf(mx1, __uint_as_float(s1[e]));
+          mx2 = fmaxf(mx2, __uint_as_float(s2[e]));
+          mx3 = fmaxf(mx3, __uint_as_float(s3[e]));
         }
+        const float m_blk = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * c;
+        if (j == 0) {
+          m_used = m_blk;
+        } else {
+          // O_t lives in TMEM and is rescaled only when some row's maximum has outgrown the stale one by 2^8:
+          // exact arithmetic either way (numerator and denominator share m_used), far fewer TMEM round trips.
+          const bool grow = m_blk > m_used + RESCALE_GAP;
+          if (__any_sync(0xffffffffu, grow)) {
+            const float m_new = grow ? m_blk : m_used;
+            const float alpha = ex2(m_used - m_new);
+#pragma unroll 1
+            for (int hhalf = 0; hhalf < 2; ++hhalf) {  // 32 columns at a time: the score row stays live in registers
+              uint32_t o[32];
+              tmem_ld_32x32b_x32(o_addr + hhalf * 32, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+              tmem_st_32x32b_x32(o_addr + hhalf * 32, o);
+            }
+            tmem_st_wait();
+            l_run *= alpha;
+            m_used = m_new;
+          }
+        }
+        // P = exp2(S*c - m_used) -> fp16 -> swizzled shared memory (K-major A operand of the PV product)
+        float l0 = 0.f, l1 = 0.f;
+        auto emit = [&](const uint32_t (&sv)[32], int ch) {
+          uint32_t packed[16];
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const float p0 = ex2(fmaf(__uint_as_float(sv[e]), c, -m_used));
+            const float p1 = ex2(fmaf(__uint_as_float(sv[e + 1]), c, -m_used));
+            l0 += p0;
+            l1 += p1;
+            __half2 h = __floats2half2_rn(p0, p1);
+            packed[e >> 1] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          // 32 keys = 4 chunks of 16 B; key group ch -> swizzle atom (ch>>1), chunks (ch&1)*4 .. +3
+          uint8_t* atom = p_row + (ch >> 1) * TILE_BYTES;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int cc = (ch & 1) * 4 + q;
+            *reinterpret_cast<uint4*>(atom + ((cc ^ (row & 7)) << 4)) =
+                make_uint4(packed[q * 4], packed[q * 4 + 1], packed[q * 4 + 2], packed[q * 4 + 3]);
+          }
+        };
+        emit(s0, 0);
+        emit(s1, 1);
+        emit(s2, 2);
+        emit(s3, 3);
+        l_run += l0 + l1;
+        // P_t(j) visible to the async proxy, S_t / O_t accesses retired -> let the MMA warp go
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[t]);
       }
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+      // epilogue: O / l
+      mbar_wait(&o_full[t], 0);
+      tc_fence_after();
+      uint32_t o0[32], o1[32];
+      tmem_ld_32x32b_x32(o_addr, o0);
+      tmem_ld_32x32b_x32(o_addr + 32, o1);
+      tmem_ld_wait();
+      const int q = q0 + t * BQ + row;
+      if (q < p.T) {
+        const float inv = 1.f / l_run;
+        __half* orow = p.out + (static_cast<long long>(b) * p.T + q) * p.ldo + head * HD;
 #pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        mx0 = fmaxf(mx0, __uint_as_float(s0[e]));
-        mx1 = fmaxf(mx1, __uint_as_float(s1[e]));
-        mx2 = fmaxf(mx2, __uint_as_float(s2[e]));
-        mx3 = fmaxf(mx3, __uint_as_float(s3[e]));
-      }
-      const float m_new = fmaxf(m_run, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * c);
-      const float alpha = ex2(m_run - m_new);  // 0 on the first block (m_run = -inf)
-      // P = exp2(S*c - m_new) -> fp16 -> swizzled shared memory (K-major A operand of the PV product)
-      uint8_t* p_row = smem + SMEM_P + (j & 1) * P_BYTES + row * 128;
-      float l0 = 0.f, l1 = 0.f;
-      auto emit = [&](const uint32_t (&sv)[32], int ch) {
-        uint32_t packed[16];
+        for (int v = 0; v < 4; ++v) {
+          uint4 ov;
+          __half2* oh = reinterpret_cast<__half2*>(&ov);
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          const float p0 = ex2(fmaf(__uint_as_float(sv[e]), c, -m_new));
-          const float p1 = ex2(fmaf(__uint_as_float(sv[e + 1]), c, -m_new));
-          l0 += p0;
-          l1 += p1;
-          __half2 h = __floats2half2_rn(p0, p1);
-          packed[e >> 1] = *reinterpret_cast<uint32_t*>(&h);
+          for (int e = 0; e < 4; ++e)
+            oh[e] = __floats2half2_rn(__uint_as_float(o0[v * 8 + 2 * e]) * inv, __uint_as_float(o0[v * 8 + 2 * e + 1]) * inv);
+          *reinterpret_cast<uint4*>(orow + v * 8) = ov;
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            oh[e] = __floats2half2_rn(__uint_as_float(o1[v * 8 + 2 * e]) * inv, __uint_as_float(o1[v * 8 + 2 * e + 1]) * inv);
+          *reinterpret_cast<uint4*>(orow + 32 + v * 8) = ov;
         }
-        // 32 keys = 4 chunks of 16 B; key group ch -> swizzle atom (ch>>1), chunks (ch&1)*4 .. +3
-        uint8_t* atom = p_row + (ch >> 1) * TILE_BYTES;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int cc = (ch & 1) * 4 + q;
-          *reinterpret_cast<uint4*>(atom + ((cc ^ (row & 7)) << 4)) =
-              make_uint4(packed[q * 4], packed[q * 4 + 1], packed[q * 4 + 2], packed[q * 4 + 3]);
-        }
-      };
-      emit(s0, 0);
-      emit(s1, 1);
-      emit(s2, 2);
-      emit(s3, 3);
-      l_run = fmaf(l_run, alpha, l0 + l1);
-      m_run = m_new;
-      // P_j visible to the async proxy, S_j reads retired -> let the MMA warp go
-      fence_proxy_async_smem();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[j & 1]);
-
-      if (j > 0) fold_o(j - 1, alpha_prev);  // overlaps with the tensor core working on P_j V_j
-      alpha_prev = alpha;
-    }
-    fold_o(nblk - 1, alpha_prev);
-    const int q = q0 + row;
-    if (q < p.T) {
-      const float inv = 1.f / l_run;
-      __half* orow = p.out + (static_cast<long long>(b) * p.T + q) * p.ldo + head * HD;
-#pragma unroll
-      for (int v = 0; v < HD / 8; ++v) {
-        uint4 ov;
-        __half2* oh = reinterpret_cast<__half2*>(&ov);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(acc[v * 8 + 2 * e] * inv, acc[v * 8 + 2 * e + 1] * inv);
-        *reinterpret_cast<uint4*>(orow + v * 8) = ov;
       }
     }
   }
@@ -308,8 +329,8 @@ int launch_attention_d64(const AttnParams& p, cudaStream_t stream) {
     K2_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     attr_set = true;
   }
-  dim3 grid((p.T + BQ - 1) / BQ, p.heads, p.B);
-  attention_d64_kernel<<<grid, 256, SMEM_TOTAL, stream>>>(p);
+  dim3 grid((p.T + QT * BQ - 1) / (QT * BQ), p.heads, p.B);
+  attention_d64_kernel<<<grid, 384, SMEM_TOTAL, stream>>>(p);
   K2_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

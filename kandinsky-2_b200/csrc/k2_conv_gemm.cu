@@ -38,7 +38,8 @@ struct Cfg {
   static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 192 ? 5 : (BN >= 128 ? 6 : 8));
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
+  static constexpr int STAT_BYTES = 4 * 32 * 33 * 4;  // epilogue transpose buffer for the fused GroupNorm statistics
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + STAT_BYTES + 1024;  // +1024 alignment slack
 };
 
 __device__ __forceinline__ void decode_m_tile(const ConvGemmParams& p, int m_idx, int& n0, int& y0,
@@ -56,7 +57,7 @@ __device__ __forceinline__ void decode_m_tile(const ConvGemmParams& p, int m_idx
 // tcgen05.ld -> + bias (+ residual) -> fp16 rows (out_mode 0) or fp32 NCHW (out_mode 1).
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t tmem_base, int acc_col, int ew, int lane,
-                                              int n0, int y0, int x0, int n_idx, int split) {
+                                              int n0, int y0, int x0, int n_idx, int split, int m_idx, float* stat_smem) {
   const int row = ew * 32 + lane;
   const int thw = p.TH * p.TW;
   constexpr int CH = (BN >= 32) ? 32 : 16;  // columns per tcgen05.ld
@@ -119,6 +120,16 @@ __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t 
 #pragma unroll
                 for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
                 *reinterpret_cast<uint4*>(orow + v * 8) = ov;
+                if constexpr (CH == 32) {
+                  if (p.gn_part) {  // keep the fp16-ROUNDED values: GroupNorm statistics are those of the stored tensor
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                      const float2 t = __half22float2(oh[e]);
+                      r[v * 8 + 2 * e] = __float_as_uint(t.x);
+                      r[v * 8 + 2 * e + 1] = __float_as_uint(t.y);
+                    }
+                  }
+                }
               }
             } else {
 #pragma unroll
@@ -144,6 +155,26 @@ __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t 
             }
           }
         }
+        if constexpr (CH == 32) {
+          // Fused GroupNorm statistics (replaces a separate read of the output tensor): per-column (sum, sum of
+          // squares) of this warp's 32 rows via a padded shared-memory transpose, written as one coalesced float2 row
+          // partial[(m_tile*4 + warp)][column]; k2_gn_finalize folds them per (image, group) in a fixed order.
+          if (p.gn_part && p.out_mode == 0 && col0 + CH <= p.Cout) {
+            float* sm = stat_smem + ew * (32 * 33);
+#pragma unroll
+            for (int e = 0; e < 32; ++e) sm[lane * 33 + e] = valid ? __uint_as_float(r[e]) : 0.f;
+            __syncwarp();
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+              const float t = sm[q * 33 + lane];
+              s1 += t;
+              s2 = fmaf(t, t, s2);
+            }
+            __syncwarp();
+            p.gn_part[(static_cast<long long>(m_idx) * 4 + ew) * p.Cout + col0 + lane] = make_float2(s1, s2);
+          }
+        }
       }
 }
 
@@ -158,6 +189,7 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
   uint64_t* tmem_full = empty_bar + C::STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* stat_smem = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -285,7 +317,7 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
       decode_m_tile(p, m_idx, n0, y0, x0);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      epilogue_tile<BN>(p, tmem_base, acc * BN, ew, lane, n0, y0, x0, n_idx, split);
+      epilogue_tile<BN>(p, tmem_base, acc * BN, ew, lane, n0, y0, x0, n_idx, split, m_idx, stat_smem);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -317,7 +349,7 @@ struct Cfg2 {
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = (BN >= 256) ? 6 : (BN >= 192 ? 7 : 8);
   static constexpr int TMEM_COLS = 512;                      // 2 accumulator buffers at columns 0 and 256
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 4 * 32 * 33 * 4 + 1024;
 };
 
 template <int BN>
@@ -332,6 +364,7 @@ conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p) {
   uint64_t* tmem_full = empty_bar + C::STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* stat_smem = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -462,7 +495,7 @@ conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p) {
       decode_m_tile(p, m_idx, n0, y0, x0);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      epilogue_tile<BN>(p, tmem_base, acc * 256, ew, lane, n0, y0, x0, n_idx, split);
+      epilogue_tile<BN>(p, tmem_base, acc * 256, ew, lane, n0, y0, x0, n_idx, split, m_idx, stat_smem);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(acc ? leader_empty1 : leader_empty0);
@@ -496,39 +529,76 @@ int launch_bn2(const ConvGemmParams& p, cudaStream_t stream) {
   return 0;
 }
 
-// split-K second pass: out[m, n] = fp16( sum_s ws[s][m][n] (fixed order) + bias[n] + residual[m, n] )
+// split-K second pass: out[m, n] = fp16( sum_s ws[s][m][n] (fixed order) + bias[n] + residual[m, n] ).
+// Block = 32 column vectors (256 channels) x 8 row lanes over 16 consecutive rows; optionally also emits the GroupNorm
+// partial statistics of its 16 rows (same format as the conv epilogue's, 16-row groups) via a shared-memory fold.
 __global__ void __launch_bounds__(256) splitk_finalize_kernel(const float* __restrict__ ws, int splits, long long M,
                                                               int Cout, const float* __restrict__ bias,
                                                               const __half* __restrict__ residual, int ldr,
-                                                              __half* __restrict__ out, int ldo) {
-  const int cv = Cout / 8;
-  const long long item = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (item >= M * cv) return;
-  const long long m = item / cv;
-  const int c0 = static_cast<int>(item - m * cv) * 8;
-  float f[8];
+                                                              __half* __restrict__ out, int ldo, float2* __restrict__ gn_part) {
+  __shared__ float red[8][32][17];
+  const int vx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c0 = (blockIdx.y * 32 + vx) * 8;
+  const long long rg = blockIdx.x;
+  float st[16];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) f[e] = bias ? __ldg(bias + c0 + e) : 0.f;
-  for (int s = 0; s < splits; ++s) {
-    const float4* w = reinterpret_cast<const float4*>(ws + (static_cast<long long>(s) * M + m) * Cout + c0);
-    const float4 a = __ldcs(w), b = __ldcs(w + 1);
-    f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w; f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
-  }
-  if (residual) {
-    const uint4 rv = __ldg(reinterpret_cast<const uint4*>(residual + m * ldr + c0));
-    const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+  for (int e = 0; e < 16; ++e) st[e] = 0.f;
+  if (c0 < Cout) {
+    float bv[8];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 t = __half22float2(rh[e]);
-      f[2 * e] += t.x;
-      f[2 * e + 1] += t.y;
+    for (int e = 0; e < 8; ++e) bv[e] = bias ? __ldg(bias + c0 + e) : 0.f;
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const long long m = rg * 16 + ry + rr * 8;
+      if (m >= M) continue;
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = bv[e];
+      for (int s = 0; s < splits; ++s) {
+        const float4* w = reinterpret_cast<const float4*>(ws + (static_cast<long long>(s) * M + m) * Cout + c0);
+        const float4 a = __ldcs(w), b = __ldcs(w + 1);
+        f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w; f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
+      }
+      if (residual) {
+        const uint4 rv = __ldg(reinterpret_cast<const uint4*>(residual + m * ldr + c0));
+        const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 t = __half22float2(rh[e]);
+          f[2 * e] += t.x;
+          f[2 * e + 1] += t.y;
+        }
+      }
+      uint4 ov;
+      __half2* oh = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        oh[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+        const float2 t = __half22float2(oh[e]);  // statistics of the ROUNDED values
+        st[2 * e] += t.x;
+        st[2 * e + 1] += t.y;
+        st[8 + 2 * e] = fmaf(t.x, t.x, st[8 + 2 * e]);
+        st[8 + 2 * e + 1] = fmaf(t.y, t.y, st[8 + 2 * e + 1]);
+      }
+      *reinterpret_cast<uint4*>(out + m * ldo + c0) = ov;
     }
   }
-  uint4 ov;
-  __half2* oh = reinterpret_cast<__half2*>(&ov);
+  if (gn_part == nullptr) return;
 #pragma unroll
-  for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
-  *reinterpret_cast<uint4*>(out + m * ldo + c0) = ov;
+  for (int e = 0; e < 16; ++e) red[ry][vx][e] = st[e];
+  __syncthreads();
+  // thread -> (column vector vx2, channel e2 of it): sums the 8 row lanes in order
+  const int vx2 = threadIdx.x >> 3, e2 = threadIdx.x & 7;
+  const int c = (blockIdx.y * 32 + vx2) * 8 + e2;
+  if (c < Cout) {
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      s1 += red[q][vx2][e2];
+      s2 += red[q][vx2][8 + e2];
+    }
+    gn_part[rg * Cout + c] = make_float2(s1, s2);
+  }
 }
 
 template <int BN>
@@ -550,10 +620,9 @@ int launch_bn(const ConvGemmParams& p, cudaStream_t stream) {
 }  // namespace
 
 int launch_splitk_finalize(const float* ws, int splits, long long M, int Cout, const float* bias, const __half* residual,
-                           int ldr, __half* out, int ldo, cudaStream_t stream) {
-  const long long items = M * (Cout / 8);
-  splitk_finalize_kernel<<<static_cast<unsigned int>((items + 255) / 256), 256, 0, stream>>>(ws, splits, M, Cout, bias,
-                                                                                             residual, ldr, out, ldo);
+                           int ldr, __half* out, int ldo, float2* gn_part, cudaStream_t stream) {
+  dim3 grid(static_cast<unsigned int>((M + 15) / 16), (Cout / 8 + 31) / 32);
+  splitk_finalize_kernel<<<grid, 256, 0, stream>>>(ws, splits, M, Cout, bias, residual, ldr, out, ldo, gn_part);
   K2_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

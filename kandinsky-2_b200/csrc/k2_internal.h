@@ -55,10 +55,11 @@ struct ConvGemmParams {
   float* ws;           // [splits][M_total][Cout] fp32 partial sums (out_mode 2)
   long long M_total;
   int two_cta;         // 1: CTA-pair kernel (cta_group::2, 256-row tiles)
+  float2* gn_part;     // [m_tiles*4][Cout] per-32-row (sum, sumsq) of the fp16-rounded output, or null
 };
 int launch_conv_gemm(const ConvGemmParams& p, int BN, cudaStream_t stream);
 int launch_splitk_finalize(const float* ws, int splits, long long M, int Cout, const float* bias, const __half* residual,
-                           int ldr, __half* out, int ldo, cudaStream_t stream);
+                           int ldr, __half* out, int ldo, float2* gn_part, cudaStream_t stream);
 
 // ---- fused attention, head dim 64 (k2_attention.cu) ---------------------------------------------
 struct AttnParams {

@@ -23,7 +23,8 @@ namespace {
 
 constexpr int VX = 16;   // channel vectors per block
 constexpr int PY = 16;   // pixel lanes per block
-constexpr int UNR = 4;   // loads in flight per thread
+constexpr int UNR = 4;   // loads in flight per thread (statistics)
+constexpr int UNA = 8;   // loads in flight per thread (apply)
 
 __device__ __forceinline__ const __half* src_ptr(const __half* s0, int C0, int ld0, const __half* s1, int ld1,
                                                  long long row, int c) {
@@ -173,6 +174,74 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const __half* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
+// finalize for statistics fused into the producing convolution's epilogue (k2_conv_gemm gn_partial):
+// partial[(tile*4 + warp)][channel] = (sum, sumsq) over 32 output rows.  One block per (image, group): fixed-order
+// fp64 fold over the image's row groups and the group's channels (which may span the two concatenated sources).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) gn_finalize_kernel(const float2* __restrict__ part0, int C0, int rg0,
+                                                          const float2* __restrict__ part1, int C1, int rg1, int HW,
+                                                          int groups, float eps, float* __restrict__ stats) {
+  __shared__ double red[2][4];
+  const int n = blockIdx.y, g = blockIdx.x;
+  const int C = C0 + C1;
+  const int cpg = C / groups;
+  // 4 independent fp32 accumulator pairs per thread (loads in flight), folded in fp64 in a fixed order
+  float fs[4] = {0.f, 0.f, 0.f, 0.f}, fq[4] = {0.f, 0.f, 0.f, 0.f};
+  // the group's channels [c_lo, c_hi) restricted to one source: part[(n*rgs + rg)][c - base]
+  auto fold = [&](const float2* part, int Cs, int base, int rgs) {
+    const int c_lo = max(g * cpg, base), c_hi = min((g + 1) * cpg, base + Cs);
+    const int w = c_hi - c_lo;
+    if (w <= 0) return;
+    const int items = rgs * w;
+    const float2* p0 = part + static_cast<long long>(n) * rgs * Cs + (c_lo - base);
+    auto load = [&](int i) {
+      const int rg = i / w;
+      return __ldg(p0 + static_cast<long long>(rg) * Cs + (i - rg * w));
+    };
+    int i = threadIdx.x;
+    for (; i + 3 * 128 < items; i += 4 * 128) {
+      float2 t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) t[u] = load(i + u * 128);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        fs[u] += t[u].x;
+        fq[u] += t[u].y;
+      }
+    }
+    for (; i < items; i += 128) {
+      const float2 t = load(i);
+      fs[0] += t.x;
+      fq[0] += t.y;
+    }
+  };
+  fold(part0, C0, 0, rg0);
+  if (C1 > 0) fold(part1, C1, C0, rg1);
+  double s = (static_cast<double>(fs[0]) + fs[1]) + (static_cast<double>(fs[2]) + fs[3]);
+  double q = (static_cast<double>(fq[0]) + fq[1]) + (static_cast<double>(fq[2]) + fq[3]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_down_sync(0xffffffffu, s, o);
+    q += __shfl_down_sync(0xffffffffu, q, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = s;
+    red[1][threadIdx.x >> 5] = q;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s = (red[0][0] + red[0][1]) + (red[0][2] + red[0][3]);
+    q = (red[1][0] + red[1][1]) + (red[1][2] + red[1][3]);
+    const double cnt = static_cast<double>(HW) * cpg;
+    const double mean = s / cnt;
+    double var = q / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[(static_cast<long long>(n) * groups + g) * 2] = static_cast<float>(mean);
+    stats[(static_cast<long long>(n) * groups + g) * 2 + 1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // apply
 // ------------------------------------------------------------------------------------------------
 struct ApplyParams {
@@ -266,15 +335,15 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const ApplyParams p) {
   };
 
   if (RESAMPLE == 0 || RESAMPLE == 2) {
-    for (int pp = p0 + py; pp < p1; pp += UNR * PY) {
-      uint4 raw[UNR];
+    for (int pp = p0 + py; pp < p1; pp += UNA * PY) {
+      uint4 raw[UNA];
 #pragma unroll
-      for (int u = 0; u < UNR; ++u) {
+      for (int u = 0; u < UNA; ++u) {
         const int q = pp + u * PY;
         if (q < p1) raw[u] = ldg16(base + (img_in + q) * ld);
       }
 #pragma unroll
-      for (int u = 0; u < UNR; ++u) {
+      for (int u = 0; u < UNA; ++u) {
         const int q = pp + u * PY;
         if (q >= p1) break;
         float f[8], o[8];
@@ -377,6 +446,19 @@ int k2_gn_stats(const void* src0, int C0, int ld0, const void* src1, int C1, int
   gn_stats_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __half*>(src0), C0, ld0, reinterpret_cast<const __half*>(src1), C1, ld1, HW, groups,
       eps, chunk, stats, partial, counters);
+  K2_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int k2_gn_finalize(const float* part0, int C0, int rg0, const float* part1, int C1, int rg1, int NB, int HW, int groups,
+                   float eps, float* stats, k2_stream_t stream) {
+  K2_REQUIRE(part0 && stats && C0 > 0 && (part1 || C1 == 0) && (C0 + C1) % groups == 0 && rg0 > 0 && (C1 == 0 || rg1 > 0),
+             "gn_finalize: bad arguments");
+  dim3 grid(groups, NB);
+  gn_finalize_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const float2*>(part0), C0, rg0, reinterpret_cast<const float2*>(part1), C1, rg1, HW, groups, eps,
+      stats);
   K2_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -33,7 +33,9 @@ SIGNATURES = {
     "k2_launch_count": (_LL, []),
     "k2_reset_launch_count": (None, []),
     "k2_set_tuning": (_I, [_I, _I]),
-    "k2_conv_gemm": (_I, [ctypes.POINTER(K2ConvSrc), _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P, _I, _P, _I, _I, _P, _LL, _P]),
+    "k2_conv_gemm": (_I, [ctypes.POINTER(K2ConvSrc), _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P, _I, _P, _I, _I, _P, _LL, _P,
+                         ctypes.POINTER(ctypes.c_int), _P]),
+    "k2_gn_finalize": (_I, [_P, _I, _I, _P, _I, _I, _I, _I, _I, _F, _P, _P]),
     "k2_upsample2x_nhwc": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _P]),
     "k2_softmax_rows": (_I, [_P, _I, _P, _I, _LL, _I, _F, _P]),
     "k2_gn_scratch_floats": (_LL, [_I, _I, _I]),

@@ -368,6 +368,7 @@ class _Plan:
         self.out = torch.empty(N, model.out_channels, H, W, **f32)
         self.xf_proj = torch.zeros(N, 4 * model.model_channels, **f32)
         self.enc_kv = {}
+        self._parts = {}
         self._scratch = {}
         self.steps = []
         self.graph = None
@@ -375,12 +376,12 @@ class _Plan:
         self._build()
 
     # buffers -----------------------------------------------------------------------------------
-    def _tmp(self, slot, *shape):
+    def _tmp(self, slot, *shape, dtype=torch.float16):
         """Scratch reused by every block that asks for the same (slot, shape): all launches are stream-ordered
         and a block's temporaries are dead when the next block starts."""
-        key = (slot,) + tuple(shape)
+        key = (slot, dtype) + tuple(shape)
         if key not in self._scratch:
-            self._scratch[key] = torch.empty(*shape, device=self.dev, dtype=torch.float16)
+            self._scratch[key] = torch.empty(*shape, device=self.dev, dtype=dtype)
         return self._scratch[key]
 
     def _new(self, *shape, dtype=torch.float16):
@@ -426,8 +427,7 @@ class _Plan:
             S(lambda: ops.stem_im2col(self.x_in, self.img_in, self.mask_in, mul23=True, kpad=kpad, out=patches), "stem_im2col")
         else:
             S(lambda: ops.stem_im2col(self.x_in, kpad=kpad, out=patches), "stem_im2col")
-        S(lambda h=h: ops.gemm_rows(patches, pk["stem_w"], h.shape[-1], bias=pk["stem_b"], out=h), "conv_gemm",
-          2 * N * H * W * h.shape[-1] * 9 * cin)
+        self._conv([(patches, 1)], pk["stem_w"], h.shape[-1], h, 2 * N * H * W * h.shape[-1] * 9 * cin, bias=pk["stem_b"])
         hs = [h]
         for bi, blk in enumerate(inp[1:], start=1):
             for li, layer in enumerate(blk):
@@ -442,7 +442,7 @@ class _Plan:
         # head: GN32 + SiLU + conv3x3 -> fp32 NCHW (unet.py:559-563; text2im_model2_1.py:101-102)
         st = self._new(N, 32, 2, dtype=torch.float32)
         hn = self._tmp("h1", *h.shape)
-        S(lambda h=h: ops.gn_stats(h, None, stats=st), "gn_stats")
+        self._stats(h, None, st)
         S(lambda h=h: ops.gn_apply(h, None, st, pk["out_g"], pk["out_b"], act=1, y=hn), "gn_apply")
         S(lambda: ops.conv_gemm([(hn, 9)], pk["out_w"], m.out_channels, bias=pk["out_c"], out=self.out, out_mode=1),
           "conv_gemm", 2 * N * H * W * m.out_channels * 9 * h.shape[-1])
@@ -461,23 +461,22 @@ class _Plan:
             h3 = self._tmp("h3", N, Ho, Wo, cout)
             o = self._new(N, Ho, Wo, cout)
             film = self.film[:, d["film_off"]:d["film_off"] + 2 * cout]
-            S(lambda: ops.gn_stats(a, b, stats=st1), "gn_stats")
+            self._stats(a, b, st1)
             if updown is None:
                 xres = None
                 S(lambda: ops.gn_apply(a, b, st1, d["g1"], d["b1"], act=1, y=h1), "gn_apply")
             else:
                 xres = self._tmp("xres", N, Ho, Wo, cin)
                 S(lambda: ops.gn_apply(a, b, st1, d["g1"], d["b1"], act=1, resample=1 if updown == "down" else 2,
-                                            y=h1, xres=xres))
-            S(lambda: ops.conv_gemm([(h1, 9)], d["w1"], cout, bias=d["c1"], out=h2), "conv_gemm", 2 * N * Ho * Wo * cout * 9 * cin)
-            S(lambda: ops.gn_stats(h2, None, stats=st2), "gn_stats")
+                                       y=h1, xres=xres), "gn_apply")
+            self._conv([(h1, 9)], d["w1"], cout, h2, 2 * N * Ho * Wo * cout * 9 * cin, bias=d["c1"], part_slot="part_h2")
+            self._stats(h2, None, st2)
             S(lambda: ops.gn_apply(h2, None, st2, d["g2"], d["b2"], film=film, act=1, y=h3), "gn_apply")
             if cin == cout:
                 if b is not None:
                     raise NotImplementedError("identity skip over a concatenated input")
                 res = xres if xres is not None else a
-                S(lambda: ops.conv_gemm([(h3, 9)], d["w2"], cout, bias=d["c2"], residual=res, out=o), "conv_gemm",
-                  2 * N * Ho * Wo * cout * 9 * cout)
+                self._conv([(h3, 9)], d["w2"], cout, o, 2 * N * Ho * Wo * cout * 9 * cout, bias=d["c2"], residual=res)
             else:
                 if updown is not None:
                     raise NotImplementedError("resampling ResBlock with a channel change")
@@ -485,8 +484,7 @@ class _Plan:
                 c1 = b.shape[-1] if b is not None else 0
                 wcat = self.m._skip_weight(d, c0, c1)
                 srcs = [(h3, 9), (a, 1)] + ([(b, 1)] if b is not None else [])
-                S(lambda: ops.conv_gemm(srcs, wcat, cout, bias=d["c2"], out=o), "conv_gemm",
-                  2 * N * Ho * Wo * cout * (9 * cout + cin))
+                self._conv(srcs, wcat, cout, o, 2 * N * Ho * Wo * cout * (9 * cout + cin), bias=d["c2"])
             return o
         # attention
         ch = layer[1]
@@ -502,16 +500,46 @@ class _Plan:
         ctx = self.m.cache["xf_out"].shape[1]
         enc = self._new(N, ctx, 2 * ch)
         self.enc_kv[p] = enc
-        S(lambda: ops.gn_stats(a, None, stats=st), "gn_stats")
+        self._stats(a, None, st)
         S(lambda: ops.gn_apply(a, None, st, d["g"], d["b"], act=0, y=xn), "gn_apply")
         S(lambda: ops.gemm_rows(xn.view(N, T, ch), d["wqkv"], 3 * ch, bias=d["bqkv"], out=qkv), "conv_gemm", 2 * N * T * 3 * ch * ch)
         S(lambda: ops.attention_d64(qkv, heads, enc, out=att), "attention", 4 * N * T * (T + ctx) * ch)
-        S(lambda: ops.gemm_rows(att, d["wproj"], ch, bias=d["bproj"], residual=a.view(N, T, ch), out=o.view(N, T, ch)),
-          "conv_gemm", 2 * N * T * ch * ch)
+        self._conv([(att.view(N, Hh, Ww, ch), 1)], d["wproj"], ch, o, 2 * N * T * ch * ch, bias=d["bproj"], residual=a)
         return o
 
     def _add(self, fn, kind="misc", flops=0):
+        """Record a launch AND run it once now (build = eager trace), so that data-dependent plan decisions -- did the
+        conv epilogue emit GroupNorm partials for this geometry? -- are known when the next step is recorded."""
+        fn()
         self.steps.append((fn, kind, flops))
+
+    def _conv(self, srcs, w, cout, out, flops, bias=None, residual=None, want_stats=True, part_slot=None):
+        """conv_gemm step; with want_stats the epilogue also writes GroupNorm partial statistics of `out` (when the
+        launch geometry allows it: k2b200.h), remembered in self._parts for the consumer's _stats()."""
+        N = self.N
+        part = None
+        if want_stats:
+            n = ops.gn_part_floats(N, out.shape[1], out.shape[2], cout)
+            part = self._tmp(part_slot, n, dtype=torch.float32) if part_slot else self._new(n, dtype=torch.float32)
+        info = [0] * 7
+        self._add(lambda: ops.conv_gemm(srcs, w, cout, bias=bias, residual=residual, out=out, gn_part=part, info=info),
+                  "conv_gemm", flops)
+        if want_stats and info[5]:
+            self._parts[out.data_ptr()] = (part, info[6] // N)
+        else:
+            self._parts.pop(out.data_ptr(), None)
+
+    def _stats(self, a, b, st):
+        """GroupNorm statistics of [a | b]: from the producers' fused partials when both have them, else a read pass."""
+        pa = self._parts.get(a.data_ptr())
+        pb = self._parts.get(b.data_ptr()) if b is not None else None
+        HW = a.shape[1] * a.shape[2]
+        if pa is not None and (b is None or pb is not None):
+            c1 = b.shape[-1] if b is not None else 0
+            self._add(lambda: ops.gn_finalize(pa[0], a.shape[-1], pb[0] if pb else None, c1, self.N, pa[1], HW, st,
+                                              rg1=pb[1] if pb else None), "gn_finalize")
+        else:
+            self._add(lambda: ops.gn_stats(a, b, stats=st), "gn_stats")
 
     # execution ---------------------------------------------------------------------------------
     def launch(self):

@@ -76,7 +76,7 @@ def _workspace(dev):
     return buf
 
 
-def conv_gemm(srcs, w_packed, cout, bias=None, residual=None, out=None, out_mode=0, geom=None):
+def conv_gemm(srcs, w_packed, cout, bias=None, residual=None, out=None, out_mode=0, geom=None, gn_part=None, info=None):
     """srcs: list of (tensor NHWC fp16 [NB,H,W,C], taps).  Returns fp16 [NB,H,W,cout] (out_mode 0) or
     fp32 NCHW [NB,cout,H,W] (out_mode 1).  geom=(NB,H,W) overrides the geometry (GEMM on flat rows)."""
     lib = nat.load()
@@ -98,9 +98,13 @@ def conv_gemm(srcs, w_packed, cout, bias=None, residual=None, out=None, out_mode
     ldr = _row_stride(residual) if residual is not None else 0
     assert w_packed.dtype == torch.float16 and w_packed.stride(1) == 1
     ws = _workspace(t0.device)
+    _info = (ctypes.c_int * 7)()
     check(lib.k2_conv_gemm(arr, len(srcs), NB, H, W, ptr(w_packed), w_packed.shape[0], w_packed.shape[1],
                            w_packed.stride(0), cout,
-                           ptr(bias), ptr(residual), ldr, ptr(out), ldo, out_mode, ptr(ws), ws.numel(), stream_ptr()))
+                           ptr(bias), ptr(residual), ldr, ptr(out), ldo, out_mode, ptr(ws), ws.numel(), ptr(gn_part),
+                           _info, stream_ptr()))
+    if info is not None:
+        info[:] = list(_info)
     return out
 
 
@@ -155,6 +159,20 @@ def gn_stats(x0, x1=None, groups=32, eps=1e-5, stats=None):
     scratch = _scratch(x0.device, need)
     check(lib.k2_gn_stats(ptr(x0), C0, _row_stride(x0), ptr(x1), C1, _row_stride(x1) if x1 is not None else 0,
                           NB, H * W, groups, eps, ptr(stats), ptr(scratch), stream_ptr()))
+    return stats
+
+
+def gn_part_floats(NB, H, W, cout):
+    """Upper bound of the fp32 count of a conv's fused-statistics partial buffer ([m_tiles*4][cout][2])."""
+    tiles = NB * ((H * W + 63) // 64 + 2 * H)  # generous: boxes are >= 64 pixels except at ragged edges
+    return max(tiles * 4, (NB * H * W + 15) // 16) * cout * 2
+
+
+def gn_finalize(part0, C0, part1, C1, NB, rg_per_image, HW, stats, groups=32, eps=1e-5, rg1=None):
+    """rg_per_image: row groups per image of source 0 (and of source 1 unless rg1 is given)."""
+    lib = nat.load()
+    check(lib.k2_gn_finalize(ptr(part0), C0, rg_per_image, ptr(part1), C1, rg1 if rg1 is not None else rg_per_image, NB, HW,
+                             groups, eps, ptr(stats), stream_ptr()))
     return stats
 
 

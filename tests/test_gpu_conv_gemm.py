@@ -119,3 +119,54 @@ def test_splitk_small_m(split):
     ref = _ref_conv(h, w3, b, 1) + _ref_conv(xs, w1, None, 0) + res.float()
     rel = ((y.float() - ref).norm() / ref.norm()).item()
     assert rel < 1e-3, rel
+
+
+@pytest.mark.parametrize("two_cta", [1, 2])
+@pytest.mark.parametrize("NB,H,W,Cin,Cout,C1", [(2, 24, 24, 128, 256, 0), (3, 16, 12, 64, 384, 128), (1, 96, 96, 64, 192, 0)])
+def test_conv_fused_groupnorm_partials(two_cta, NB, H, W, Cin, Cout, C1):
+    """The conv epilogue's per-32-row (sum, sumsq) partials + k2_gn_finalize == a statistics pass over the stored output
+    (also over the concat with a second producer's output)."""
+    from kandinsky2 import ops
+    g = torch.Generator(device="cuda").manual_seed(8)
+    ops.set_tuning(2, two_cta)
+    try:
+        outs, parts, rg = [], [], None
+        for cout in [Cout] + ([C1] if C1 else []):
+            x = torch.randn(NB, H, W, Cin, device="cuda", generator=g).half()
+            w = torch.randn(cout, Cin, 3, 3, device="cuda", generator=g) / (3 * Cin ** 0.5)
+            b = torch.randn(cout, device="cuda", generator=g)
+            res = torch.randn(NB, H, W, cout, device="cuda", generator=g).half()
+            part = torch.zeros(ops.gn_part_floats(NB, H, W, cout), device="cuda")
+            info = [0] * 7
+            y = ops.conv_gemm([(x, 9)], ops.pack_conv_weight(w), cout, bias=b, residual=res, gn_part=part, info=info)
+            assert info[5] == 1 and info[4] == 1 and info[2] == 1, info
+            rg = info[6] // NB
+            outs.append(y)
+            parts.append(part)
+    finally:
+        ops.set_tuning(2, 0)
+    st = torch.empty(NB, 32, 2, device="cuda")
+    ops.gn_finalize(parts[0], Cout, parts[1] if C1 else None, C1, NB, rg, H * W, st)
+    ref = ops.gn_stats(outs[0], outs[1] if C1 else None)
+    torch.cuda.synchronize()
+    assert torch.allclose(st[..., 0], ref[..., 0], atol=2e-5), (st[..., 0] - ref[..., 0]).abs().max()
+    assert torch.allclose(st[..., 1], ref[..., 1], rtol=2e-5)
+
+
+def test_splitk_fused_groupnorm_partials():
+    """split-K second pass emits the partial statistics (16-row groups) of its rounded output."""
+    from kandinsky2 import ops
+    g = torch.Generator(device="cuda").manual_seed(9)
+    NB, H, W, Cin, Cout = 8, 12, 12, 1536, 1536
+    x = torch.randn(NB, H, W, Cin, device="cuda", generator=g).half()
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) / (3 * Cin ** 0.5)
+    b = torch.randn(Cout, device="cuda", generator=g)
+    part = torch.zeros(ops.gn_part_floats(NB, H, W, Cout), device="cuda")
+    info = [0] * 7
+    y = ops.conv_gemm([(x, 9)], ops.pack_conv_weight(w), Cout, bias=b, gn_part=part, info=info)
+    assert info[2] > 1 and info[5] == 2 and info[6] == NB * H * W // 16, info
+    st = torch.empty(NB, 32, 2, device="cuda")
+    ops.gn_finalize(part, Cout, None, 0, NB, info[6] // NB, H * W, st)
+    ref = ops.gn_stats(y, None)
+    torch.cuda.synchronize()
+    assert torch.allclose(st[..., 0], ref[..., 0], atol=2e-5) and torch.allclose(st[..., 1], ref[..., 1], rtol=2e-5)
