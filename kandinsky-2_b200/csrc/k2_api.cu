@@ -17,6 +17,7 @@ static std::atomic<long long> g_launches{0};
 static int g_force_bn = 0;
 static int g_force_split = 0;  // 0 auto, 1 off, n>1 forced
 static int g_force_2cta = 0;   // 0 auto, 1 off, 2 on
+static int g_halo_mode = 0;    // 0 off; 1/2: dense halo rows (pitch 10) without/with base offset; 3/4: pitch 16
 
 
 void set_error(const std::string& msg) { g_err = msg; }
@@ -144,6 +145,10 @@ int k2_set_tuning(int key, int value) {
     g_force_2cta = value;
     return 0;
   }
+  if (key == 3) {
+    g_halo_mode = value;
+    return 0;
+  }
 
   return fail("k2_set_tuning: unknown key");
 }
@@ -164,7 +169,24 @@ int k2_conv_gemm(const K2ConvSrc* srcs, int nsrc, int NB, int H, int W, const vo
   p.NB = NB;
   p.H = H;
   p.W = W;
-  choose_tile(NB, H, W, p.TN, p.TH, p.TW);
+  // halo kernel (one (8+2)x(16+2) activation box per K chunk instead of nine shifted boxes): 3x3 convolutions whose
+  // image tiles exactly into 8 x 16 pixel boxes -- levels 0-1 of the UNet, where ~70 % of the conv FLOPs are
+  bool any9 = false;
+  for (int s = 0; s < nsrc; ++s) any9 = any9 || srcs[s].taps == 9;
+  int halo_pitch = 0, halo_bo = 0;
+  if (g_halo_mode > 0 && any9 && W % 8 == 0 && H % 16 == 0 && out_mode == 0 && Cout > 64 && g_force_2cta != 1) {
+    halo_pitch = (g_halo_mode <= 2) ? 10 : 16;
+    halo_bo = (g_halo_mode == 2 || g_halo_mode == 4) ? 1 : 0;
+  }
+  if (halo_pitch) {
+    p.TN = 1;
+    p.TH = 16;
+    p.TW = 8;
+  } else {
+    choose_tile(NB, H, W, p.TN, p.TH, p.TW);
+  }
+  p.halo_pitch = halo_pitch;
+  p.halo_bo = halo_bo;
   p.tiles_w = (W + p.TW - 1) / p.TW;
   p.tiles_h = (H + p.TH - 1) / p.TH;
   p.tiles_n = (NB + p.TN - 1) / p.TN;
@@ -185,6 +207,10 @@ int k2_conv_gemm(const K2ConvSrc* srcs, int nsrc, int NB, int H, int W, const vo
     uint64_t str[3] = {static_cast<uint64_t>(src.ld) * 2, static_cast<uint64_t>(src.ld) * 2 * W,
                        static_cast<uint64_t>(src.ld) * 2 * W * H};
     uint32_t box[4] = {64, static_cast<uint32_t>(p.TW), static_cast<uint32_t>(p.TH), static_cast<uint32_t>(p.TN)};
+    if (halo_pitch && src.taps == 9) {
+      box[1] = static_cast<uint32_t>(halo_pitch);
+      box[2] = 18;
+    }
     if (encode_tmap_f16(&p.tmA[s], src.ptr, 4, dims, str, box)) return -1;
   }
   K2_REQUIRE(kchunks * 64 == Ktot, "conv_gemm: Ktot does not match the sources (taps * ceil(C/64)*64 summed)");
@@ -208,7 +234,8 @@ int k2_conv_gemm(const K2ConvSrc* srcs, int nsrc, int NB, int H, int W, const vo
     else BN = 256;
   }
   if (two_cta && BN < 128) two_cta = 0;
-  {
+  if (halo_pitch) two_cta = 1;
+  if (!halo_pitch) {
     const long long M_total = static_cast<long long>(NB) * H * W;
     const int nt = (Cout + BN - 1) / BN;
     const long long units = static_cast<long long>(two_cta ? (p.m_tiles + 1) / 2 : p.m_tiles) * nt;

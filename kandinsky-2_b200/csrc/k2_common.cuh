@@ -213,6 +213,18 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;             // SWIZZLE_128B
   return d;
 }
+// General form: explicit stride between 8-row groups (SBO) and matrix base offset (bits [49,52): the phase of the
+// 128B-swizzle pattern at the start address, (addr >> 7) & 7, for operands that do not start on a 1024 B boundary).
+__device__ __forceinline__ uint64_t make_sw128_desc_ex(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t base_offset) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(base_offset & 7) << 49;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
 // Instruction descriptor for kind::f16, fp16 A/B, fp32 accumulate.
 //   [4,6) c_format=1 (f32) | [7,10) a_format=0 (f16) | [10,13) b_format=0 | 15 a_major | 16 b_major
 //   [17,23) N>>3 | [24,29) M>>4

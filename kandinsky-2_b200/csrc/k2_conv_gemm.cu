@@ -529,6 +529,231 @@ int launch_bn2(const ConvGemmParams& p, cudaStream_t stream) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Halo variant of the CTA-pair kernel for 3x3 convolutions: the 1-/2-CTA kernels above fetch the SAME activation
+// pixels nine times (one shifted 128-pixel box per tap), and L2->SM operand bandwidth (~64 B/clk/SM) is what bounds
+// them.  Here an M tile is 8 wide x 16 high and ONE (8+2) x (16+2) halo box per 64-channel chunk is staged in shared
+// memory; the nine taps are nine tcgen05 A descriptors into that box: a row of 8 output pixels is 8 consecutive 128 B
+// halo rows (one 8-row core group), the next output row starts `pitch` halo pixels later, so the stride between core
+// groups is pitch*128 B and tap (dy, dx) only moves the start address by ((1+dy)*pitch + 1+dx)*128 B.  Activation
+// traffic per chunk drops from 9 x 16 KB to one box; the weight tiles (one per tap) are unchanged.
+// ------------------------------------------------------------------------------------------------
+template <int BN>
+struct Cfg3 {
+  static constexpr int A_STAGE = 36864;                    // 18 rows x (up to) 16 pixels x 128 B
+  static constexpr int A_STAGES = 3;
+  static constexpr int B_STAGE = (BN / 2) * BK * 2;
+  static constexpr int B_STAGES = (BN >= 256) ? 4 : 5;
+  static constexpr int BAR_OFF = A_STAGES * A_STAGE + B_STAGES * B_STAGE;
+  static constexpr int STAT_OFF = BAR_OFF + 256;
+  static constexpr int SMEM_BYTES = STAT_OFF + 4 * 32 * 33 * 4 + 1024;
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+conv_gemm3_kernel(const __grid_constant__ ConvGemmParams p) {
+  using C = Cfg3<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smemB = smem + C::A_STAGES * C::A_STAGE;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + C::BAR_OFF);
+  uint64_t* a_empty = a_full + C::A_STAGES;
+  uint64_t* b_full = a_empty + C::A_STAGES;
+  uint64_t* b_empty = b_full + C::B_STAGES;
+  uint64_t* tmem_full = b_empty + C::B_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* stat_smem = reinterpret_cast<float*>(smem + C::STAT_OFF);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  const int pitch = p.halo_pitch;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmB);
+    for (int s = 0; s < 3; ++s)
+      if (p.seg_taps[s]) tma_prefetch_desc(&p.tmA[s]);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    for (int i = 0; i < C::A_STAGES; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < C::B_STAGES; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp_idx == 2) {
+    tmem_alloc2(tmem_ptr, 512);
+    tmem_relinquish2();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int m_pairs = (p.m_tiles + 1) >> 1;
+  const int total_tiles = m_pairs * p.n_tiles;
+
+  if (warp_idx == 0) {
+    // ===================================== TMA producer (both CTAs) ==========================
+    if (lane == 0) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      const uint32_t halo_bytes = static_cast<uint32_t>(18 * pitch * 128);
+      for (int tile = pair; tile < total_tiles; tile += num_pairs) {
+        const int m_idx = (tile % m_pairs) * 2 + static_cast<int>(rank);
+        const int n_idx = tile / m_pairs;
+        int n0, y0, x0;
+        decode_m_tile(p, m_idx, n0, y0, x0);
+        int kc_base = 0;
+        for (int s = 0; s < 3; ++s) {
+          const int taps = p.seg_taps[s];
+          if (taps == 0) break;
+          const int kch = p.seg_kchunks[s];
+          for (int c = 0; c < kch; ++c) {
+            mbar_wait(&a_empty[as], aph ^ 1);
+            uint8_t* sA = smem + as * C::A_STAGE;
+            if (taps == 9) {
+              if (rank == 0) mbar_arrive_expect_tx(&a_full[as], 2u * halo_bytes);
+              tma2_load_4d(sA, &p.tmA[s], &a_full[as], c * BK, x0 - 1, y0 - 1, n0);
+            } else {
+              if (rank == 0) mbar_arrive_expect_tx(&a_full[as], 2u * A_STAGE_BYTES);
+              tma2_load_4d(sA, &p.tmA[s], &a_full[as], c * BK, x0, y0, n0);
+            }
+            if (++as == C::A_STAGES) {
+              as = 0;
+              aph ^= 1;
+            }
+            for (int tap = 0; tap < taps; ++tap) {
+              mbar_wait(&b_empty[bs], bph ^ 1);
+              if (rank == 0) mbar_arrive_expect_tx(&b_full[bs], 2u * C::B_STAGE);
+              tma2_load_2d(smemB + bs * C::B_STAGE, &p.tmB, &b_full[bs], (kc_base + tap * kch + c) * BK,
+                           n_idx * BN + static_cast<int>(rank) * (BN / 2));
+              if (++bs == C::B_STAGES) {
+                bs = 0;
+                bph ^= 1;
+              }
+            }
+          }
+          kc_base += taps * kch;
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================================== MMA issuer (leader CTA only) ======================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(256, BN, 0, 0);
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < total_tiles; tile += num_pairs) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 256);
+        uint32_t first = 1;
+        for (int s = 0; s < 3; ++s) {
+          const int taps = p.seg_taps[s];
+          if (taps == 0) break;
+          const int kch = p.seg_kchunks[s];
+          for (int c = 0; c < kch; ++c) {
+            mbar_wait(&a_full[as], aph);
+            tc_fence_after();
+            const uint32_t a_base = smem_u32(smem + as * C::A_STAGE);
+            for (int tap = 0; tap < taps; ++tap) {
+              mbar_wait(&b_full[bs], bph);
+              tc_fence_after();
+              uint64_t adesc;
+              if (taps == 9) {
+                const uint32_t start = a_base + static_cast<uint32_t>(((tap / 3) * pitch + (tap % 3)) * 128);
+                adesc = make_sw128_desc_ex(start, static_cast<uint32_t>(pitch * 128), p.halo_bo ? (start >> 7) & 7u : 0u);
+              } else {
+                adesc = make_sw128_desc(a_base);
+              }
+              const uint64_t bdesc = make_sw128_desc(smem_u32(smemB + bs * C::B_STAGE));
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {
+                umma2_f16(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+                          (first && k == 0) ? 0u : 1u);
+              }
+              first = 0;
+              umma2_commit_mc(&b_empty[bs], 0x3);
+              if (++bs == C::B_STAGES) {
+                bs = 0;
+                bph ^= 1;
+              }
+            }
+            umma2_commit_mc(&a_empty[as], 0x3);
+            if (++as == C::A_STAGES) {
+              as = 0;
+              aph ^= 1;
+            }
+          }
+        }
+        umma2_commit_mc(&tmem_full[acc], 0x3);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp_idx >= 4) {
+    // ===================================== epilogue (both CTAs, own TMEM) ====================
+    const int ew = warp_idx - 4;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const uint32_t leader_empty0 = mapa_u32(smem_u32(&tmem_empty[0]), 0);
+    const uint32_t leader_empty1 = mapa_u32(smem_u32(&tmem_empty[1]), 0);
+    for (int tile = pair; tile < total_tiles; tile += num_pairs) {
+      const int m_idx = (tile % m_pairs) * 2 + static_cast<int>(rank);
+      const int n_idx = tile / m_pairs;
+      int n0, y0, x0;
+      decode_m_tile(p, m_idx, n0, y0, x0);
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      epilogue_tile<BN>(p, tmem_base, acc * 256, ew, lane, n0, y0, x0, n_idx, 0, m_idx, stat_smem);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(acc ? leader_empty1 : leader_empty0);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp_idx == 2) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512);
+  }
+}
+
+template <int BN>
+int launch_bn3(const ConvGemmParams& p, cudaStream_t stream) {
+  using C = Cfg3<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    K2_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int m_pairs = (p.m_tiles + 1) / 2;
+  const int total = m_pairs * p.n_tiles;
+  const int max_pairs = num_sms() / 2;
+  const int pairs = total < max_pairs ? total : max_pairs;
+  conv_gemm3_kernel<BN><<<2 * pairs, 256, C::SMEM_BYTES, stream>>>(p);
+  K2_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // split-K second pass: out[m, n] = fp16( sum_s ws[s][m][n] (fixed order) + bias[n] + residual[m, n] ).
 // Block = 32 column vectors (256 channels) x 8 row lanes over 16 consecutive rows; optionally also emits the GroupNorm
 // partial statistics of its 16 rows (same format as the conv epilogue's, 16-row groups) via a shared-memory fold.
@@ -628,6 +853,14 @@ int launch_splitk_finalize(const float* ws, int splits, long long M, int Cout, c
 }
 
 int launch_conv_gemm(const ConvGemmParams& p, int BN, cudaStream_t stream) {
+  if (p.halo_pitch) {
+    switch (BN) {
+      case 128: return launch_bn3<128>(p, stream);
+      case 192: return launch_bn3<192>(p, stream);
+      case 256: return launch_bn3<256>(p, stream);
+      default: return fail("conv_gemm: unsupported BN for the halo kernel");
+    }
+  }
   if (p.two_cta) {
     switch (BN) {
       case 128: return launch_bn2<128>(p, stream);

@@ -56,6 +56,8 @@ struct ConvGemmParams {
   long long M_total;
   int two_cta;         // 1: CTA-pair kernel (cta_group::2, 256-row tiles)
   float2* gn_part;     // [m_tiles*4][Cout] per-32-row (sum, sumsq) of the fp16-rounded output, or null
+  int halo_pitch;      // 0: per-tap boxes; 10 / 16: halo kernel, pixels per halo row in shared memory
+  int halo_bo;         // halo kernel: 1 = put (start >> 7) & 7 into the descriptor's base-offset field
 };
 int launch_conv_gemm(const ConvGemmParams& p, int BN, cudaStream_t stream);
 int launch_splitk_finalize(const float* ws, int splits, long long M, int Cout, const float* bias, const __half* residual,

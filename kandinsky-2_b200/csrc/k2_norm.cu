@@ -24,7 +24,7 @@ namespace {
 constexpr int VX = 16;   // channel vectors per block
 constexpr int PY = 16;   // pixel lanes per block
 constexpr int UNR = 4;   // loads in flight per thread (statistics)
-constexpr int UNA = 8;   // loads in flight per thread (apply)
+constexpr int UNA = 4;   // vectors per thread per iteration (apply); two iterations are in flight
 
 __device__ __forceinline__ const __half* src_ptr(const __half* s0, int C0, int ld0, const __half* s1, int ld1,
                                                  long long row, int c) {
@@ -335,13 +335,20 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const ApplyParams p) {
   };
 
   if (RESAMPLE == 0 || RESAMPLE == 2) {
-    for (int pp = p0 + py; pp < p1; pp += UNA * PY) {
-      uint4 raw[UNA];
+    // software-pipelined: the loads of iteration i+1 are in flight while iteration i is transformed and stored
+    uint4 raw[UNA], nxt[UNA];
+    auto load_set = [&](int pp, uint4 (&dst)[UNA]) {
 #pragma unroll
       for (int u = 0; u < UNA; ++u) {
         const int q = pp + u * PY;
-        if (q < p1) raw[u] = ldg16(base + (img_in + q) * ld);
+        if (q < p1) dst[u] = ldg16(base + (img_in + q) * ld);
       }
+    };
+    int pp = p0 + py;
+    if (pp < p1) load_set(pp, raw);
+    for (; pp < p1; pp += UNA * PY) {
+      const int npp = pp + UNA * PY;
+      if (npp < p1) load_set(npp, nxt);
 #pragma unroll
       for (int u = 0; u < UNA; ++u) {
         const int q = pp + u * PY;
@@ -366,6 +373,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const ApplyParams p) {
             }
         }
       }
+#pragma unroll
+      for (int u = 0; u < UNA; ++u) raw[u] = nxt[u];
     }
   } else {
     // 2x2 average pool of act(norm(x)) and of raw x; work items are OUTPUT pixels
