@@ -168,6 +168,22 @@ def run_reference(args):
         "gpu_launches": 0, "steps_timed": len(times)}))
 
 
+def _init_pipe_with_model(pipe, config, dev, model):
+    """Kandinsky2_2 around an already-built UNet (the 1.22B synthetic model of the step benchmark)."""
+    from kandinsky2.pipelines import SyntheticEmbedder
+    from kandinsky2.vqgan import MOVQ
+    pipe.config = config
+    pipe.device = dev
+    pipe.task_type = "text2img"
+    pipe.use_fp16 = True
+    pipe.model = model
+    ie = config["image_enc_params"]
+    pipe.scale = ie["scale"]
+    pipe.image_encoder = MOVQ(**ie["params"], device=dev, param_dtype=torch.float16).init_synthetic_(1)
+    pipe.embedder = SyntheticEmbedder(1280)
+    pipe.base_seed = 1234
+
+
 def workload_config(args, world):
     return {"workload": f"Kandinsky-2.2 text2img {args.height}x{args.width}, batch {args.batch} per GPU, 50-step "
                         f"DDPM schedule, CFG 4 (BASELINE configs[1])",
@@ -182,6 +198,7 @@ def run_k2(args):
     from kandinsky2.model.gaussian_diffusion import FusedStep, create_ddpm_v22
     from kandinsky2.model.unet import Text2ImUNet
     world, rank, local = dist_setup(args.gpus)
+    ops.set_tuning(4, 0 if os.environ.get("K2_PDL", "1") == "0" else 1)  # programmatic dependent launch of the step's kernels
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     B, H, W = args.batch, args.height // 8, args.width // 8
@@ -302,6 +319,12 @@ def run_k2(args):
             "per_kind_ms": {k: round(v["ms"], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
             "attention_tflops": prof["attention"]["flops"] / (prof["attention"]["ms"] * 1e-3) / 1e12,
         }
+    traffic_file = os.path.join(ROOT, "profiles", "conv_traffic_r1.json")
+    if "roofline" in line and os.path.exists(traffic_file):
+        with open(traffic_file) as f:
+            tf = json.load(f)
+        line["roofline"]["traffic"] = tf["dram_bytes_per_launch"]
+        line["roofline"]["traffic_note"] = tf["note"]
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = int(os.environ.get('K2_CPU_THREADS', 0)) or min(os.cpu_count() or 1, 32)
         t = cpu_oracle_sample(1, H, W, threads, reps=1, warm=0)[0]
@@ -309,6 +332,30 @@ def run_k2(args):
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": f"one CFG-doubled fp32 oracle forward of 1 of the {B} images at {H}x{W} "
                                           f"({t:.1f} s), step time scaled x{B}"}
+    if not args.no_images:
+        # BASELINE's second figure: images/s of the whole decoder call (50 denoising steps + MoVQ decode + uint8), through
+        # the public pipeline API, each rank generating its own `batch` images.
+        from kandinsky2.configs import CONFIG_2_2
+        from kandinsky2.pipelines import Kandinsky2_2
+        del step
+        model.del_cache()
+        pipe = Kandinsky2_2.__new__(Kandinsky2_2)
+        _init_pipe_with_model(pipe, CONFIG_2_2, dev, model)
+        for _ in range(2):  # second call is steady state (plans, graphs and MoVQ packing exist)
+            barrier()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            imgs = pipe.generate_text2img("bench", batch_size=B * world, decoder_steps=50, decoder_guidance_scale=4,
+                                          h=args.height, w=args.width)
+            e.record()
+            barrier()
+            ms_img = torch.tensor([s.elapsed_time(e)], device=dev)
+            if world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(ms_img, op=dist.ReduceOp.MAX)
+        line["images"] = {"value": B * world / (ms_img.item() * 1e-3), "unit": "images/s", "decoder_steps": 50,
+                          "ms_per_call": ms_img.item(), "images_per_rank": len(imgs),
+                          "includes": "latent init, 50 x (UNet + scheduler), MoVQ decode, uint8 + D2H + PIL"}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -328,6 +375,7 @@ def main():
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--detail", default=None, help="write per-launch timings of one eager step to this JSON file")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-images", action="store_true", help="skip the whole-call images/s measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

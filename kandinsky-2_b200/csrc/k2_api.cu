@@ -17,6 +17,7 @@ static std::atomic<long long> g_launches{0};
 static int g_force_bn = 0;
 static int g_force_split = 0;  // 0 auto, 1 off, n>1 forced
 static int g_force_2cta = 0;   // 0 auto, 1 off, 2 on
+static int g_pdl = 0;          // programmatic dependent launch of the step's kernels
 static int g_halo_mode = 0;    // 0 off; 1/2: dense halo rows (pitch 10) without/with base offset; 3/4: pitch 16
 
 
@@ -26,6 +27,8 @@ int fail(const std::string& msg) {
   return -1;
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+bool pdl_enabled() { return g_pdl != 0; }
 
 int num_sms() {
   static int n = 0;
@@ -84,40 +87,43 @@ int encode_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t
   return 0;
 }
 
-// Pick the (TN, TH, TW) output box of one M tile: <= 128 pixels, minimising the tile count.
+// Pick the (TN, TH, TW) output box of one M tile (<= 128 pixels = the rows of one MMA tile): minimise the number of
+// tiles; boxes may span several images (TN > 1) when whole-image row blocks pack better -- e.g. 12x12 latents: 2 images
+// x 5 rows x 12 = 120 pixels per tile (12 tiles) instead of 1 image x 6 rows (16 tiles, 56 % of the MMA rows used).
 static void choose_tile(int NB, int H, int W, int& TN, int& TH, int& TW) {
-  if (H * W <= 128) {
-    TW = W;
-    TH = H;
-    TN = 128 / (H * W);
-    if (TN > NB) TN = NB;
-    if (TN < 1) TN = 1;
-    return;
-  }
-  TN = 1;
   long long best_tiles = -1;
-  int bw = 1, bh = 1;
-  int wmax = W < 128 ? W : 128;
+  int bn = 1, bw = 1, bh = 1;
+  const int wmax = W < 128 ? W : 128;
   for (int tw = 1; tw <= wmax; ++tw) {
-    int thmax = 128 / tw;
-    if (thmax > H) thmax = H;
-    if (thmax < 1) continue;
-    long long tiles_h = (H + thmax - 1) / thmax;
-    int th = static_cast<int>((H + tiles_h - 1) / tiles_h);  // balanced
-    long long tiles = tiles_h * ((W + tw - 1) / tw);
-    bool better = best_tiles < 0 || tiles < best_tiles;
-    if (!better && tiles == best_tiles) {
-      // tie: prefer the squarer box (halo reuse), then the wider one
-      int d_new = tw > th ? tw - th : th - tw;
-      int d_old = bw > bh ? bw - bh : bh - bw;
-      better = (d_new < d_old) || (d_new == d_old && tw > bw);
-    }
-    if (better) {
-      best_tiles = tiles;
-      bw = tw;
-      bh = th;
+    const long long tiles_w = (W + tw - 1) / tw;
+    for (int tn = 1; tn <= NB && tn * tw <= 128; ++tn) {
+      if (tn > 1 && tw != W) continue;  // multi-image boxes only with full-width rows (keeps the halo reuse sane)
+      int thmax = 128 / (tw * tn);
+      if (thmax > H) thmax = H;
+      if (thmax < 1) continue;
+      const long long tiles_h = (H + thmax - 1) / thmax;
+      const int th = static_cast<int>((H + tiles_h - 1) / tiles_h);  // balanced
+      const long long tiles = tiles_h * tiles_w * ((NB + tn - 1) / tn);
+      bool better = best_tiles < 0 || tiles < best_tiles;
+      if (!better && tiles == best_tiles) {
+        // ties: fewer images per box (fused GroupNorm statistics need TN == 1), then the squarer box, then the wider
+        if (tn != bn) {
+          better = tn < bn;
+        } else {
+          const int d_new = tw > th ? tw - th : th - tw;
+          const int d_old = bw > bh ? bw - bh : bh - bw;
+          better = (d_new < d_old) || (d_new == d_old && tw > bw);
+        }
+      }
+      if (better) {
+        best_tiles = tiles;
+        bn = tn;
+        bw = tw;
+        bh = th;
+      }
     }
   }
+  TN = bn;
   TW = bw;
   TH = bh;
 }
@@ -147,6 +153,10 @@ int k2_set_tuning(int key, int value) {
   }
   if (key == 3) {
     g_halo_mode = value;
+    return 0;
+  }
+  if (key == 4) {
+    g_pdl = value;
     return 0;
   }
 

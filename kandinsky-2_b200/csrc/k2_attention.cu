@@ -101,6 +101,8 @@ __global__ void __launch_bounds__(384, 1) attention_d64_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();
+  pdl_launch();
 
   if (warp_idx == 0) {
     // ===================================== TMA producer =====================================
@@ -330,8 +332,7 @@ int launch_attention_d64(const AttnParams& p, cudaStream_t stream) {
     attr_set = true;
   }
   dim3 grid((p.T + QT * BQ - 1) / (QT * BQ), p.heads, p.B);
-  attention_d64_kernel<<<grid, 384, SMEM_TOTAL, stream>>>(p);
-  K2_CHECK_CUDA(cudaGetLastError());
+  K2_CHECK_CUDA(launch_k(attention_d64_kernel, grid, dim3(384), SMEM_TOTAL, stream, p));
   return 0;
 }
 

@@ -304,6 +304,13 @@ __device__ __forceinline__ void umma2_commit_mc(uint64_t* bar, uint16_t mask) {
       : "memory");
 }
 
+// Programmatic dependent launch: every kernel of the step waits here (before its first global-memory access) for the
+// previous kernel in the stream to complete, and immediately lets the next kernel's CTAs be scheduled, so their
+// launch latency and prologue (barrier init, TMEM allocation, descriptor prefetch) overlap this kernel's execution.
+// Both are no-ops for a launch without the programmatic-serialization attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
 
 }  // namespace k2

@@ -218,6 +218,8 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();
+  pdl_launch();
 
   const int total_tiles = p.m_tiles * p.n_tiles * p.splits;
 
@@ -396,6 +398,8 @@ conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p) {
   cluster_sync_all();  // barriers of both CTAs initialised before any remote arrival / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();
+  pdl_launch();
 
   const int m_pairs = (p.m_tiles + 1) >> 1;
   const int total_tiles = m_pairs * p.n_tiles * p.splits;
@@ -524,8 +528,7 @@ int launch_bn2(const ConvGemmParams& p, cudaStream_t stream) {
   const int total = m_pairs * p.n_tiles * p.splits;
   const int max_pairs = num_sms() / 2;
   const int pairs = total < max_pairs ? total : max_pairs;
-  conv_gemm2_kernel<BN><<<2 * pairs, 256, C::SMEM_BYTES, stream>>>(p);
-  K2_CHECK_CUDA(cudaGetLastError());
+  K2_CHECK_CUDA(launch_k(conv_gemm2_kernel<BN>, dim3(2 * pairs), dim3(256), C::SMEM_BYTES, stream, p));
   return 0;
 }
 
@@ -601,6 +604,8 @@ conv_gemm3_kernel(const __grid_constant__ ConvGemmParams p) {
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();
+  pdl_launch();
 
   const int m_pairs = (p.m_tiles + 1) >> 1;
   const int total_tiles = m_pairs * p.n_tiles;
@@ -749,8 +754,7 @@ int launch_bn3(const ConvGemmParams& p, cudaStream_t stream) {
   const int total = m_pairs * p.n_tiles;
   const int max_pairs = num_sms() / 2;
   const int pairs = total < max_pairs ? total : max_pairs;
-  conv_gemm3_kernel<BN><<<2 * pairs, 256, C::SMEM_BYTES, stream>>>(p);
-  K2_CHECK_CUDA(cudaGetLastError());
+  K2_CHECK_CUDA(launch_k(conv_gemm3_kernel<BN>, dim3(2 * pairs), dim3(256), C::SMEM_BYTES, stream, p));
   return 0;
 }
 
@@ -765,6 +769,8 @@ __global__ void __launch_bounds__(256) splitk_finalize_kernel(const float* __res
   const int vx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c0 = (blockIdx.y * 32 + vx) * 8;
   const long long rg = blockIdx.x;
+  pdl_wait();
+  pdl_launch();
   float st[16];
 #pragma unroll
   for (int e = 0; e < 16; ++e) st[e] = 0.f;
@@ -837,8 +843,7 @@ int launch_bn(const ConvGemmParams& p, cudaStream_t stream) {
   }
   int total = p.m_tiles * p.n_tiles * p.splits;
   int grid = total < num_sms() ? total : num_sms();
-  conv_gemm_kernel<BN><<<grid, 256, C::SMEM_BYTES, stream>>>(p);
-  K2_CHECK_CUDA(cudaGetLastError());
+  K2_CHECK_CUDA(launch_k(conv_gemm_kernel<BN>, dim3(grid), dim3(256), C::SMEM_BYTES, stream, p));
   return 0;
 }
 
@@ -847,8 +852,8 @@ int launch_bn(const ConvGemmParams& p, cudaStream_t stream) {
 int launch_splitk_finalize(const float* ws, int splits, long long M, int Cout, const float* bias, const __half* residual,
                            int ldr, __half* out, int ldo, float2* gn_part, cudaStream_t stream) {
   dim3 grid(static_cast<unsigned int>((M + 15) / 16), (Cout / 8 + 31) / 32);
-  splitk_finalize_kernel<<<grid, 256, 0, stream>>>(ws, splits, M, Cout, bias, residual, ldr, out, ldo, gn_part);
-  K2_CHECK_CUDA(cudaGetLastError());
+  K2_CHECK_CUDA(launch_k(splitk_finalize_kernel, grid, dim3(256), 0, stream, ws, splits, M, Cout, bias, residual, ldr, out, ldo,
+                         gn_part));
   return 0;
 }
 

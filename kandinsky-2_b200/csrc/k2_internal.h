@@ -24,6 +24,24 @@ int fail(const std::string& msg);  // records msg, returns -1
   } while (0)
 
 int num_sms();
+bool pdl_enabled();
+
+// Launch with (optionally) the programmatic-stream-serialization attribute. ONLY for kernels that call pdl_wait().
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 void count_launch(int n = 1);  // bump the library-wide kernel launch counter
 
 // ---- TMA tensor-map encoding (driver entry point fetched at run time; no libcuda link) ----------

@@ -42,6 +42,8 @@ __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x
                                                      int Kp, int vec_ok, int silu_in, int silu_out) {
   extern __shared__ float xs[];  // [LIN_MT][Kp]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_wait();
+  pdl_launch();
   const int m0 = blockIdx.y * LIN_MT;
   const int mt = min(LIN_MT, M - m0);
   for (int idx = threadIdx.x; idx < LIN_MT * Kp; idx += blockDim.x) {
@@ -155,6 +157,8 @@ __global__ void timestep_embedding_kernel(const float* __restrict__ t, float* __
                                           float max_period) {
   const int half = dim / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_wait();
+  pdl_launch();
   if (i >= B * dim) return;
   const int b = i / dim, j = i % dim;
   float v = 0.f;
@@ -180,6 +184,8 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
                                                           int H, int W, __half* __restrict__ out, int Kpad) {
   const long long item = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(NB) * H * W * Kpad;
+  pdl_wait();
+  pdl_launch();
   if (item >= total) return;
   const int k = static_cast<int>(item % Kpad);
   const long long pix = item / Kpad;
@@ -227,6 +233,8 @@ struct SamplerParams {
 
 __global__ void __launch_bounds__(256) sampler_x0_kernel(const SamplerParams p) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  pdl_wait();
+  pdl_launch();
   const long long total = static_cast<long long>(p.B) * 4 * p.HW;
   if (i >= total) return;
   const int sp = static_cast<int>(i % p.HW);
@@ -283,6 +291,8 @@ __device__ float radix_select(const float* __restrict__ v, int n, int rank, unsi
 __global__ void __launch_bounds__(1024) sampler_percentile_kernel(const float* __restrict__ x0, int n, float* sval) {
   __shared__ unsigned int hist[256];
   __shared__ unsigned int sh[2];
+  pdl_wait();
+  pdl_launch();
   const double pos = 0.995 * static_cast<double>(n - 1);
   int lo = static_cast<int>(floor(pos));
   const double frac = pos - lo;
@@ -300,6 +310,8 @@ __global__ void __launch_bounds__(1024) sampler_percentile_kernel(const float* _
 
 __global__ void __launch_bounds__(256) sampler_post_kernel(const SamplerParams p) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  pdl_wait();
+  pdl_launch();
   const long long total = static_cast<long long>(p.B) * 4 * p.HW;
   if (i >= total) return;
   const int sp = static_cast<int>(i % p.HW);
@@ -498,9 +510,11 @@ int k2_linear(const float* x, int ldx, const void* W, int w_is_half, const float
   dim3 grid((N + 8 * LIN_CB - 1) / (8 * LIN_CB), (M + LIN_MT - 1) / LIN_MT);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (w_is_half)
-    linear_kernel<true><<<grid, 256, smem, st>>>(x, ldx, W, b, add, ldadd, y, ldy, M, N, K, Kp, vec_ok, silu_in, silu_out);
+    K2_CHECK_CUDA(launch_k(linear_kernel<true>, grid, dim3(256), smem, st, x, ldx, W, b, add, ldadd, y, ldy, M, N, K, Kp, vec_ok,
+                           silu_in, silu_out));
   else
-    linear_kernel<false><<<grid, 256, smem, st>>>(x, ldx, W, b, add, ldadd, y, ldy, M, N, K, Kp, vec_ok, silu_in, silu_out);
+    K2_CHECK_CUDA(launch_k(linear_kernel<false>, grid, dim3(256), smem, st, x, ldx, W, b, add, ldadd, y, ldy, M, N, K, Kp, vec_ok,
+                           silu_in, silu_out));
   K2_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -517,8 +531,8 @@ int k2_layernorm(const float* x, const float* gamma, const float* beta, float* y
 
 int k2_timestep_embedding(const float* t, float* out, int B, int dim, float max_period, k2_stream_t stream) {
   K2_REQUIRE(t && out && B > 0 && dim > 0, "timestep_embedding: bad arguments");
-  timestep_embedding_kernel<<<blocks_for(static_cast<long long>(B) * dim, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      t, out, B, dim, max_period);
+  K2_CHECK_CUDA(launch_k(timestep_embedding_kernel, dim3(blocks_for(static_cast<long long>(B) * dim, 256)), dim3(256), 0,
+                         static_cast<cudaStream_t>(stream), t, out, B, dim, max_period));
   K2_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -541,8 +555,8 @@ int k2_stem_im2col(const float* x, int Cx, const float* x2, int C2, const float*
   K2_REQUIRE(Kpad % 64 == 0 && Kpad >= 9 * (Cx + C2 + C3), "stem_im2col: Kpad too small / not a multiple of 64");
   K2_REQUIRE(!mul23 || (x2 && x3 && C3 == 1), "stem_im2col: mul23 needs x2 and a 1-channel x3");
   const long long total = static_cast<long long>(NB) * H * W * Kpad;
-  stem_im2col_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, Cx, x2, C2, x3, C3, mul23, NB, H, W, reinterpret_cast<__half*>(out), Kpad);
+  K2_CHECK_CUDA(launch_k(stem_im2col_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), x, Cx,
+                         x2, C2, x3, C3, mul23, NB, H, W, reinterpret_cast<__half*>(out), Kpad));
   K2_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;
@@ -560,12 +574,13 @@ int k2_sampler_step(const float* model_out, float* x, const float* noise, const 
   p.x0 = work; p.sval = work + static_cast<long long>(B) * 4 * H * W;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long total = static_cast<long long>(B) * 4 * H * W;
-  sampler_x0_kernel<<<blocks_for(total, 256), 256, 0, st>>>(p);
+  K2_CHECK_CUDA(launch_k(sampler_x0_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, st, p));
   if (threshold_mode == 1) {
-    sampler_percentile_kernel<<<1, 1024, 0, st>>>(p.x0, 4 * H * W, p.sval);
+    K2_CHECK_CUDA(launch_k(sampler_percentile_kernel, dim3(1), dim3(1024), 0, st, static_cast<const float*>(p.x0), 4 * H * W,
+                           p.sval));
     count_launch();
   }
-  sampler_post_kernel<<<blocks_for(total, 256), 256, 0, st>>>(p);
+  K2_CHECK_CUDA(launch_k(sampler_post_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, st, p));
   K2_CHECK_CUDA(cudaGetLastError());
   count_launch(2);
   return 0;

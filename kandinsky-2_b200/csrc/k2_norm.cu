@@ -67,6 +67,8 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const __half* __restrict_
   const int chunks = gridDim.x;
   const int p0 = blockIdx.x * chunk;
   const int p1 = min(HW, p0 + chunk);
+  pdl_wait();
+  pdl_launch();
   float a[16];
 #pragma unroll
   for (int e = 0; e < 16; ++e) a[e] = 0.f;
@@ -185,6 +187,8 @@ __global__ void __launch_bounds__(128) gn_finalize_kernel(const float2* __restri
   const int n = blockIdx.y, g = blockIdx.x;
   const int C = C0 + C1;
   const int cpg = C / groups;
+  pdl_wait();
+  pdl_launch();
   // 4 independent fp32 accumulator pairs per thread (loads in flight), folded in fp64 in a fixed order
   float fs[4] = {0.f, 0.f, 0.f, 0.f}, fq[4] = {0.f, 0.f, 0.f, 0.f};
   // the group's channels [c_lo, c_hi) restricted to one source: part[(n*rgs + rg)][c - base]
@@ -274,6 +278,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const ApplyParams p) {
   const int py = threadIdx.x / VX;
   const int v = blockIdx.y * VX + vx;
   const int n = blockIdx.z;
+  pdl_wait();
+  pdl_launch();
   if (v >= CV) return;
   const int c0 = v * 8;
   const int Hw = (RESAMPLE == 1) ? p.H / 2 : p.H;
@@ -452,10 +458,9 @@ int k2_gn_stats(const void* src0, int C0, int ld0, const void* src1, int C1, int
   float* partial = scratch + 1024;
   unsigned int* counters = reinterpret_cast<unsigned int*>(scratch);  // zeroed once by the caller, self-resetting
   dim3 grid(chunks, ctiles, NB);
-  gn_stats_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __half*>(src0), C0, ld0, reinterpret_cast<const __half*>(src1), C1, ld1, HW, groups,
-      eps, chunk, stats, partial, counters);
-  K2_CHECK_CUDA(cudaGetLastError());
+  K2_CHECK_CUDA(launch_k(gn_stats_kernel, grid, dim3(256), 0, static_cast<cudaStream_t>(stream),
+                         reinterpret_cast<const __half*>(src0), C0, ld0, reinterpret_cast<const __half*>(src1), C1, ld1, HW,
+                         groups, eps, chunk, stats, partial, counters));
   count_launch();
   return 0;
 }
@@ -465,10 +470,9 @@ int k2_gn_finalize(const float* part0, int C0, int rg0, const float* part1, int 
   K2_REQUIRE(part0 && stats && C0 > 0 && (part1 || C1 == 0) && (C0 + C1) % groups == 0 && rg0 > 0 && (C1 == 0 || rg1 > 0),
              "gn_finalize: bad arguments");
   dim3 grid(groups, NB);
-  gn_finalize_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const float2*>(part0), C0, rg0, reinterpret_cast<const float2*>(part1), C1, rg1, HW, groups, eps,
-      stats);
-  K2_CHECK_CUDA(cudaGetLastError());
+  K2_CHECK_CUDA(launch_k(gn_finalize_kernel, grid, dim3(128), 0, static_cast<cudaStream_t>(stream),
+                         reinterpret_cast<const float2*>(part0), C0, rg0, reinterpret_cast<const float2*>(part1), C1, rg1, HW,
+                         groups, eps, stats));
   count_launch();
   return 0;
 }
@@ -501,14 +505,14 @@ int k2_gn_apply(const void* src0, int C0, int ld0, const void* src1, int C1, int
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool sp = zq != nullptr;
   if (resample == 0) {
-    if (sp) gn_apply_kernel<0, true><<<grid, 256, 0, st>>>(p);
-    else gn_apply_kernel<0, false><<<grid, 256, 0, st>>>(p);
+    if (sp) K2_CHECK_CUDA(launch_k(gn_apply_kernel<0, true>, grid, dim3(256), 0, st, p));
+    else K2_CHECK_CUDA(launch_k(gn_apply_kernel<0, false>, grid, dim3(256), 0, st, p));
   } else if (resample == 1) {
-    if (sp) gn_apply_kernel<1, true><<<grid, 256, 0, st>>>(p);
-    else gn_apply_kernel<1, false><<<grid, 256, 0, st>>>(p);
+    if (sp) K2_CHECK_CUDA(launch_k(gn_apply_kernel<1, true>, grid, dim3(256), 0, st, p));
+    else K2_CHECK_CUDA(launch_k(gn_apply_kernel<1, false>, grid, dim3(256), 0, st, p));
   } else {
-    if (sp) gn_apply_kernel<2, true><<<grid, 256, 0, st>>>(p);
-    else gn_apply_kernel<2, false><<<grid, 256, 0, st>>>(p);
+    if (sp) K2_CHECK_CUDA(launch_k(gn_apply_kernel<2, true>, grid, dim3(256), 0, st, p));
+    else K2_CHECK_CUDA(launch_k(gn_apply_kernel<2, false>, grid, dim3(256), 0, st, p));
   }
   K2_CHECK_CUDA(cudaGetLastError());
   count_launch();

@@ -102,3 +102,87 @@ def test_del_cache_recomputes_conditioning():
     assert not torch.equal(y1, y2)
     sdc = {k: v.cuda() for k, v in sd.items()}
     _check(y2, uo.unet_forward(sdc, cfg, x, t, **k2))
+
+
+def test_unet_pdl_bit_identical():
+    """Programmatic dependent launch (kernels overlap their prologues with the predecessor's tail) must not change results,
+    eager or graph-replayed."""
+    from kandinsky2 import ops
+    from oracle import synth
+    from oracle import unet_oracle as uo
+    fx = torch.load(os.path.join(GOLD, "unet_tiny.pt"))
+    cfg = fx["cfg"]
+    sd = synth.synth_state_dict(uo.unet_param_spec(cfg), seed=fx["weight_seed"])
+    inp = {k: v.cuda() for k, v in fx["inputs"].items()}
+    kw = {k: v for k, v in inp.items() if k not in ("x", "t")}
+    outs = []
+    for pdl in (0, 1):
+        ops.set_tuning(4, pdl)
+        try:
+            m = _build(cfg, sd)
+            m.use_cuda_graph = False
+            ye = m(inp["x"], inp["t"], **kw)
+            m.use_cuda_graph = True
+            yg = m(inp["x"], inp["t"], **kw)
+            yg2 = m(inp["x"], inp["t"], **kw)
+        finally:
+            ops.set_tuning(4, 0)
+        assert torch.equal(ye, yg) and torch.equal(yg, yg2)
+        outs.append(ye)
+    assert torch.equal(outs[0], outs[1])
+    _check(outs[1], fx["out"])
+
+
+def test_unet_full_size_vs_oracle():
+    """BASELINE configs[1] geometry at full model size (1.22 B parameters, 96x96 latent, Kandinsky-2.2 head, 32 context
+    tokens), UNet batch 2 = one image under CFG: the oracle runs in fp32 on the GPU.  Also checks two size-independent
+    properties on the full batch of 8: permuting the batch permutes the output bit-exactly (no cross-sample coupling),
+    and duplicated samples give duplicated outputs."""
+    from kandinsky2.model.unet import Text2ImUNet
+    from oracle import unet_oracle as uo
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    cfg = uo.CONFIG_2_2
+    g = torch.Generator(device="cuda").manual_seed(0)
+    sd = {}
+    for k, shape in uo.unet_param_spec(cfg):
+        if k.endswith("bias"):
+            sd[k] = 0.05 * torch.randn(shape, device="cuda", generator=g)
+        elif len(shape) == 1:
+            sd[k] = 1.0 + 0.1 * torch.randn(shape, device="cuda", generator=g)
+        else:
+            fan = 1
+            for d in shape[1:]:
+                fan *= d
+            sd[k] = torch.randn(shape, device="cuda", generator=g) / fan ** 0.5
+    m = Text2ImUNet(model_dim=768, image_encoder_in_dim=1280, num_image_embs=32, pooling_type="from_model", in_channels=4,
+                    model_channels=384, out_channels=8, num_res_blocks=3, attention_resolutions=(2, 4, 8),
+                    channel_mult=(1, 2, 3, 4), use_fp16=True, num_head_channels=64, use_scale_shift_norm=True,
+                    resblock_updown=True, cond_version="2.2", device="cuda", param_dtype=torch.float16)
+    m.load_state_dict(sd)
+    m.finalize(release_params=True)
+    x = torch.randn(2, 4, 96, 96, device="cuda", generator=g)
+    t = torch.tensor([980.0, 980.0], device="cuda")
+    img = torch.randn(2, 1280, device="cuda", generator=g)
+    y = m(x, t, image_emb=img)
+    sd16 = {k: (v.half().float() if v.dim() > 1 and not k.startswith(("time_embed", "encoder_hid", "add_emb")) and "emb_layers" not in k
+                else v) for k, v in sd.items()}
+    with torch.no_grad():
+        ref = uo.unet_forward(sd16, cfg, x, t, image_emb=img)
+    err, rel = _check(y, ref)
+    print(f"full size: max abs {err:.3e} rel L2 {rel:.3e} (output rms {ref.pow(2).mean().sqrt().item():.3f})")
+    del sd, sd16, ref
+    torch.cuda.empty_cache()
+    # batch of 8 (the benchmark's UNet batch): permutation equivariance and duplicate consistency, bit-exact
+    m.del_cache()
+    x8 = torch.randn(8, 4, 96, 96, device="cuda", generator=g)
+    x8[5] = x8[2]
+    img8 = torch.randn(8, 1280, device="cuda", generator=g)
+    img8[5] = img8[2]
+    t8 = torch.full((8,), 500.0, device="cuda")
+    y8 = m(x8, t8, image_emb=img8)
+    assert torch.equal(y8[5], y8[2])
+    perm = torch.tensor([3, 0, 7, 1, 2, 6, 5, 4], device="cuda")
+    m.del_cache()
+    y8p = m(x8[perm], t8, image_emb=img8[perm])
+    assert torch.equal(y8p, y8[perm])
