@@ -174,6 +174,14 @@ __global__ void __launch_bounds__(384, 1) attention_d64_kernel(const __grid_cons
             if (t == ntile - 1) umma_commit(&kv_empty[pstage]);
           }
           issue_s(t, stage);
+          if (j == 0 && t == 0 && ntile == 2) {
+            // De-phase the two softmax warpgroups by about half a block: if both exponentiate at the same time they
+            // share the MUFU pipe and then both wait for the tensor core (lock-step, measured 52 % MUFU utilisation);
+            // started half a period apart, each has the MUFU to itself while the other's products are issued.
+            const long long t0 = clock64();
+            while (clock64() - t0 < p.stagger_cycles) {
+            }
+          }
         }
         pstage = stage;
         if (++stage == KV_STAGES) {
@@ -376,6 +384,7 @@ extern "C" int k2_attention_d64(const void* qkv, int ldq, int hs, int q_off, int
   p.out = reinterpret_cast<__half*>(out);
   p.ldo = ldo;
   p.scale_log2e = scale * 1.4426950408889634f;
+  p.stagger_cycles = attention_stagger();
   int rc = launch_attention_d64(p, static_cast<cudaStream_t>(stream));
   if (rc == 0) count_launch();
   return rc;

@@ -91,7 +91,9 @@ struct AttnParams {
   __half* out;         // [B, T, ldo], channel h*64+d
   int ldo;
   float scale_log2e;   // softmax scale * log2(e)
+  int stagger_cycles;  // initial delay of the second query tile's first score product (de-phases the warpgroups)
 };
+int attention_stagger();
 int launch_attention_d64(const AttnParams& p, cudaStream_t stream);
 
 }  // namespace k2
