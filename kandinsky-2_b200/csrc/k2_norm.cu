@@ -313,24 +313,30 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const ApplyParams p) {
   const int ld = (c0 < p.C0) ? p.ld0 : p.ld1;
   const long long img_in = static_cast<long long>(n) * p.H * p.W;
 
+  // SpatialNorm: the modulation depends on the latent pixel under (yi, xi); a thread's consecutive pixels usually share
+  // it (the feature map is up to 8x finer than the latent), so it is recomputed only when the latent pixel changes.
+  float a8[8], b8[8];
+  int last_z = -1;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    a8[e] = A[e];
+    b8[e] = Bc[e];
+  }
   auto transform = [&](const float (&f)[8], int yi, int xi, float (&o)[8]) {
-    float a8[8], b8[8];
     if (SPATIAL) {
       const int zy = (yi * p.zh) / p.H, zx = (xi * p.zw) / p.W;
-      const float4 z = __ldg(reinterpret_cast<const float4*>(p.zq + ((static_cast<long long>(n) * p.zh + zy) * p.zw + zx) * 4));
+      const int zi = zy * p.zw + zx;
+      if (zi != last_z) {
+        last_z = zi;
+        const float4 z = __ldg(reinterpret_cast<const float4*>(p.zq + (static_cast<long long>(n) * p.zh * p.zw + zi) * 4));
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float* w = p.sn_w + static_cast<long long>(c0 + e) * 10;
-        const float my = __ldg(w + 0) * z.x + __ldg(w + 1) * z.y + __ldg(w + 2) * z.z + __ldg(w + 3) * z.w + __ldg(w + 4);
-        const float mb = __ldg(w + 5) * z.x + __ldg(w + 6) * z.y + __ldg(w + 7) * z.z + __ldg(w + 8) * z.w + __ldg(w + 9);
-        a8[e] = A[e] * my;
-        b8[e] = Bc[e] * my + mb;
-      }
-    } else {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        a8[e] = A[e];
-        b8[e] = Bc[e];
+        for (int e = 0; e < 8; ++e) {
+          const float* w = p.sn_w + static_cast<long long>(c0 + e) * 10;
+          const float my = __ldg(w + 0) * z.x + __ldg(w + 1) * z.y + __ldg(w + 2) * z.z + __ldg(w + 3) * z.w + __ldg(w + 4);
+          const float mb = __ldg(w + 5) * z.x + __ldg(w + 6) * z.y + __ldg(w + 7) * z.z + __ldg(w + 8) * z.w + __ldg(w + 9);
+          a8[e] = A[e] * my;
+          b8[e] = Bc[e] * my + mb;
+        }
       }
     }
 #pragma unroll
@@ -346,18 +352,18 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const ApplyParams p) {
     auto load_set = [&](int pp, uint4 (&dst)[UNA]) {
 #pragma unroll
       for (int u = 0; u < UNA; ++u) {
-        const int q = pp + u * PY;
+        const int q = pp + u;
         if (q < p1) dst[u] = ldg16(base + (img_in + q) * ld);
       }
     };
-    int pp = p0 + py;
+    int pp = p0 + py * UNA;
     if (pp < p1) load_set(pp, raw);
     for (; pp < p1; pp += UNA * PY) {
       const int npp = pp + UNA * PY;
       if (npp < p1) load_set(npp, nxt);
 #pragma unroll
       for (int u = 0; u < UNA; ++u) {
-        const int q = pp + u * PY;
+        const int q = pp + u;
         if (q >= p1) break;
         float f[8], o[8];
         unpack8(raw[u], f);

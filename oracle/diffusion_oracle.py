@@ -85,3 +85,20 @@ def p_sample_loop(unet_fn, tab, x_T, step_noise, guidance, rescale_timesteps=Tru
         out = unet_fn(xx, torch.full((xx.shape[0],), t))
         x = p_sample_step(tab, i, x, out, step_noise[n], guidance, **kw)
     return x
+
+
+def ddim_schedule(num_steps, base_betas=None):
+    """make_ddim_timesteps('uniform') + make_ddim_sampling_parameters(eta=0)  (model/samplers.py:21-55)."""
+    b = linear_betas() if base_betas is None else base_betas
+    acp = np.cumprod(1.0 - b)
+    c = len(b) // num_steps
+    t = np.asarray(list(range(0, len(b), c))) + 1
+    alphas = acp[t]
+    alphas_prev = np.asarray([acp[0]] + acp[t[:-1]].tolist())
+    return t, alphas, alphas_prev
+
+
+def ddim_step(x, eps, a_t, a_prev):
+    """p_sample_ddim with sigma = 0 (model/samplers.py:311-330)."""
+    pred_x0 = (x - (1.0 - a_t) ** 0.5 * eps) / a_t ** 0.5
+    return a_prev ** 0.5 * pred_x0 + (1.0 - a_prev) ** 0.5 * eps

@@ -180,6 +180,15 @@ def golden_schedule():
                    coef1_50=d50.posterior_mean_coef1.copy(), coef2_50=d50.posterior_mean_coef2.copy(),
                    sqrt_recip50=d50.sqrt_recip_alphas_cumprod.copy(), sqrt_recipm1_50=d50.sqrt_recipm1_alphas_cumprod.copy(),
                    temb=nn_.timestep_embedding(torch.tensor([999.0, 0.0, 500.5]), 384))
+        sm = R.load("model.samplers")  # pure-numpy schedule helpers of the DDIM sampler (the class itself needs CUDA)
+        d1000 = mc.create_gaussian_diffusion(steps=1000, learn_sigma=True, noise_schedule="linear", rescale_timesteps=True,
+                                             rescale_learned_sigmas=True, timestep_respacing="", linear_start=0.00085,
+                                             linear_end=0.012)
+        for S in (50, 30):
+            t = sm.make_ddim_timesteps("uniform", S, 1000, verbose=False)
+            sig, al, alp = sm.make_ddim_sampling_parameters(d1000.alphas_cumprod, t, 0.0, verbose=False)
+            kat[f"ddim{S}"] = dict(t=t.copy(), alphas=np.asarray(al).copy(), alphas_prev=np.asarray(alp).copy(),
+                                   sigmas=np.asarray(sig).copy())
     torch.save(kat, os.path.join(GOLD, "schedule_kat.pt"))
     print("schedule_kat: betas50[:3]", kat["betas50"][:3])
 

@@ -81,6 +81,26 @@ def test_schedule_known_answers():
     assert d.model_timestep(49) == 999.0 and d.model_timestep(1) == 20.0
     v22 = create_ddpm_v22(50)
     assert v22.timestep_map[:3] == [0, 20, 40] and v22.timestep_map[-1] == 980 and v22.num_timesteps == 50
+    # DDIM schedule helpers (samplers.py:21-55) -- oracle restatement and the product's coefficient table
+    from kandinsky2.model.gaussian_diffusion import DDIMSampler
+    d1000 = create_gaussian_diffusion(steps=1000, learn_sigma=True, noise_schedule="linear", rescale_timesteps=True,
+                                      rescale_learned_sigmas=True, timestep_respacing="", linear_start=0.00085,
+                                      linear_end=0.012)
+    for S in (50, 30):
+        ref = kat[f"ddim{S}"]
+        tt, al, alp = do.ddim_schedule(S)
+        assert np.array_equal(tt, ref["t"]) and np.array_equal(al, ref["alphas"]) and np.array_equal(alp, ref["alphas_prev"])
+        assert not ref["sigmas"].any()
+        s = DDIMSampler(None, d1000)
+        s.make_schedule(S)
+        assert np.array_equal(s.ddim_timesteps, ref["t"]) and np.array_equal(s.ddim_alphas, ref["alphas"])
+        # the fused-step coefficients reproduce the reference's two-line update on random data
+        g = np.random.default_rng(0)
+        x, e = g.standard_normal(64), g.standard_normal(64)
+        c = s.coef_table().astype(np.float64)
+        for i in (0, S // 2, len(tt) - 1):
+            x0 = c[i, 0] * x - c[i, 1] * e
+            assert np.allclose(c[i, 2] * x0 + c[i, 3] * x, do.ddim_step(x, e, al[i], alp[i]), rtol=2e-5, atol=2e-5)
     # timestep embedding known answers (cos first)
     from oracle import unet_oracle as uo
     te = uo.timestep_embedding(torch.tensor([999.0, 0.0, 500.5]), 384)

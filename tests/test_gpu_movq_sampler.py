@@ -95,8 +95,10 @@ def test_pipeline_surface(version):
         imgs = pipe.generate_text2img("a red cat", num_steps=4, batch_size=2, guidance_scale=4, h=70, w=100, sampler="p_sampler")
         again = pipe.generate_text2img("a red cat", num_steps=4, batch_size=2, guidance_scale=4, h=70, w=100, sampler="p_sampler")
         mixed = pipe.mix_images(["a cat", "a dog"], [0.3, 0.7], num_steps=3, batch_size=1, h=64, w=64, sampler="p_sampler")
+        ddim = pipe.generate_text2img("a red cat", num_steps=10, batch_size=1, h=64, w=64)  # default sampler = ddim_sampler
+        assert len(ddim) == 1 and ddim[0].size == (64, 64)
         with pytest.raises(NotImplementedError):
-            pipe.generate_text2img("x", num_steps=4)  # default ddim_sampler is not on the implemented path
+            pipe.generate_text2img("x", num_steps=4, sampler="plms_sampler")
     else:
         imgs = pipe.generate_text2img("a red cat", batch_size=2, decoder_steps=4, h=70, w=100)
         again = pipe.generate_text2img("a red cat", batch_size=2, decoder_steps=4, h=70, w=100)
@@ -118,3 +120,31 @@ def test_pipeline_inpainting_21():
     imgs = pipe.generate_inpainting("a hat", lat, mask.numpy(), num_steps=3, batch_size=1, guidance_scale=4, h=64, w=64,
                                     sampler="p_sampler")
     assert len(imgs) == 1 and imgs[0].size == (64, 64)
+
+
+def test_ddim_loop_matches_oracle_rule():
+    """DDIM (eta 0) through the fused step kernel vs the oracle's restatement of p_sample_ddim driven by the oracle UNet."""
+    from kandinsky2.model.gaussian_diffusion import DDIMSampler, create_gaussian_diffusion
+    from oracle import diffusion_oracle as do, synth, unet_oracle as uo
+    from tests.test_gpu_unet import _build
+    fx = _load("traj_tiny")
+    cfg = fx["cfg"]
+    sd = synth.synth_state_dict(uo.unet_param_spec(cfg), seed=fx["weight_seed"])
+    m = _build(cfg, sd)
+    d = create_gaussian_diffusion(steps=1000, learn_sigma=True, noise_schedule="linear", rescale_timesteps=True,
+                                  rescale_learned_sigmas=True, timestep_respacing="", linear_start=0.00085, linear_end=0.012)
+    x_T = fx["x_T"].cuda()
+    B = x_T.shape[0]
+    kw = {k: v.cuda() for k, v in fx["cond"].items()}
+    S, gscale = 4, 3.0
+    out, _ = DDIMSampler(m, d).sample(S, 2 * B, (4, 16, 16), conditioning=kw, x_T=torch.cat([x_T, x_T]), guidance_scale=gscale)
+    tt, al, alp = do.ddim_schedule(S)
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    x = x_T.clone()
+    with torch.no_grad():
+        for i in range(len(tt))[::-1]:
+            mo = uo.unet_forward(sdc, cfg, torch.cat([x, x]), torch.full((2 * B,), float(tt[i]), device="cuda"), **kw)
+            eps = mo[B:, :4] + gscale * (mo[:B, :4] - mo[B:, :4])
+            x = do.ddim_step(x, eps, float(al[i]), float(alp[i]))
+    err = (out[:B] - x).abs().max().item()
+    assert err < 3e-2, err
