@@ -16,6 +16,7 @@ namespace {
 // ------------------------------------------------------------------------------------------------
 constexpr int LIN_MT = 8;   // rows of x staged in shared memory per block
 constexpr int LIN_CB = 4;   // output columns per warp pass (register blocking over the staged x)
+constexpr int LIN_NI = 4;   // column groups per warp (amortises the staging of x)
 
 template <bool W_HALF>
 __device__ __forceinline__ void load_w8(const void* Wv, long long off, float (&w)[8]) {
@@ -39,7 +40,7 @@ template <bool W_HALF>
 __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x, int ldx, const void* __restrict__ Wv,
                                                      const float* __restrict__ b, const float* __restrict__ add,
                                                      int ldadd, float* __restrict__ y, int ldy, int M, int N, int K,
-                                                     int Kp, int vec_ok, int silu_in, int silu_out) {
+                                                     int Kp, int vec_ok, int silu_in, int silu_out, int ni) {
   extern __shared__ float xs[];  // [LIN_MT][Kp]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_wait();
@@ -56,61 +57,64 @@ __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x
     xs[idx] = v;
   }
   __syncthreads();
-  const int n0 = (blockIdx.x * 8 + warp) * LIN_CB;
-  if (n0 >= N) return;
-  float acc[LIN_CB][LIN_MT];
+  // each warp walks LIN_NI groups of LIN_CB output columns, so one staging of x serves 8 * LIN_CB * LIN_NI columns
+  for (int it = 0; it < ni; ++it) {
+    const int n0 = ((blockIdx.x * ni + it) * 8 + warp) * LIN_CB;
+    if (n0 >= N) break;
+    float acc[LIN_CB][LIN_MT];
 #pragma unroll
-  for (int cb = 0; cb < LIN_CB; ++cb)
+    for (int cb = 0; cb < LIN_CB; ++cb)
 #pragma unroll
-    for (int i = 0; i < LIN_MT; ++i) acc[cb][i] = 0.f;
-  const int K8 = vec_ok ? (K & ~7) : 0;
-  for (int k = lane * 8; k < K8; k += 256) {
-    float w[LIN_CB][8];
+      for (int i = 0; i < LIN_MT; ++i) acc[cb][i] = 0.f;
+    const int K8 = vec_ok ? (K & ~7) : 0;
+    for (int k = lane * 8; k < K8; k += 256) {
+      float w[LIN_CB][8];
 #pragma unroll
-    for (int cb = 0; cb < LIN_CB; ++cb) {
-      if (n0 + cb < N) {
-        load_w8<W_HALF>(Wv, static_cast<long long>(n0 + cb) * K + k, w[cb]);
-      } else {
+      for (int cb = 0; cb < LIN_CB; ++cb) {
+        if (n0 + cb < N) {
+          load_w8<W_HALF>(Wv, static_cast<long long>(n0 + cb) * K + k, w[cb]);
+        } else {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) w[cb][e] = 0.f;
+          for (int e = 0; e < 8; ++e) w[cb][e] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < LIN_MT; ++i) {
+        const float4 xa = *reinterpret_cast<const float4*>(xs + i * Kp + k);
+        const float4 xb = *reinterpret_cast<const float4*>(xs + i * Kp + k + 4);
+        const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+        for (int cb = 0; cb < LIN_CB; ++cb)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[cb][i] = fmaf(xv[e], w[cb][e], acc[cb][i]);
+      }
+    }
+    for (int k = K8 + lane; k < K; k += 32) {
+#pragma unroll
+      for (int cb = 0; cb < LIN_CB; ++cb) {
+        if (n0 + cb < N) {
+          const long long off = static_cast<long long>(n0 + cb) * K + k;
+          const float w = W_HALF ? __half2float(reinterpret_cast<const __half*>(Wv)[off])
+                                 : reinterpret_cast<const float*>(Wv)[off];
+#pragma unroll
+          for (int i = 0; i < LIN_MT; ++i) acc[cb][i] = fmaf(xs[i * Kp + k], w, acc[cb][i]);
+        }
       }
     }
 #pragma unroll
-    for (int i = 0; i < LIN_MT; ++i) {
-      const float4 xa = *reinterpret_cast<const float4*>(xs + i * Kp + k);
-      const float4 xb = *reinterpret_cast<const float4*>(xs + i * Kp + k + 4);
-      const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
-#pragma unroll
-      for (int cb = 0; cb < LIN_CB; ++cb)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[cb][i] = fmaf(xv[e], w[cb][e], acc[cb][i]);
-    }
-  }
-  for (int k = K8 + lane; k < K; k += 32) {
-#pragma unroll
     for (int cb = 0; cb < LIN_CB; ++cb) {
-      if (n0 + cb < N) {
-        const long long off = static_cast<long long>(n0 + cb) * K + k;
-        const float w = W_HALF ? __half2float(reinterpret_cast<const __half*>(Wv)[off])
-                               : reinterpret_cast<const float*>(Wv)[off];
 #pragma unroll
-        for (int i = 0; i < LIN_MT; ++i) acc[cb][i] = fmaf(xs[i * Kp + k], w, acc[cb][i]);
-      }
-    }
-  }
+      for (int i = 0; i < LIN_MT; ++i) {
+        float v = acc[cb][i];
 #pragma unroll
-  for (int cb = 0; cb < LIN_CB; ++cb) {
-#pragma unroll
-    for (int i = 0; i < LIN_MT; ++i) {
-      float v = acc[cb][i];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      const int n = n0 + cb;
-      if (lane == 0 && i < mt && n < N) {
-        if (b) v += b[n];
-        if (silu_out) v = silu_f(v);
-        if (add) v += add[static_cast<long long>(m0 + i) * ldadd + n];
-        y[static_cast<long long>(m0 + i) * ldy + n] = v;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        const int n = n0 + cb;
+        if (lane == 0 && i < mt && n < N) {
+          if (b) v += b[n];
+          if (silu_out) v = silu_f(v);
+          if (add) v += add[static_cast<long long>(m0 + i) * ldadd + n];
+          y[static_cast<long long>(m0 + i) * ldy + n] = v;
+        }
       }
     }
   }
@@ -507,14 +511,15 @@ int k2_linear(const float* x, int ldx, const void* W, int w_is_half, const float
     K2_CHECK_CUDA(cudaFuncSetAttribute(linear_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     attr_set = true;
   }
-  dim3 grid((N + 8 * LIN_CB - 1) / (8 * LIN_CB), (M + LIN_MT - 1) / LIN_MT);
+  const int ni = (N >= 8 * LIN_CB * LIN_NI * 2 * num_sms()) ? LIN_NI : 1;  // small N: keep every SM busy instead
+  dim3 grid((N + 8 * LIN_CB * ni - 1) / (8 * LIN_CB * ni), (M + LIN_MT - 1) / LIN_MT);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (w_is_half)
     K2_CHECK_CUDA(launch_k(linear_kernel<true>, grid, dim3(256), smem, st, x, ldx, W, b, add, ldadd, y, ldy, M, N, K, Kp, vec_ok,
-                           silu_in, silu_out));
+                           silu_in, silu_out, ni));
   else
     K2_CHECK_CUDA(launch_k(linear_kernel<false>, grid, dim3(256), smem, st, x, ldx, W, b, add, ldadd, y, ldy, M, N, K, Kp, vec_ok,
-                           silu_in, silu_out));
+                           silu_in, silu_out, ni));
   K2_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;
