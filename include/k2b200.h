@@ -170,6 +170,10 @@ int k2_pointwise_nchw_f32(const float* x, const float* w, const float* b, float*
                           k2_stream_t stream);
 /* nearest 2x upsample of fp16 NHWC rows (movq_modules.py:93-97 F.interpolate before the conv) */
 int k2_upsample2x_nhwc(const void* x, int ldx, void* y, int ldy, int NB, int H, int W, int C, k2_stream_t stream);
+/* y[n, yo, xo, :] = x[n, 2*yo+oy, 2*xo+ox, :] on fp16 NHWC rows.  With (oy, ox) = (1, 1) applied to a stride-1 'same' 3x3
+ * conv this is the VQGAN encoder's Downsample: pad (0,1,0,1) + conv3x3 stride 2 (vqgan_blocks.py:109-126). */
+int k2_subsample2_nhwc(const void* x, int ldx, void* y, int ldy, int NB, int H, int W, int C, int oy, int ox,
+                       k2_stream_t stream);
 /* y[r, :] = softmax(scale * x[r, :]) over n columns, fp16 in/out, fp32 math (movq_modules.py:213-215) */
 int k2_softmax_rows(const void* x, int ldx, void* y, int ldy, long long rows, int n, float scale, k2_stream_t stream);
 int k2_nchw_to_nhwc_f32(const float* x, float* y, int NB, int C, int H, int W, k2_stream_t stream);

@@ -430,6 +430,22 @@ __global__ void __launch_bounds__(256) upsample2x_kernel(const __half* __restric
     }
 }
 
+// every second pixel of NHWC fp16 rows: y[n, yo, xo, :] = x[n, 2*yo + oy, 2*xo + ox, :]
+__global__ void __launch_bounds__(256) subsample2_kernel(const __half* __restrict__ x, int ldx, __half* __restrict__ y, int ldy,
+                                                         int NB, int H, int W, int CV, int oy, int ox) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long item = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(NB) * Ho * Wo * CV;
+  if (item >= total) return;
+  const int v = static_cast<int>(item % CV);
+  const long long pix = item / CV;
+  const int xo = static_cast<int>(pix % Wo);
+  const int yo = static_cast<int>((pix / Wo) % Ho);
+  const int n = static_cast<int>(pix / (static_cast<long long>(Wo) * Ho));
+  const long long irow = (static_cast<long long>(n) * H + (2 * yo + oy)) * W + (2 * xo + ox);
+  *reinterpret_cast<uint4*>(y + pix * ldy + v * 8) = __ldg(reinterpret_cast<const uint4*>(x + irow * ldx + v * 8));
+}
+
 // row softmax, fp16 in/out, fp32 math; one block per row, 16-byte vectors
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const __half* __restrict__ x, int ldx, __half* __restrict__ y,
                                                            int ldy, int n, float scale_log2e) {
@@ -596,6 +612,18 @@ int k2_upsample2x_nhwc(const void* x, int ldx, void* y, int ldy, int NB, int H, 
   const long long total = static_cast<long long>(NB) * H * W * (C / 8);
   upsample2x_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __half*>(x), ldx, reinterpret_cast<__half*>(y), ldy, NB, H, W, C / 8);
+  K2_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int k2_subsample2_nhwc(const void* x, int ldx, void* y, int ldy, int NB, int H, int W, int C, int oy, int ox,
+                       k2_stream_t stream) {
+  K2_REQUIRE(x && y && C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && H % 2 == 0 && W % 2 == 0 && (oy | 1) == 1 && (ox | 1) == 1,
+             "subsample2: bad arguments");
+  const long long total = static_cast<long long>(NB) * (H / 2) * (W / 2) * (C / 8);
+  subsample2_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half*>(x), ldx, reinterpret_cast<__half*>(y), ldy, NB, H, W, C / 8, oy, ox);
   K2_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;

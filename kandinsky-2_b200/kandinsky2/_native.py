@@ -37,6 +37,7 @@ SIGNATURES = {
                          ctypes.POINTER(ctypes.c_int), _P]),
     "k2_gn_finalize": (_I, [_P, _I, _I, _P, _I, _I, _I, _I, _I, _F, _P, _P]),
     "k2_upsample2x_nhwc": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _P]),
+    "k2_subsample2_nhwc": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "k2_softmax_rows": (_I, [_P, _I, _P, _I, _LL, _I, _F, _P]),
     "k2_gn_scratch_floats": (_LL, [_I, _I, _I]),
     "k2_gn_stats": (_I, [_P, _I, _I, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P]),

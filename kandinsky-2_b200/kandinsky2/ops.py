@@ -330,6 +330,15 @@ def upsample2x(x, out=None):
     return out
 
 
+def subsample2(x, oy=1, ox=1):
+    """fp16 NHWC [NB,H,W,C] -> [NB,H/2,W/2,C] taking pixels (2y+oy, 2x+ox)."""
+    lib = nat.load()
+    NB, H, W, C = x.shape
+    out = torch.empty((NB, H // 2, W // 2, C), dtype=torch.float16, device=x.device)
+    check(lib.k2_subsample2_nhwc(ptr(x), _row_stride(x), ptr(out), _row_stride(out), NB, H, W, C, oy, ox, stream_ptr()))
+    return out
+
+
 def softmax_rows(x, scale, out=None):
     """fp16 [rows, n] (row-strided) -> softmax(scale * x) fp16."""
     lib = nat.load()

@@ -8,8 +8,7 @@ The stages BEFORE the path (CLIP text/image towers, the diffusion prior, the XLM
 scope of this build: they enter through an `embedder` object.  The
 default SyntheticEmbedder draws deterministic N(0,1) embeddings keyed by the prompt text, which is what the
 benchmark configurations specify (BASELINE.json: "synthetic CLIP embeds"); a real deployment passes an embedder
-wrapping its prior / encoders.  Likewise the image->latent MoVQ encoder (8f rank 1) is not here: img2img / inpainting
-accept the init image as a latent tensor.
+wrapping its prior / encoders.  img2img / inpainting take a PIL image (encoded by the MoVQ encoder) or an already-encoded latent tensor.
 """
 import hashlib
 import math
@@ -20,7 +19,7 @@ from . import ops, parallel
 from ._native import K2Error
 from .model.gaussian_diffusion import DDIMSampler, create_ddpm_v22, create_gaussian_diffusion
 from .model.model_creation import create_model
-from .utils import prepare_mask, uint8_to_pil
+from .utils import prepare_image, prepare_mask, q_sample, uint8_to_pil
 from .vqgan import MOVQ
 
 
@@ -102,6 +101,15 @@ class _DecoderBase:
     def _finish(self, latents, h, w):
         u8 = self.image_encoder.decode_to_uint8(latents / self.scale, crop_h=h, crop_w=w)
         return uint8_to_pil(u8)
+
+    def _encode_image(self, image, h, w):
+        """PIL image (resized to (w, h), utils.py:33-39) or image tensor [1,3,H,W] in [-1,1] -> latent via the MoVQ
+        encoder (kandinsky2_1_model.py:458-461); a [1,4,h/8,w/8] tensor is taken as an already-encoded latent."""
+        if torch.is_tensor(image):
+            if image.shape[1] == self.image_encoder.embed_dim:
+                return image.float().to(self.device)
+            return self.image_encoder.encode(image.to(self.device))
+        return self.image_encoder.encode(prepare_image(image, w=w, h=h).to(self.device))
 
     def _shard(self, batch_size):
         rank, ws = parallel.world()
@@ -194,32 +202,29 @@ class Kandinsky2_1(_DecoderBase):
                                  h=h, w=w, sampler=sampler, num_steps=num_steps,
                                  diffusion=self._diffusion(sampler, num_steps))
 
-    def _as_latent(self, pil_img, what):
-        if not torch.is_tensor(pil_img):
-            raise NotImplementedError(f"{what}: encoding a PIL image needs the MoVQ encoder (SURVEY.md 8f rank 1); "
-                                      "pass the init image as a latent tensor [1, 4, h/8, w/8]")
-        return pil_img.float()
 
     def generate_img2img(self, prompt, pil_img, strength=0.7, num_steps=100, batch_size=1, guidance_scale=7, h=512,
                          w=512, sampler="ddim_sampler", prior_cf_scale=4, prior_steps="25"):
-        """kandinsky2_1_model.py:428-484: start from q_sample(latent, start_step) and run the last steps."""
-        from .utils import q_sample
-        image = self._as_latent(pil_img, "generate_img2img") * self.scale
+        """kandinsky2_1_model.py:428-484: encode the image, noise it to step int(T*(1-strength)) and run the remaining steps."""
         diffusion = self._diffusion(sampler, num_steps)
-        start_step = int(diffusion.num_timesteps * strength)
+        image = self._encode_image(pil_img, h, w) * self.scale
+        start_step = int(diffusion.num_timesteps * (1 - strength))
         g = torch.Generator().manual_seed(self.base_seed)
-        x = q_sample(image, start_step, diffusion.alphas_cumprod, noise=torch.randn(image.shape, generator=g))
+        noise = torch.randn(image.shape, generator=g).to(self.device)
+        dc = self.config["diffusion_config"]
+        x = q_sample(image, diffusion.timestep_map[start_step - 1], schedule_name=dc["noise_schedule"],
+                     num_steps=dc["steps"], noise=noise)
         x = x.repeat(2 * batch_size, 1, 1, 1)
         image_emb = self._image_embs(prompt, batch_size)
         return self.generate_img(prompt=prompt, img_prompt=image_emb, batch_size=batch_size,
                                  guidance_scale=guidance_scale, h=h, w=w, sampler=sampler, num_steps=num_steps,
-                                 diffusion=diffusion, noise=x.to(self.device), init_step=start_step)
+                                 diffusion=diffusion, noise=x, init_step=start_step)
 
     def generate_inpainting(self, prompt, pil_img, img_mask, num_steps=100, batch_size=1, guidance_scale=7, h=512,
                             w=512, sampler="ddim_sampler", prior_cf_scale=4, prior_steps="25",
                             negative_prior_prompt="", negative_decoder_prompt=""):
         """kandinsky2_1_model.py:487-548 (mask: 1 = keep, nearest-resized to the latent grid, then prepare_mask)."""
-        image = self._as_latent(pil_img, "generate_inpainting") * self.scale
+        image = self._encode_image(pil_img, h, w) * self.scale
         m = torch.as_tensor(img_mask).float()[None, None]
         m = torch.nn.functional.interpolate(m, tuple(image.shape[-2:]), mode="nearest")
         m = prepare_mask(m)
@@ -288,26 +293,26 @@ class Kandinsky2_2(_DecoderBase):
     def generate_img2img(self, prompt, image, strength=0.4, batch_size=1, decoder_steps=100, prior_steps=25,
                          decoder_guidance_scale=4, prior_guidance_scale=4, h=512, w=512, negative_prior_prompt="",
                          negative_decoder_prompt=""):
-        from .utils import q_sample
-        if not torch.is_tensor(image):
-            raise NotImplementedError("generate_img2img: pass the init image as a latent tensor (MoVQ encoder: 8f rank 1)")
         h, w = self.get_new_h_w(h, w)
         pos, neg = self._embeds(prompt, batch_size, negative_decoder_prompt)
+        lat = self._encode_image(image, h, w)
         diffusion = create_ddpm_v22(decoder_steps)
-        start = min(int(decoder_steps * strength), decoder_steps)
+        # diffusers KandinskyV22Img2ImgPipeline: the last int(steps*strength) timesteps, scheduler.add_noise at the first of them
+        start = max(min(int(decoder_steps * strength), decoder_steps), 1)
+        ac = float(diffusion.alphas_cumprod[start - 1])
         g = torch.Generator().manual_seed(self.base_seed)
-        x = q_sample(image.float(), max(start - 1, 0), diffusion.alphas_cumprod, noise=torch.randn(image.shape, generator=g))
+        noise = torch.randn(lat.shape, generator=g).to(self.device)
+        x = ac ** 0.5 * lat + (1.0 - ac) ** 0.5 * noise
         return self._decode_loop(pos, neg, batch_size, decoder_steps, decoder_guidance_scale, h, w,
-                                 latents=x.repeat(2 * batch_size, 1, 1, 1).to(self.device), init_step=start)
+                                 latents=x.repeat(2 * batch_size, 1, 1, 1), init_step=start)
 
     def generate_inpainting(self, prompt, pil_img, img_mask, batch_size=1, decoder_steps=50, prior_steps=25,
                             decoder_guidance_scale=4, prior_guidance_scale=4, h=512, w=512, negative_prior_prompt="",
                             negative_decoder_prompt=""):
-        if not torch.is_tensor(pil_img):
-            raise NotImplementedError("generate_inpainting: pass the image as a latent tensor (MoVQ encoder: 8f rank 1)")
         h, w = self.get_new_h_w(h, w)
         pos, neg = self._embeds(prompt, batch_size, negative_decoder_prompt)
+        lat = self._encode_image(pil_img, h, w)
         m = torch.as_tensor(img_mask).float()[None, None]
-        m = torch.nn.functional.interpolate(m, (h // 8, w // 8), mode="nearest")
+        m = torch.nn.functional.interpolate(m, (h // 8, w // 8), mode="nearest").to(self.device)
         return self._decode_loop(pos, neg, batch_size, decoder_steps, decoder_guidance_scale, h, w,
-                                 inpaint_latent=pil_img.float(), inpaint_mask=m)
+                                 inpaint_latent=lat, inpaint_mask=m)

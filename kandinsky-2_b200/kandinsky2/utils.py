@@ -34,10 +34,16 @@ def uint8_to_pil(batch_u8):
     return [Image.fromarray(a) for a in arr]
 
 
-def q_sample(x_start, t, alphas_cumprod, noise=None):
-    """Forward diffusion to step t (utils.py q_sample): sqrt(ac_t) x0 + sqrt(1-ac_t) noise."""
+def q_sample(x_start, t, schedule_name="linear", num_steps=1000, noise=None):
+    """Forward diffusion of x_start to timestep t (utils.py:42-54).  As in the reference this uses
+    get_named_beta_schedule's DEFAULT linear range (1e-4 .. 2e-2 scaled by 1000/num_steps), not the decoder's."""
+    if schedule_name != "linear":
+        raise NotImplementedError(schedule_name)
+    scale = 1000 / num_steps
+    betas = np.linspace(scale * 0.0001, scale * 0.02, num_steps, dtype=np.float64)
+    ac = np.cumprod(1.0 - betas, axis=0)
     if noise is None:
         noise = torch.randn_like(x_start)
-    a = float(np.sqrt(alphas_cumprod[t]))
-    b = float(np.sqrt(1.0 - alphas_cumprod[t]))
+    a = float(np.float32(np.sqrt(ac[int(t)])))
+    b = float(np.float32(np.sqrt(1.0 - ac[int(t)])))
     return a * x_start + b * noise

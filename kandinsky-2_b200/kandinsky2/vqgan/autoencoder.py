@@ -25,6 +25,23 @@ class _Node(nn.Module):
     pass
 
 
+def _enc_topology(dd):
+    ch, mult, nrb = dd["ch"], tuple(dd["ch_mult"]), dd["num_res_blocks"]
+    curr = dd["resolution"]
+    in_mult = (1,) + mult
+    levels = []
+    for i in range(len(mult)):
+        bi, bo = ch * in_mult[i], ch * mult[i]
+        blocks = []
+        for _ in range(nrb):
+            blocks.append((bi, bo))
+            bi = bo
+        levels.append(dict(level=i, blocks=blocks, attn=curr in tuple(dd["attn_resolutions"]), down=i != len(mult) - 1, ch=bo))
+        if i != len(mult) - 1:
+            curr //= 2
+    return levels
+
+
 def _topology(dd):
     ch, mult, nrb = dd["ch"], tuple(dd["ch_mult"]), dd["num_res_blocks"]
     nres = len(mult)
@@ -80,6 +97,39 @@ class MOVQ(nn.Module):
             for n in ("q", "k", "v", "proj_out"):
                 P(p + n + ".weight", c, c, 1, 1); P(p + n + ".bias", c)
 
+        # ---- encoder (image -> latent; vqgan_blocks.py:253-367) -- plain GroupNorm(32, eps 1e-6), no SpatialNorm
+        def ERES(p, cin, cout):
+            P(p + "norm1.weight", cin); P(p + "norm1.bias", cin)
+            P(p + "conv1.weight", cout, cin, 3, 3); P(p + "conv1.bias", cout)
+            P(p + "norm2.weight", cout); P(p + "norm2.bias", cout)
+            P(p + "conv2.weight", cout, cout, 3, 3); P(p + "conv2.bias", cout)
+            if cin != cout:
+                P(p + "nin_shortcut.weight", cout, cin, 1, 1); P(p + "nin_shortcut.bias", cout)
+
+        def EATT(p, c):
+            P(p + "norm.weight", c); P(p + "norm.bias", c)
+            for n in ("q", "k", "v", "proj_out"):
+                P(p + n + ".weight", c, c, 1, 1); P(p + n + ".bias", c)
+
+        self.enc_levels = _enc_topology(dd)
+        P("encoder.conv_in.weight", dd["ch"], dd["in_channels"], 3, 3); P("encoder.conv_in.bias", dd["ch"])
+        for lv in self.enc_levels:
+            p = f"encoder.down.{lv['level']}."
+            for bi, (cin, cout) in enumerate(lv["blocks"]):
+                ERES(p + f"block.{bi}.", cin, cout)
+            if lv["attn"]:
+                for bi in range(len(lv["blocks"])):
+                    EATT(p + f"attn.{bi}.", lv["ch"])
+            if lv["down"]:
+                P(p + "downsample.conv.weight", lv["ch"], lv["ch"], 3, 3); P(p + "downsample.conv.bias", lv["ch"])
+        ce = self.enc_levels[-1]["ch"]
+        ERES("encoder.mid.block_1.", ce, ce)
+        EATT("encoder.mid.attn_1.", ce)
+        ERES("encoder.mid.block_2.", ce, ce)
+        zc_out = dd["z_channels"] * (2 if dd.get("double_z") else 1)
+        P("encoder.norm_out.weight", ce); P("encoder.norm_out.bias", ce)
+        P("encoder.conv_out.weight", zc_out, ce, 3, 3); P("encoder.conv_out.bias", zc_out)
+
         self.block_in, self.levels = _topology(dd)
         P("decoder.conv_in.weight", self.block_in, dd["z_channels"], 3, 3); P("decoder.conv_in.bias", self.block_in)
         RES("decoder.mid.block_1.", self.block_in, self.block_in)
@@ -98,14 +148,13 @@ class MOVQ(nn.Module):
         SN("decoder.norm_out.", c_last)
         P("decoder.conv_out.weight", dd["out_ch"], c_last, 3, 3); P("decoder.conv_out.bias", dd["out_ch"])
         P("quantize.embedding.weight", n_embed, embed_dim)
+        P("quant_conv.weight", embed_dim, dd["z_channels"], 1, 1); P("quant_conv.bias", embed_dim)
         P("post_quant_conv.weight", dd["z_channels"], embed_dim, 1, 1); P("post_quant_conv.bias", dd["z_channels"])
 
     # ------------------------------------------------------------------------------------------
     def load_state_dict(self, state_dict, strict=True, assign=False):
-        """Reference checkpoints (movq_final.ckpt) also hold encoder.* / quant_conv.* (image -> latent), which
-        this decoder-only module does not own: they are dropped before the strict check."""
-        sd = {k: v for k, v in state_dict.items()
-              if not (k.startswith("encoder.") or k.startswith("quant_conv.") or k.startswith("loss."))}
+        """Same keys as the reference's MOVQ (autoencoder.py:167-174); training-only `loss.*` entries are dropped."""
+        sd = {k: v for k, v in state_dict.items() if not k.startswith("loss.")}
         self._packed = None
         return super().load_state_dict(sd, strict=strict, assign=assign)
 
@@ -158,13 +207,17 @@ class MOVQ(nn.Module):
             d["w2"] = w2
             return d
 
-        def att(p):
+        def att_common(p):
             pc = ops.pack_conv_weight
-            return dict(n=sn(p + "norm."),
-                        wqk=torch.cat([pc(self._get(p + "q.weight")), pc(self._get(p + "k.weight"))], 0).contiguous(),
+            return dict(wqk=torch.cat([pc(self._get(p + "q.weight")), pc(self._get(p + "k.weight"))], 0).contiguous(),
                         bqk=torch.cat([f32(p + "q.bias"), f32(p + "k.bias")]).contiguous(),
                         wv=pc(self._get(p + "v.weight")), bv=f32(p + "v.bias"),
                         wp=pc(self._get(p + "proj_out.weight")), bp=f32(p + "proj_out.bias"))
+
+        def att(p):
+            d = att_common(p)
+            d["n"] = sn(p + "norm.")
+            return d
 
         pk["pq_w"] = f32("post_quant_conv.weight").reshape(self.ddconfig["z_channels"], self.embed_dim).contiguous()
         pk["pq_b"] = f32("post_quant_conv.bias")
@@ -182,6 +235,45 @@ class MOVQ(nn.Module):
             if lv["up"]:
                 pk[p + "up_w"] = ops.pack_conv_weight(self._get(p + "upsample.conv.weight"))
                 pk[p + "up_b"] = f32(p + "upsample.conv.bias")
+        # ---- encoder
+        def gn(p):
+            return dict(g=f32(p + "weight"), b=f32(p + "bias"))
+
+        def eres(p, cin, cout):
+            d = dict(n1=gn(p + "norm1."), n2=gn(p + "norm2."), w1=ops.pack_conv_weight(self._get(p + "conv1.weight")),
+                     c1=f32(p + "conv1.bias"), c2=f32(p + "conv2.bias"))
+            w2 = ops.pack_conv_weight(self._get(p + "conv2.weight"))
+            if cin != cout:
+                w2 = torch.cat([w2, ops.pack_conv_weight(self._get(p + "nin_shortcut.weight"))], 1).contiguous()
+                d["c2"] = d["c2"] + f32(p + "nin_shortcut.bias")
+            d["w2"] = w2
+            return d
+
+        def eatt(p):
+            d = att_common(p)
+            d["n"] = gn(p + "norm.")
+            return d
+
+        pk["e_in_w"] = ops.pack_stem_weight(self._get("encoder.conv_in.weight"))
+        pk["e_in_b"] = f32("encoder.conv_in.bias")
+        for lv in self.enc_levels:
+            p = f"encoder.down.{lv['level']}."
+            for bi, (cin, cout) in enumerate(lv["blocks"]):
+                pk[p + f"block.{bi}"] = eres(p + f"block.{bi}.", cin, cout)
+                if lv["attn"]:
+                    pk[p + f"attn.{bi}"] = eatt(p + f"attn.{bi}.")
+            if lv["down"]:
+                pk[p + "down_w"] = ops.pack_conv_weight(self._get(p + "downsample.conv.weight"))
+                pk[p + "down_b"] = f32(p + "downsample.conv.bias")
+        ce = self.enc_levels[-1]["ch"]
+        pk["e_mid1"] = eres("encoder.mid.block_1.", ce, ce)
+        pk["e_mida"] = eatt("encoder.mid.attn_1.")
+        pk["e_mid2"] = eres("encoder.mid.block_2.", ce, ce)
+        pk["e_out_n"] = gn("encoder.norm_out.")
+        pk["e_out_w"] = ops.pad_rows(ops.pack_conv_weight(self._get("encoder.conv_out.weight")), 16)
+        pk["e_out_b"] = f32("encoder.conv_out.bias")
+        pk["qc_w"] = f32("quant_conv.weight").reshape(self.embed_dim, -1).contiguous()
+        pk["qc_b"] = f32("quant_conv.bias")
         pk["out_n"] = sn("decoder.norm_out.")
         pk["out_w"] = ops.pad_rows(ops.pack_conv_weight(self._get("decoder.conv_out.weight")), 16)
         pk["out_b"] = f32("decoder.conv_out.bias")
@@ -191,7 +283,10 @@ class MOVQ(nn.Module):
 
     # ------------------------------------------------------------------------------------------
     def _sn_act(self, x, zq, n, act):
+        """SpatialNorm (decoder: zq given) or plain GroupNorm(32, eps 1e-6) (encoder: zq None), optional swish."""
         st = ops.gn_stats(x, None, groups=32, eps=1e-6)
+        if zq is None:
+            return ops.gn_apply(x, None, st, n["g"], n["b"], act=act)
         return ops.gn_apply(x, None, st, n["g"], n["b"], act=act, zq=zq, sn_w=n["w"])
 
     def _res(self, x, zq, d):
@@ -247,6 +342,34 @@ class MOVQ(nn.Module):
         img = ops.conv_gemm([(h, 9)], pk["out_w"], self.ddconfig["out_ch"], bias=pk["out_b"], out_mode=1)
         dt = out_dtype or (quant.dtype if quant.is_floating_point() else torch.float32)
         return img if dt == torch.float32 else img.to(dt)
+
+    @torch.no_grad()
+    def encode(self, x):
+        """image [B, 3, H, W] in [-1, 1] -> latent fp32 [B, embed_dim, H/8, W/8], no quantisation (autoencoder.py:176-180:
+        quant_conv(Encoder(x))).  The stride-2 Downsample conv (pad (0,1,0,1), vqgan_blocks.py:109-126) is evaluated as
+        the stride-1 'same' conv on tensor cores followed by taking the odd pixels."""
+        if not x.is_cuda:
+            raise K2Error("k2b200 MOVQ.encode: input must be a CUDA tensor (no CPU fallback)")
+        if self._packed is None:
+            self.finalize()
+        pk = self._packed
+        h = ops.gemm_rows(ops.stem_im2col(x.float().contiguous()), pk["e_in_w"], self.ddconfig["ch"], bias=pk["e_in_b"])
+        for lv in self.enc_levels:
+            p = f"encoder.down.{lv['level']}."
+            for bi in range(len(lv["blocks"])):
+                h = self._res(h, None, pk[p + f"block.{bi}"])
+                if lv["attn"]:
+                    h = self._attn(h, None, pk[p + f"attn.{bi}"])
+            if lv["down"]:
+                full = ops.conv_gemm([(h, 9)], pk[p + "down_w"], lv["ch"], bias=pk[p + "down_b"])
+                h = ops.subsample2(full, 1, 1)
+        h = self._res(h, None, pk["e_mid1"])
+        h = self._attn(h, None, pk["e_mida"])
+        h = self._res(h, None, pk["e_mid2"])
+        h = self._sn_act(h, None, pk["e_out_n"], 1)
+        zc_out = pk["e_out_b"].shape[0]
+        z = ops.conv_gemm([(h, 9)], pk["e_out_w"], zc_out, bias=pk["e_out_b"], out_mode=1)
+        return ops.pointwise_nchw_f32(z, pk["qc_w"], pk["qc_b"])
 
     @torch.no_grad()
     def decode_to_uint8(self, quant, crop_h=None, crop_w=None):

@@ -85,26 +85,31 @@ def golden_movq(name, dd, B, h, w, wseed, iseed, n_embed=64):
         ae = R.load("vqgan.autoencoder")
         with contextlib.redirect_stdout(io.StringIO()):  # the reference ctor prints (movq_modules.py:261-265)
             m = ae.MOVQ(dict(dd, double_z=False, dropout=0.0), n_embed=n_embed, embed_dim=4).eval()
-    spec = mo.movq_decoder_param_spec(dd, 4, n_embed)
-    ref = {k: tuple(v.shape) for k, v in m.state_dict().items()
-           if k.startswith(("decoder.", "post_quant_conv.", "quantize."))}
-    assert ref == {k: tuple(s) for k, s in spec}, "oracle MoVQ parameter spec != reference state_dict"
+    dd = dict(dd, double_z=False)
+    spec = mo.movq_param_spec(dd, 4, n_embed)
+    ref = [(k, tuple(v.shape)) for k, v in m.state_dict().items()]
+    assert ref == [(k, tuple(s)) for k, s in spec], "oracle MoVQ parameter spec != reference state_dict"
     sd = synth.synth_state_dict(spec, seed=wseed)
-    m.load_state_dict(sd, strict=False)
+    m.load_state_dict(sd, strict=True)
     g = torch.Generator().manual_seed(iseed)
     z = torch.randn(B, 4, h, w, generator=g)
+    scale = 2 ** (len(dd["ch_mult"]) - 1)
+    image = torch.rand(B, 3, h * scale, w * scale, generator=g) * 2 - 1
     with torch.no_grad():
         y_ref = m.decode(z)
         y_orc = mo.movq_decode(sd, dd, z)
+        lat_ref = m.encode(image)
+        lat_orc = mo.movq_encode(sd, dd, image)
         zf = z.permute(0, 2, 3, 1).reshape(-1, 4)
         # VectorQuantizer.forward's distance/argmin lines (quntize.py:89-98) on the same z
         emb = m.quantize.embedding.weight
         d = torch.sum(zf ** 2, dim=1, keepdim=True) + torch.sum(emb ** 2, dim=1) - 2 * torch.einsum("bd,dn->bn", zf, emb.t())
         idx_ref = torch.argmin(d, dim=1)
         idx_orc = mo.vq_indices(zf, sd["quantize.embedding.weight"])
+    assert (lat_ref - lat_orc).abs().max().item() <= 1e-5, "MoVQ encoder oracle deviates"
     err = (y_ref - y_orc).abs().max().item()
     assert err <= 1e-5 and torch.equal(idx_ref, idx_orc), f"{name}: MoVQ oracle deviates ({err})"
-    torch.save(dict(dd=dd, n_embed=n_embed, weight_seed=wseed, z=z, out=y_ref, indices=idx_ref),
+    torch.save(dict(dd=dd, n_embed=n_embed, weight_seed=wseed, z=z, out=y_ref, indices=idx_ref, image=image, latent=lat_ref),
                os.path.join(GOLD, name + ".pt"))
     print(f"{name}: reference out std {y_ref.std():.4f}, oracle-vs-reference max abs {err:.2e}")
 

@@ -87,6 +87,119 @@ def movq_decoder_param_spec(dd, embed_dim=4, n_embed=None):
     return spec
 
 
+# ---------------------------------------------------------------------------------------------
+# encoder (image -> latent): vqgan_blocks.py:253-367 (Encoder), :87-91 (Normalize: GroupNorm 32, eps 1e-6),
+# :109-126 (Downsample: pad (0,1,0,1) + conv3x3 stride 2), :129-193 (ResnetBlock), :196-239 (AttnBlock);
+# MOVQ.encode = quant_conv(encoder(x)) without quantisation (autoencoder.py:176-180)
+# ---------------------------------------------------------------------------------------------
+def encoder_topology(dd):
+    ch, mult, nrb = dd["ch"], tuple(dd["ch_mult"]), dd["num_res_blocks"]
+    curr = dd["resolution"]
+    in_mult = (1,) + mult
+    levels = []
+    for i in range(len(mult)):
+        bi, bo = ch * in_mult[i], ch * mult[i]
+        blocks = []
+        for _ in range(nrb):
+            blocks.append((bi, bo))
+            bi = bo
+        levels.append(dict(level=i, blocks=blocks, attn=curr in tuple(dd["attn_resolutions"]), down=i != len(mult) - 1, ch=bo))
+        if i != len(mult) - 1:
+            curr //= 2
+    return levels
+
+
+def _enc_res_spec(p, cin, cout, spec):
+    spec += [(p + "norm1.weight", (cin,)), (p + "norm1.bias", (cin,)),
+             (p + "conv1.weight", (cout, cin, 3, 3)), (p + "conv1.bias", (cout,)),
+             (p + "norm2.weight", (cout,)), (p + "norm2.bias", (cout,)),
+             (p + "conv2.weight", (cout, cout, 3, 3)), (p + "conv2.bias", (cout,))]
+    if cin != cout:
+        spec += [(p + "nin_shortcut.weight", (cout, cin, 1, 1)), (p + "nin_shortcut.bias", (cout,))]
+
+
+def _enc_attn_spec(p, c, spec):
+    spec += [(p + "norm.weight", (c,)), (p + "norm.bias", (c,))]
+    for n in ("q", "k", "v", "proj_out"):
+        spec += [(p + n + ".weight", (c, c, 1, 1)), (p + n + ".bias", (c,))]
+
+
+def movq_encoder_param_spec(dd, embed_dim=4):
+    spec = [("encoder.conv_in.weight", (dd["ch"], dd["in_channels"], 3, 3)), ("encoder.conv_in.bias", (dd["ch"],))]
+    levels = encoder_topology(dd)
+    for lv in levels:
+        p = f"encoder.down.{lv['level']}."
+        for bi, (cin, cout) in enumerate(lv["blocks"]):
+            _enc_res_spec(p + f"block.{bi}.", cin, cout, spec)
+        if lv["attn"]:
+            for bi in range(len(lv["blocks"])):
+                _enc_attn_spec(p + f"attn.{bi}.", lv["ch"], spec)
+        if lv["down"]:
+            spec += [(p + "downsample.conv.weight", (lv["ch"], lv["ch"], 3, 3)), (p + "downsample.conv.bias", (lv["ch"],))]
+    c = levels[-1]["ch"]
+    _enc_res_spec("encoder.mid.block_1.", c, c, spec)
+    _enc_attn_spec("encoder.mid.attn_1.", c, spec)
+    _enc_res_spec("encoder.mid.block_2.", c, c, spec)
+    zc = dd["z_channels"] * (2 if dd.get("double_z") else 1)
+    spec += [("encoder.norm_out.weight", (c,)), ("encoder.norm_out.bias", (c,)),
+             ("encoder.conv_out.weight", (zc, c, 3, 3)), ("encoder.conv_out.bias", (zc,)),
+             ("quant_conv.weight", (embed_dim, dd["z_channels"], 1, 1)), ("quant_conv.bias", (embed_dim,))]
+    return spec
+
+
+def _gn6(x, sd, p):
+    return F.group_norm(x, 32, sd[p + "weight"], sd[p + "bias"], 1e-6)
+
+
+def _enc_res(x, sd, p):
+    h = F.conv2d(_swish(_gn6(x, sd, p + "norm1.")), sd[p + "conv1.weight"], sd[p + "conv1.bias"], padding=1)
+    h = F.conv2d(_swish(_gn6(h, sd, p + "norm2.")), sd[p + "conv2.weight"], sd[p + "conv2.bias"], padding=1)
+    if (p + "nin_shortcut.weight") in sd:
+        x = F.conv2d(x, sd[p + "nin_shortcut.weight"], sd[p + "nin_shortcut.bias"])
+    return x + h
+
+
+def _enc_attn(x, sd, p):
+    h = _gn6(x, sd, p + "norm.")
+    q = F.conv2d(h, sd[p + "q.weight"], sd[p + "q.bias"])
+    k = F.conv2d(h, sd[p + "k.weight"], sd[p + "k.bias"])
+    v = F.conv2d(h, sd[p + "v.weight"], sd[p + "v.bias"])
+    b, c, hh, ww = q.shape
+    w_ = torch.bmm(q.reshape(b, c, -1).permute(0, 2, 1), k.reshape(b, c, -1)) * (int(c) ** (-0.5))
+    w_ = F.softmax(w_, dim=2)
+    h = torch.bmm(v.reshape(b, c, -1), w_.permute(0, 2, 1)).reshape(b, c, hh, ww)
+    return x + F.conv2d(h, sd[p + "proj_out.weight"], sd[p + "proj_out.bias"])
+
+
+def movq_encode(sd, dd, x):
+    """image fp32 [B, 3, H, W] in [-1, 1] -> latent [B, embed_dim, H/2^(levels-1), ...] (no quantisation)."""
+    h = F.conv2d(x, sd["encoder.conv_in.weight"], sd["encoder.conv_in.bias"], padding=1)
+    for lv in encoder_topology(dd):
+        p = f"encoder.down.{lv['level']}."
+        for bi in range(len(lv["blocks"])):
+            h = _enc_res(h, sd, p + f"block.{bi}.")
+            if lv["attn"]:
+                h = _enc_attn(h, sd, p + f"attn.{bi}.")
+        if lv["down"]:
+            h = F.conv2d(F.pad(h, (0, 1, 0, 1)), sd[p + "downsample.conv.weight"], sd[p + "downsample.conv.bias"], stride=2)
+    h = _enc_res(h, sd, "encoder.mid.block_1.")
+    h = _enc_attn(h, sd, "encoder.mid.attn_1.")
+    h = _enc_res(h, sd, "encoder.mid.block_2.")
+    h = F.conv2d(_swish(_gn6(h, sd, "encoder.norm_out.")), sd["encoder.conv_out.weight"], sd["encoder.conv_out.bias"], padding=1)
+    return F.conv2d(h, sd["quant_conv.weight"], sd["quant_conv.bias"])
+
+
+def movq_param_spec(dd, embed_dim=4, n_embed=None):
+    """Full MOVQ state dict in the reference's registration order (autoencoder.py:167-174)."""
+    enc = movq_encoder_param_spec(dd, embed_dim)
+    dec = movq_decoder_param_spec(dd, embed_dim, n_embed)
+    qc = [e for e in enc if e[0].startswith("quant_conv.")]
+    enc = [e for e in enc if not e[0].startswith("quant_conv.")]
+    pq = [e for e in dec if e[0].startswith("post_quant_conv.")]
+    dec = [e for e in dec if not e[0].startswith("post_quant_conv.")]
+    return enc + dec + qc + pq
+
+
 def _sn(f, zq, sd, p):
     z = F.interpolate(zq, size=f.shape[-2:], mode="nearest")
     nf = F.group_norm(f, 32, sd[p + "norm_layer.weight"], sd[p + "norm_layer.bias"], 1e-6)

@@ -42,11 +42,10 @@ def test_movq_state_dict_keys_match_reference_spec():
     from oracle import movq_oracle as mo
     m = MOVQ(mo.DDCONFIG_TINY, 64, 4)
     assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == \
-        [(k, tuple(s)) for k, s in mo.movq_decoder_param_spec(mo.DDCONFIG_TINY, 4, 64)]
-    # a reference checkpoint also carries encoder / quant_conv tensors: accepted and ignored
+        [(k, tuple(s)) for k, s in mo.movq_param_spec(dict(mo.DDCONFIG_TINY, double_z=False), 4, 64)]
+    # training checkpoints may carry loss.* entries: dropped
     sd = dict(m.state_dict())
-    sd["encoder.conv_in.weight"] = torch.zeros(1)
-    sd["quant_conv.weight"] = torch.zeros(1)
+    sd["loss.discriminator.main.0.weight"] = torch.zeros(1)
     m.load_state_dict(sd, strict=True)
 
 

@@ -31,12 +31,15 @@ def test_unet_oracle_matches_reference_golden(name):
 def test_movq_oracle_matches_reference_golden():
     from oracle import movq_oracle as mo, synth
     fx = _load("movq_tiny")
-    sd = synth.synth_state_dict(mo.movq_decoder_param_spec(fx["dd"], 4, fx["n_embed"]), seed=fx["weight_seed"])
+    sd = synth.synth_state_dict(mo.movq_param_spec(fx["dd"], 4, fx["n_embed"]), seed=fx["weight_seed"])
     with torch.no_grad():
         y = mo.movq_decode(sd, fx["dd"], fx["z"])
     assert (y - fx["out"]).abs().max().item() <= 1e-5
     zf = fx["z"].permute(0, 2, 3, 1).reshape(-1, 4)
     assert torch.equal(mo.vq_indices(zf, sd["quantize.embedding.weight"]), fx["indices"])  # bit-exact indices
+    with torch.no_grad():
+        ze = mo.movq_encode(sd, fx["dd"], fx["image"])
+    assert (ze - fx["latent"]).abs().max().item() <= 1e-5
 
 
 def test_trajectory_oracle_matches_reference_golden():

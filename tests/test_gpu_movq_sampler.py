@@ -18,7 +18,7 @@ def test_movq_decode_golden():
     from kandinsky2.vqgan import MOVQ
     from oracle import movq_oracle as mo, synth
     fx = _load("movq_tiny")
-    sd = synth.synth_state_dict(mo.movq_decoder_param_spec(fx["dd"], 4, fx["n_embed"]), seed=fx["weight_seed"])
+    sd = synth.synth_state_dict(mo.movq_param_spec(fx["dd"], 4, fx["n_embed"]), seed=fx["weight_seed"])
     m = MOVQ(fx["dd"], fx["n_embed"], 4)
     m.load_state_dict(sd)
     m.to("cuda")
@@ -34,6 +34,10 @@ def test_movq_decode_golden():
     # uint8 tail equals the reference's process_images arithmetic applied to OUR fp32 image
     u8 = m.decode_to_uint8(fx["z"].cuda(), crop_h=14, crop_w=15)
     assert torch.equal(u8, mo.process_images(y)[:, :14, :15])
+    # encoder (image -> latent) vs the reference's MOVQ.encode
+    ze = m.encode(fx["image"].cuda())
+    relz = ((ze - fx["latent"].cuda()).norm() / fx["latent"].cuda().norm()).item()
+    assert ze.shape == fx["latent"].shape and relz < 6e-3, relz
 
 
 def test_movq_decode_mid_vs_oracle():
@@ -43,7 +47,7 @@ def test_movq_decode_mid_vs_oracle():
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
     dd = dict(mo.DDCONFIG_2_1, ch=64, ch_mult=(1, 2, 4), resolution=128)
-    sd = synth.synth_state_dict(mo.movq_decoder_param_spec(dd, 4, 128), seed=9)
+    sd = synth.synth_state_dict(mo.movq_param_spec(dd, 4, 128), seed=9)
     m = MOVQ(dd, 128, 4)
     m.load_state_dict(sd)
     m.to("cuda")
@@ -120,6 +124,24 @@ def test_pipeline_inpainting_21():
     imgs = pipe.generate_inpainting("a hat", lat, mask.numpy(), num_steps=3, batch_size=1, guidance_scale=4, h=64, w=64,
                                     sampler="p_sampler")
     assert len(imgs) == 1 and imgs[0].size == (64, 64)
+    # PIL input goes through the MoVQ encoder; default sampler (DDIM)
+    imgs2 = pipe.generate_inpainting("a hat", imgs[0], mask.numpy(), num_steps=5, batch_size=1, h=64, w=64)
+    assert imgs2[0].size == (64, 64)
+
+
+def test_pipeline_img2img_pil():
+    from kandinsky2 import get_kandinsky2
+    from PIL import Image
+    import numpy as np
+    src = Image.fromarray((np.random.default_rng(0).random((70, 90, 3)) * 255).astype("uint8"))
+    for version in ("2.1", "2.2"):
+        pipe = get_kandinsky2("cuda", task_type="img2img", model_version=version, cache_dir="/nonexistent",
+                              config_overrides=_tiny_overrides())
+        if version == "2.1":
+            out = pipe.generate_img2img("a dog", src, strength=0.6, num_steps=10, batch_size=1, h=64, w=64)
+        else:
+            out = pipe.generate_img2img("a dog", src, strength=0.5, batch_size=1, decoder_steps=6, h=64, w=64)
+        assert len(out) == 1 and out[0].size == (64, 64)
 
 
 def test_ddim_loop_matches_oracle_rule():
