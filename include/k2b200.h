@@ -158,6 +158,15 @@ int k2_sampler_step(const float* model_out, float* x, const float* noise, const 
                     int W, float guidance, int cond_first, float clip, int threshold_mode,
                     const float* inpaint_init, const float* inpaint_mask, float* work, k2_stream_t stream);
 
+/* PLMS / DDIM update with an explicit epsilon history (replaces PLMSSampler.p_sample_plms, samplers.py:571-637, and the
+ * CFG closure): e_t = uncond + g (cond - uncond) from model_out's first 4 channels (C2 channels per sample);
+ * e' = coef[4] e_t + coef[5] hist0 + coef[6] hist1 + coef[7] hist2 (NULL history entries are skipped);
+ * out = coef[2] (coef[0] x - coef[1] e') + coef[3] e'; e_t is also written to `store` if not NULL.  coef is device fp32[8]
+ * = {1/sqrt(a_t), sqrt(1-a_t)/sqrt(a_t), sqrt(a_prev), sqrt(1-a_prev), w0, w1, w2, w3}. */
+int k2_plms_step(const float* model_out, int C2, const float* x, float* out, const float* hist0, const float* hist1,
+                 const float* hist2, float* store, const float* coef, int B, int H, int W, float guidance, int cond_first,
+                 k2_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * MoVQ helpers: nearest-codebook search (quntize.py:89-98; fp32, ties -> lowest index, int64 out),
  * fp32 NCHW -> NHWC transposes for the 4-channel latent, final image quantisation

@@ -334,6 +334,48 @@ __global__ void __launch_bounds__(256) sampler_post_kernel(const SamplerParams p
   p.x[i] = mean + p.coef[6] * expf(0.5f * logvar) * p.noise[i];
 }
 
+// PLMS / DDIM update with an explicit epsilon history (samplers.py:571-637):
+//   e_t  = CFG(model_out)                                  (kandinsky2_1_model.py:222-233, eps channels only)
+//   e'   = w[0]*e_t + w[1]*hist[0] + w[2]*hist[1] + w[3]*hist[2]      (Adams-Bashforth weights chosen by the host)
+//   out  = sqrt(a_prev) * (x - sqrt(1-a_t) e') / sqrt(a_t) + sqrt(1-a_prev) e'      with coef = {1/sqrt(a_t),
+//          sqrt(1-a_t)/sqrt(a_t), sqrt(a_prev), sqrt(1-a_prev)}
+//   optionally e_t is stored into `store` (the history slot the host rotates in).
+struct PlmsParams {
+  const float* model_out;  // [2B, C2, H, W], eps = channels [0, 4)
+  const float* x;          // [B, 4, H, W]
+  float* out;              // [B, 4, H, W] (may alias x)
+  const float* hist[3];
+  float* store;            // or null
+  const float* coef;       // device [8]: c0..c3 as above, w0..w3 = coef[4..8)
+  int B, HW, C2;
+  float guidance;
+  int cond_first;
+};
+
+__global__ void __launch_bounds__(256) plms_step_kernel(const PlmsParams p) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  pdl_wait();
+  pdl_launch();
+  const long long total = static_cast<long long>(p.B) * 4 * p.HW;
+  if (i >= total) return;
+  const int sp = static_cast<int>(i % p.HW);
+  const int c = static_cast<int>((i / p.HW) % 4);
+  const int b = static_cast<int>(i / (4LL * p.HW));
+  const int bc = p.cond_first ? b : b + p.B;
+  const int bu = p.cond_first ? b + p.B : b;
+  const float ec = p.model_out[(static_cast<long long>(bc) * p.C2 + c) * p.HW + sp];
+  const float eu = p.model_out[(static_cast<long long>(bu) * p.C2 + c) * p.HW + sp];
+  const float e_t = eu + p.guidance * (ec - eu);
+  float ep = p.coef[4] * e_t;
+  if (p.hist[0]) ep = fmaf(p.coef[5], p.hist[0][i], ep);
+  if (p.hist[1]) ep = fmaf(p.coef[6], p.hist[1][i], ep);
+  if (p.hist[2]) ep = fmaf(p.coef[7], p.hist[2][i], ep);
+  const float x0 = p.coef[0] * p.x[i] - p.coef[1] * ep;
+  const float xn = p.coef[2] * x0 + p.coef[3] * ep;
+  if (p.store) p.store[i] = e_t;
+  p.out[i] = xn;
+}
+
 // ------------------------------------------------------------------------------------------------
 // MoVQ helpers
 // ------------------------------------------------------------------------------------------------
@@ -635,6 +677,19 @@ int k2_softmax_rows(const void* x, int ldx, void* y, int ldy, long long rows, in
   softmax_rows_kernel<<<static_cast<unsigned int>(rows), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __half*>(x), ldx, reinterpret_cast<__half*>(y), ldy, n, scale * 1.4426950408889634f);
   K2_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int k2_plms_step(const float* model_out, int C2, const float* x, float* out, const float* hist0, const float* hist1,
+                 const float* hist2, float* store, const float* coef, int B, int H, int W, float guidance, int cond_first,
+                 k2_stream_t stream) {
+  K2_REQUIRE(model_out && x && out && coef && B > 0 && C2 >= 4, "plms_step: bad arguments");
+  PlmsParams p;
+  p.model_out = model_out; p.x = x; p.out = out; p.hist[0] = hist0; p.hist[1] = hist1; p.hist[2] = hist2; p.store = store;
+  p.coef = coef; p.B = B; p.HW = H * W; p.C2 = C2; p.guidance = guidance; p.cond_first = cond_first;
+  const long long total = static_cast<long long>(B) * 4 * H * W;
+  K2_CHECK_CUDA(launch_k(plms_step_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), p));
   count_launch();
   return 0;
 }

@@ -236,6 +236,59 @@ class DDIMSampler:
         return out, {}
 
 
+class PLMSSampler(DDIMSampler):
+    """Pseudo linear multistep sampler (samplers.py:334-637) over the DDIM schedule: the first step is an improved-Euler
+    step with TWO UNet evaluations, later steps combine the current CFG epsilon with up to three previous ones
+    (Adams-Bashforth 2/3/4) and apply the DDIM (eta 0) update with the combined epsilon -- k2_plms_step."""
+
+    _AB = {1: (1.5, -0.5, 0.0, 0.0), 2: (23 / 12, -16 / 12, 5 / 12, 0.0), 3: (55 / 24, -59 / 24, 37 / 24, -9 / 24)}
+
+    @torch.no_grad()
+    def sample(self, S, batch_size, shape, conditioning=None, eta=0.0, x_T=None, init_step=None, *, guidance_scale=1.0,
+               cond_first=True, callback=None, **unused):
+        self.make_schedule(S, ddim_eta=eta, init_step=init_step)
+        C, H, W = shape
+        B = batch_size // 2
+        model = self.model
+        device = next(model.parameters()).device
+        x_full = x_T.float().to(device) if x_T is not None else torch.randn(batch_size, C, H, W, device=device)
+        x = x_full[:B].contiguous()
+        step = FusedStep(model, B, H, W, dict(conditioning or {}), guidance_scale, cond_first, 1e30, 0)
+        plan = step.plan
+        a_t, a_p = self.ddim_alphas, self.ddim_alphas_prev
+        ts = self.ddim_timesteps.astype(np.float32)
+        n = self.num_timesteps
+
+        def coef(i, w):
+            row = [1.0 / np.sqrt(a_t[i]), np.sqrt(1.0 - a_t[i]) / np.sqrt(a_t[i]), np.sqrt(a_p[i]), np.sqrt(1.0 - a_p[i])] + list(w)
+            return torch.tensor(row, dtype=torch.float32, device=device)
+
+        def forward(xin, t):
+            plan.x_in[:B].copy_(xin)
+            plan.x_in[B:].copy_(xin)
+            plan.t_in.fill_(float(t))
+            plan.run(model.use_cuda_graph)
+            return plan.out
+
+        hist = []                                      # newest first
+        ring = [torch.empty_like(x) for _ in range(4)]  # epsilon history slots (3 live + the one being written)
+        x_tmp = torch.empty_like(x)
+        for it, i in enumerate(range(n)[::-1]):
+            slot = ring[it % 4]
+            mo = forward(x, ts[i])
+            if not hist:
+                # pseudo improved Euler: x' from e_t, second evaluation at t_next, then the step with (e_t + e_next) / 2
+                ops.plms_step(mo, x, x_tmp, [], slot, coef(i, (1.0, 0.0, 0.0, 0.0)), guidance_scale, cond_first)
+                mo2 = forward(x_tmp, ts[max(i - 1, 0)])
+                ops.plms_step(mo2, x, x, [slot], None, coef(i, (0.5, 0.5, 0.0, 0.0)), guidance_scale, cond_first)
+            else:
+                ops.plms_step(mo, x, x, hist, slot, coef(i, self._AB[len(hist)]), guidance_scale, cond_first)
+            hist = [slot] + hist[:2]
+            if callback is not None:
+                callback(i, x)
+        return torch.cat([x, x], 0), {}
+
+
 class FusedStep:
     """One denoising step = CFG-doubled UNet forward + k2_sampler_step, on static buffers (graph-replayable)."""
 

@@ -302,6 +302,16 @@ def sampler_step(model_out, x, noise, coef, guidance, cond_first, clip=2.0, thre
     return x
 
 
+def plms_step(model_out, x, out, hist, store, coef, guidance, cond_first):
+    """hist: list of up to 3 fp32 [B,4,H,W] tensors, newest first (None entries allowed)."""
+    lib = nat.load()
+    B, _, H, W = x.shape
+    hh = list(hist) + [None] * (3 - len(hist))
+    check(lib.k2_plms_step(ptr(model_out), model_out.shape[1], ptr(x), ptr(out), ptr(hh[0]), ptr(hh[1]), ptr(hh[2]), ptr(store),
+                           ptr(coef), B, H, W, float(guidance), int(cond_first), stream_ptr()))
+    return out
+
+
 def vq_argmin(z, codebook):
     """z fp32 [n, dim], codebook fp32 [n_embed, dim] -> int64 [n] (ties -> lowest index)."""
     lib = nat.load()

@@ -17,7 +17,7 @@ import torch
 
 from . import ops, parallel
 from ._native import K2Error
-from .model.gaussian_diffusion import DDIMSampler, create_ddpm_v22, create_gaussian_diffusion
+from .model.gaussian_diffusion import DDIMSampler, PLMSSampler, create_ddpm_v22, create_gaussian_diffusion
 from .model.model_creation import create_model
 from .utils import prepare_image, prepare_mask, q_sample, uint8_to_pil
 from .vqgan import MOVQ
@@ -134,10 +134,7 @@ class Kandinsky2_1(_DecoderBase):
     def generate_img(self, prompt, img_prompt, batch_size=1, diffusion=None, guidance_scale=7, init_step=None,
                      noise=None, init_img=None, img_mask=None, h=512, w=512, sampler="ddim_sampler", num_steps=50):
         """kandinsky2_1_model.py:184-292. img_prompt = cat([cond image emb, zero image emb]) [2B, 768]."""
-        if sampler not in ("p_sampler", "ddim_sampler"):
-            if sampler == "plms_sampler":
-                raise NotImplementedError("plms_sampler (multi-step history, samplers.py:334-637) is not implemented; "
-                                          "use 'ddim_sampler' or 'p_sampler'")
+        if sampler not in ("p_sampler", "ddim_sampler", "plms_sampler"):
             raise ValueError("Only ddim_sampler and plms_sampler is available")
         new_h, new_w = self.get_new_h_w(h, w)
         rank, ws, lo, hi = self._shard(batch_size)
@@ -164,8 +161,9 @@ class Kandinsky2_1(_DecoderBase):
                                               progress=False, model_kwargs=kw, init_step=init_step,
                                               guidance_scale=guidance_scale, cond_first=True, clip_denoised=True,
                                               sample_generators=self._generators(lo, hi), **inpaint)[:B]
-        else:  # kandinsky2_1_model.py:259-275: DDIM over the un-respaced schedule, eta 0
-            samples, _ = DDIMSampler(self.model, diffusion).sample(num_steps, 2 * B, (4, new_h, new_w), conditioning=kw,
+        else:  # kandinsky2_1_model.py:259-284: DDIM / PLMS over the un-respaced schedule, eta 0
+            cls = DDIMSampler if sampler == "ddim_sampler" else PLMSSampler
+            samples, _ = cls(self.model, diffusion).sample(num_steps, 2 * B, (4, new_h, new_w), conditioning=kw,
                                                                      x_T=noise, init_step=init_step,
                                                                      guidance_scale=guidance_scale, cond_first=True)
             samples = samples[:B]

@@ -101,8 +101,10 @@ def test_pipeline_surface(version):
         mixed = pipe.mix_images(["a cat", "a dog"], [0.3, 0.7], num_steps=3, batch_size=1, h=64, w=64, sampler="p_sampler")
         ddim = pipe.generate_text2img("a red cat", num_steps=10, batch_size=1, h=64, w=64)  # default sampler = ddim_sampler
         assert len(ddim) == 1 and ddim[0].size == (64, 64)
-        with pytest.raises(NotImplementedError):
-            pipe.generate_text2img("x", num_steps=4, sampler="plms_sampler")
+        plms = pipe.generate_text2img("a red cat", num_steps=10, batch_size=1, h=64, w=64, sampler="plms_sampler")
+        assert len(plms) == 1 and plms[0].size == (64, 64)
+        with pytest.raises(ValueError):
+            pipe.generate_text2img("x", num_steps=4, sampler="euler")
     else:
         imgs = pipe.generate_text2img("a red cat", batch_size=2, decoder_steps=4, h=70, w=100)
         again = pipe.generate_text2img("a red cat", batch_size=2, decoder_steps=4, h=70, w=100)
@@ -172,3 +174,46 @@ def test_ddim_loop_matches_oracle_rule():
     rel = ((out[:B] - x).norm() / x.norm()).item()
     # 4 DDIM steps from t = 751: 1/sqrt(a_t) up to ~6 and guidance 3 amplify the UNet's fp16 error per step
     assert rel < 2e-2 and err < 0.15 * x.abs().max().item(), (err, rel, x.abs().max().item())
+
+
+def test_plms_loop_matches_oracle_rule():
+    """PLMS (samplers.py:571-637: improved-Euler first step with two UNet calls, then Adams-Bashforth 2/3/4 over the CFG
+    epsilon history) through k2_plms_step vs the same rule evaluated with the fp32 oracle UNet."""
+    from kandinsky2.model.gaussian_diffusion import PLMSSampler, create_gaussian_diffusion
+    from oracle import diffusion_oracle as do, synth, unet_oracle as uo
+    from tests.test_gpu_unet import _build
+    fx = _load("traj_tiny")
+    cfg = fx["cfg"]
+    sd = synth.synth_state_dict(uo.unet_param_spec(cfg), seed=fx["weight_seed"])
+    m = _build(cfg, sd)
+    d = create_gaussian_diffusion(steps=1000, learn_sigma=True, noise_schedule="linear", rescale_timesteps=True,
+                                  rescale_learned_sigmas=True, timestep_respacing="", linear_start=0.00085, linear_end=0.012)
+    x_T = fx["x_T"].cuda()
+    B = x_T.shape[0]
+    kw = {k: v.cuda() for k, v in fx["cond"].items()}
+    S, gscale = 5, 2.0
+    out, _ = PLMSSampler(m, d).sample(S, 2 * B, (4, 16, 16), conditioning=kw, x_T=torch.cat([x_T, x_T]), guidance_scale=gscale)
+    tt, al, alp = do.ddim_schedule(S)
+    sdc = {k: v.cuda() for k, v in sd.items()}
+
+    def eps_at(x, t):
+        mo = uo.unet_forward(sdc, cfg, torch.cat([x, x]), torch.full((2 * B,), float(t), device="cuda"), **kw)
+        return mo[B:, :4] + gscale * (mo[:B, :4] - mo[B:, :4])
+
+    x, old = x_T.clone(), []
+    with torch.no_grad():
+        for i in range(len(tt))[::-1]:
+            e_t = eps_at(x, tt[i])
+            if len(old) == 0:
+                e_next = eps_at(do.ddim_step(x, e_t, float(al[i]), float(alp[i])), tt[max(i - 1, 0)])
+                ep = (e_t + e_next) / 2
+            elif len(old) == 1:
+                ep = (3 * e_t - old[-1]) / 2
+            elif len(old) == 2:
+                ep = (23 * e_t - 16 * old[-1] + 5 * old[-2]) / 12
+            else:
+                ep = (55 * e_t - 59 * old[-1] + 37 * old[-2] - 9 * old[-3]) / 24
+            x = do.ddim_step(x, ep, float(al[i]), float(alp[i]))
+            old = (old + [e_t])[-3:]
+    rel = ((out[:B] - x).norm() / x.norm()).item()
+    assert rel < 3e-2, rel
