@@ -149,8 +149,9 @@ class Kandinsky2_1(_DecoderBase):
         if self.task_type == "inpainting":
             init = init_img.to(self.device).float()
             mask = img_mask.to(self.device).float()
-            kw["inpaint_image"] = (init * mask)[: 2 * B] if init.shape[0] >= 2 * B else (init * mask).repeat(2 * B, 1, 1, 1)
-            kw["inpaint_mask"] = mask[: 2 * B] if mask.shape[0] >= 2 * B else mask.repeat(2 * B, 1, 1, 1)
+            # the reference repeats ONE image / mask for the cond and uncond rows (:536-537); same image for every sample here
+            kw["inpaint_image"] = (init * mask)[:1].repeat(2 * B, 1, 1, 1)
+            kw["inpaint_mask"] = mask[:1].repeat(2 * B, 1, 1, 1)
             inpaint = dict(inpaint_init=init[:1].repeat(B, 1, 1, 1), inpaint_mask=mask[:1].repeat(B, 1, 1, 1))
         if noise is None:
             x = self._latents(lo, hi, (4, new_h, new_w))
