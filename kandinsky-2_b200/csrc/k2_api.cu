@@ -256,9 +256,22 @@ int k2_conv_gemm(const K2ConvSrc* srcs, int nsrc, int NB, int H, int W, const vo
     const int nt = (Cout + BN - 1) / BN;
     const long long units = static_cast<long long>(two_cta ? (p.m_tiles + 1) / 2 : p.m_tiles) * nt;
     const int slots = two_cta ? num_sms() / 2 : num_sms();
+    // split-K factor: waves of work units x (K chunks per unit + ~12 chunk-times of per-unit ramp / epilogue) + the
+    // second pass; this ranking reproduces the measured order on every small-M shape of profiles/conv_sweep_small_r1.txt
     int want = 1;
-    if (units * 5 < slots * 3 && kchunks >= 48) want = 3;        // < 60 % of the machine
-    else if (units * 2 < slots * 3 && kchunks >= 64) want = 2;   // < 1.5 waves
+    {
+      long long best = -1;
+      for (int sp = 1; sp <= 8; ++sp) {
+        const int kps = (kchunks + sp - 1) / sp;
+        if (sp > 1 && (kps < 8 || (sp - 1) * kps >= kchunks)) continue;
+        const long long waves = (units * sp + slots - 1) / slots;
+        const long long cost = waves * (kps + 12) + 2 * (sp - 1);
+        if (best < 0 || cost < best) {
+          best = cost;
+          want = sp;
+        }
+      }
+    }
     if (g_force_split > 0) want = g_force_split;
     const bool can = workspace && out_mode == 0 && Cout % 8 == 0;
     if (want > 1 && can) {

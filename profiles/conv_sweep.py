@@ -39,10 +39,19 @@ def time_it(fn, reps=20):
     return s.elapsed_time(e) / reps * 1e3  # us
 
 
+TWO = (1, 2)
+SPLITS = (1, 2, 3, 4, 6, 8)
+
+
 def main():
     g = torch.Generator(device="cuda").manual_seed(0)
     check = os.environ.get("K2_SWEEP_CHECK", "1") == "1"
-    for (N, H, W, Cin, Cout, label) in SHAPES:
+    global TWO, SPLITS
+    shapes = SHAPES
+    if os.environ.get("K2_SWEEP_SMALL"):
+        shapes = [s for s in SHAPES if s[1] <= 24]
+        TWO, SPLITS = (2,), (1, 2, 3, 4, 5, 6, 7, 8)
+    for (N, H, W, Cin, Cout, label) in shapes:
         x = torch.randn(N, H, W, Cin, device="cuda", generator=g).half()
         w = torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) / (3 * Cin ** 0.5)
         b = torch.randn(Cout, device="cuda", generator=g)
@@ -53,7 +62,7 @@ def main():
         if check:
             ref = F.conv2d(x[:1].float().permute(0, 3, 1, 2), w.half().float(), b, padding=1).permute(0, 2, 3, 1)
         print(f"# {label}: M={N * H * W} K={9 * Cin} N={Cout} {gflop:.1f} GFLOP", flush=True)
-        for two, bn, sp in itertools.product((1, 2), (128, 192, 256), (1, 2, 3, 4, 6, 8)):
+        for two, bn, sp in itertools.product(TWO, (128, 192, 256), SPLITS):
             if sp > 1 and N * H * W > 8 * 48 * 48:
                 continue
             ops.set_tuning(2, two); ops.set_tuning(0, bn); ops.set_tuning(1, sp)
