@@ -18,6 +18,7 @@ static int g_force_bn = 0;
 static int g_force_split = 0;  // 0 auto, 1 off, n>1 forced
 static int g_force_2cta = 0;   // 0 auto, 1 off, 2 on
 static int g_attn_stagger = 300;
+static int g_attn_poly = 0;  // measured: the softmax is not MUFU-bound (profiles/README.md), offloading only adds instructions
 static int g_pdl = 0;          // programmatic dependent launch of the step's kernels
 static int g_halo_mode = 0;    // 0 off; 1/2: dense halo rows (pitch 10) without/with base offset; 3/4: pitch 16
 
@@ -31,6 +32,7 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 bool pdl_enabled() { return g_pdl != 0; }
 int attention_stagger() { return g_attn_stagger; }
+int attention_poly_mode() { return g_attn_poly; }
 
 int num_sms() {
   static int n = 0;
@@ -163,6 +165,10 @@ int k2_set_tuning(int key, int value) {
   }
   if (key == 5) {
     g_attn_stagger = value;
+    return 0;
+  }
+  if (key == 6) {
+    g_attn_poly = value;
     return 0;
   }
 

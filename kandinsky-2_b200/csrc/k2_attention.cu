@@ -53,6 +53,9 @@ __device__ __forceinline__ float ex2(float x) {
 
 // 384 threads: warp0 TMA producer, warp1 MMA issuer, warp2 TMEM allocator, warp3 idle,
 // warps 4-7 softmax warpgroup of query tile 0, warps 8-11 softmax warpgroup of query tile 1.
+// POLY: bit i set -> element i (mod 8) of every score row takes the MUFU-free exp2 (see k2_common.cuh: the softmax is
+// bound by the MUFU pipe; moving ~3/8 of the exponentials to the FMA pipe balances the two).
+template <int POLY>
 __global__ void __launch_bounds__(384, 1) attention_d64_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -106,7 +109,7 @@ __global__ void __launch_bounds__(384, 1) attention_d64_kernel(const __grid_cons
 
   if (warp_idx == 0) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
+    if (elect_one()) {  // one lane, and ptxas KNOWS it is one: UTCHMMA / UTMALDG operands need no per-lane waterfall loop
       mbar_arrive_expect_tx(q_full, ntile * TILE_BYTES);
       for (int t = 0; t < ntile; ++t)
         tma_load_3d(smem + SMEM_Q + t * TILE_BYTES, &p.tmQKV, q_full, head * p.hs + p.q_off, q0 + t * BQ, b);
@@ -135,7 +138,7 @@ __global__ void __launch_bounds__(384, 1) attention_d64_kernel(const __grid_cons
     // ===================================== MMA issuer ========================================
     // program order per key block j:  for each tile t: [P_t(j-1) V(j-1) -> O_t]  then  [Q_t K(j)^T -> S_t]
     // so the tensor core works on one tile's products while the other tile's warpgroup exponentiates.
-    if (lane == 0) {
+    if (elect_one()) {  // one lane, and ptxas KNOWS it is one: UTCHMMA / UTMALDG operands need no per-lane waterfall loop
       constexpr uint32_t idesc_s = make_idesc_f16(BQ, BKV, 0, 0);  // Q (K-major) x K (K-major)
       constexpr uint32_t idesc_o = make_idesc_f16(BQ, HD, 0, 1);   // P (K-major) x V (MN-major)
       auto issue_pv = [&](int t, int jb, int stage_b) {
@@ -231,8 +234,9 @@ __global__ void __launch_bounds__(384, 1) attention_d64_kernel(const __grid_cons
           }
         }
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+        if (POLY & 0x400) mx0 = __uint_as_float(s0[lane & 31]);
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
+        for (int e = 0; e < ((POLY & 0x400) ? 0 : 32); ++e) {
           mx0 = fmaxf(mx0, __uint_as_float(s0[e]));
           mx1 = fmaxf(mx1, __uint_as_float(s1[e]));
           mx2 = fmaxf(mx2, __uint_as_float(s2[e]));
@@ -268,8 +272,10 @@ __global__ void __launch_bounds__(384, 1) attention_d64_kernel(const __grid_cons
           uint32_t packed[16];
 #pragma unroll
           for (int e = 0; e < 32; e += 2) {
-            const float p0 = ex2(fmaf(__uint_as_float(sv[e]), c, -m_used));
-            const float p1 = ex2(fmaf(__uint_as_float(sv[e + 1]), c, -m_used));
+            const float a0 = fmaf(__uint_as_float(sv[e]), c, -m_used);
+            const float a1 = fmaf(__uint_as_float(sv[e + 1]), c, -m_used);
+            const float p0 = (POLY & 0x100) ? a0 : (((POLY >> (e & 7)) & 1) ? ex2_poly(a0) : ex2(a0));
+            const float p1 = (POLY & 0x100) ? a1 : (((POLY >> ((e + 1) & 7)) & 1) ? ex2_poly(a1) : ex2(a1));
             l0 += p0;
             l1 += p1;
             __half2 h = __floats2half2_rn(p0, p1);
@@ -280,8 +286,9 @@ __global__ void __launch_bounds__(384, 1) attention_d64_kernel(const __grid_cons
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int cc = (ch & 1) * 4 + q;
-            *reinterpret_cast<uint4*>(atom + ((cc ^ (row & 7)) << 4)) =
-                make_uint4(packed[q * 4], packed[q * 4 + 1], packed[q * 4 + 2], packed[q * 4 + 3]);
+            if (!(POLY & 0x200) || packed[q * 4] == 0x12345678u)
+              *reinterpret_cast<uint4*>(atom + ((cc ^ (row & 7)) << 4)) =
+                  make_uint4(packed[q * 4], packed[q * 4 + 1], packed[q * 4 + 2], packed[q * 4 + 3]);
           }
         };
         emit(s0, 0);
@@ -336,11 +343,27 @@ __global__ void __launch_bounds__(384, 1) attention_d64_kernel(const __grid_cons
 int launch_attention_d64(const AttnParams& p, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    K2_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    K2_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<0x00>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    K2_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<0x24>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    K2_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<0x52>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    K2_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<0x55>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    K2_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<0x100>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    K2_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<0x200>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    K2_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<0x400>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    K2_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<0x700>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     attr_set = true;
   }
   dim3 grid((p.T + QT * BQ - 1) / (QT * BQ), p.heads, p.B);
-  K2_CHECK_CUDA(launch_k(attention_d64_kernel, grid, dim3(384), SMEM_TOTAL, stream, p));
+  switch (attention_poly_mode()) {  // share of the exponentials taken off the MUFU pipe: 0, 2/8, 3/8, 4/8
+    case 0: K2_CHECK_CUDA(launch_k(attention_d64_kernel<0x00>, grid, dim3(384), SMEM_TOTAL, stream, p)); break;
+    case 2: K2_CHECK_CUDA(launch_k(attention_d64_kernel<0x24>, grid, dim3(384), SMEM_TOTAL, stream, p)); break;
+    case 4: K2_CHECK_CUDA(launch_k(attention_d64_kernel<0x55>, grid, dim3(384), SMEM_TOTAL, stream, p)); break;
+    case 101: K2_CHECK_CUDA(launch_k(attention_d64_kernel<0x100>, grid, dim3(384), SMEM_TOTAL, stream, p)); break;  // ablations
+    case 102: K2_CHECK_CUDA(launch_k(attention_d64_kernel<0x200>, grid, dim3(384), SMEM_TOTAL, stream, p)); break;
+    case 104: K2_CHECK_CUDA(launch_k(attention_d64_kernel<0x400>, grid, dim3(384), SMEM_TOTAL, stream, p)); break;
+    case 107: K2_CHECK_CUDA(launch_k(attention_d64_kernel<0x700>, grid, dim3(384), SMEM_TOTAL, stream, p)); break;
+    default: K2_CHECK_CUDA(launch_k(attention_d64_kernel<0x52>, grid, dim3(384), SMEM_TOTAL, stream, p)); break;
+  }
   return 0;
 }
 

@@ -313,6 +313,28 @@ __device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.laun
 
 // x * sigmoid(x) with one MUFU.EX2 and one MUFU.RCP (an IEEE division here costs ~10 extra instructions per element,
 // and GroupNorm+SiLU touches 1.3 G elements per step)
-__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }
+// On B200 the MUFU (XU) pipe retires 8 lanes/clk/SM -- a warp-wide ex2 / rcp / tanh occupies it for 16 cycles -- and both
+// GroupNorm+SiLU (1.3 G elements per step) and the attention softmax are bound by it, so every transcendental counts:
+// SiLU as h + h*tanh(h), h = x/2 (ONE MUFU.TANH, rel. error 2^-11, below the fp16 rounding of the stored result)
+// instead of ex2 + rcp (two).
+__device__ __forceinline__ float silu_f(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+// 2^x on the FMA/ALU pipes only (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], degree-4 minimax
+// polynomial for 2^f (max rel. error 2.7e-6), exponent added to the bit pattern.  Valid for x <= 126; x < -126
+// (including -inf) returns 2^-126 ~ 0.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -126.f);
+  const float t = x + 12582912.f;            // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float f = x - (t - 12582912.f);
+  float p = fmaf(0.009560510516166687f, f, 0.05591703951358795f);
+  p = fmaf(p, f, 0.24024981260299683f);
+  p = fmaf(p, f, 0.6931219696998596f);
+  p = fmaf(p, f, 0.9999991655349731f);
+  return __int_as_float(__float_as_int(p) + ((__float_as_int(t) - 0x4B400000) << 23));
+}
 
 }  // namespace k2

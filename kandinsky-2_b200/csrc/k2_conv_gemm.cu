@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
 
   if (warp_idx == 0) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
+    if (elect_one()) {  // one lane, and ptxas KNOWS it is one: UTCHMMA / UTMALDG operands need no per-lane waterfall loop
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx_bytes = p.a_box_bytes + C::B_STAGE_BYTES;
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
     }
   } else if (warp_idx == 1) {
     // ===================================== MMA issuer ========================================
-    if (lane == 0) {
+    if (elect_one()) {  // one lane, and ptxas KNOWS it is one: UTCHMMA / UTMALDG operands need no per-lane waterfall loop
       constexpr uint32_t idesc = make_idesc_f16(BM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -406,7 +406,7 @@ conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p) {
 
   if (warp_idx == 0) {
     // ===================================== TMA producer (both CTAs) ==========================
-    if (lane == 0) {
+    if (elect_one()) {  // one lane, and ptxas KNOWS it is one: UTCHMMA / UTMALDG operands need no per-lane waterfall loop
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx_bytes = 2u * (p.a_box_bytes + C::B_STAGE_BYTES);
@@ -451,7 +451,7 @@ conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p) {
     }
   } else if (warp_idx == 1) {
     // ===================================== MMA issuer (leader CTA only) ======================
-    if (lane == 0 && rank == 0) {
+    if (rank == 0 && elect_one()) {
       constexpr uint32_t idesc = make_idesc_f16(256, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -612,7 +612,7 @@ conv_gemm3_kernel(const __grid_constant__ ConvGemmParams p) {
 
   if (warp_idx == 0) {
     // ===================================== TMA producer (both CTAs) ==========================
-    if (lane == 0) {
+    if (elect_one()) {  // one lane, and ptxas KNOWS it is one: UTCHMMA / UTMALDG operands need no per-lane waterfall loop
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       const uint32_t halo_bytes = static_cast<uint32_t>(18 * pitch * 128);
@@ -657,7 +657,7 @@ conv_gemm3_kernel(const __grid_constant__ ConvGemmParams p) {
     }
   } else if (warp_idx == 1) {
     // ===================================== MMA issuer (leader CTA only) ======================
-    if (lane == 0 && rank == 0) {
+    if (rank == 0 && elect_one()) {
       constexpr uint32_t idesc = make_idesc_f16(256, BN, 0, 0);
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;

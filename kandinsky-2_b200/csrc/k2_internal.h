@@ -94,6 +94,7 @@ struct AttnParams {
   int stagger_cycles;  // initial delay of the second query tile's first score product (de-phases the warpgroups)
 };
 int attention_stagger();
+int attention_poly_mode();  // eighths of the softmax exponentials evaluated without MUFU: 0, 2, 3, 4
 int launch_attention_d64(const AttnParams& p, cudaStream_t stream);
 
 }  // namespace k2
