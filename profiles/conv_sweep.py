@@ -48,6 +48,9 @@ def main():
     check = os.environ.get("K2_SWEEP_CHECK", "1") == "1"
     global TWO, SPLITS
     shapes = SHAPES
+    if os.environ.get("K2_SWEEP_BIG"):
+        shapes = [s for s in SHAPES if s[1] >= 48]
+        TWO, SPLITS = (1, 2), (1,)
     if os.environ.get("K2_SWEEP_SMALL"):
         shapes = [s for s in SHAPES if s[1] <= 24]
         TWO, SPLITS = (2,), (1, 2, 3, 4, 5, 6, 7, 8)
