@@ -33,6 +33,8 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 bool pdl_enabled() { return g_pdl != 0; }
 int attention_stagger() { return g_attn_stagger; }
 int attention_poly_mode() { return g_attn_poly; }
+static unsigned long long g_attn_trace = 0;
+unsigned long long* attention_trace_buffer() { return reinterpret_cast<unsigned long long*>(g_attn_trace); }
 
 int num_sms() {
   static int n = 0;
@@ -169,6 +171,14 @@ int k2_set_tuning(int key, int value) {
   }
   if (key == 6) {
     g_attn_poly = value;
+    return 0;
+  }
+  if (key == 7) {  // diagnostics: device address of the attention trace buffer, low / high 32 bits
+    g_attn_trace = (g_attn_trace & 0xffffffff00000000ull) | static_cast<unsigned int>(value);
+    return 0;
+  }
+  if (key == 8) {
+    g_attn_trace = (g_attn_trace & 0xffffffffull) | (static_cast<unsigned long long>(static_cast<unsigned int>(value)) << 32);
     return 0;
   }
 

@@ -15,8 +15,11 @@
 //     acc = acc*alpha + O_j    in registers (fp32), normalised by the row sum at the end.
 // V tiles are used as an MN-major B operand exactly as TMA lands them ([key][64 d] rows), so V is never
 // transposed.  Warp roles: warp0 TMA producer (Q once, K/V ring of 3 stages), warp1 MMA issuer, warp2 TMEM
-// allocator, warps4-7 softmax/epilogue.  S_{j+1} is issued before P_j is consumed, so the tensor core
-// works on the next scores while the softmax warps exponentiate the current ones.
+// allocator, warps 4-7 / 8-11 softmax + epilogue of query tile 0 / 1.  A warpgroup releases S_t as soon as the scores
+// sit in its registers (s_free), and the issuer answers with S_t(j+1) right away: the next scores are complete long
+// before the exponentials of block j are, so in steady state the warpgroups never wait for the tensor core (measured
+// with the clock64 trace, profiles/attn_trace.py: the old order P_t(j) -> PV_t(j) -> S_t(j+1) left each warpgroup idle
+// for ~1000 of every ~3450 cycles).  pv_done tells the warpgroup that O_t is current and the P_t buffer is free.
 #include <string.h>
 
 #include <algorithm>
@@ -55,6 +58,17 @@ __device__ __forceinline__ float ex2(float x) {
 // warps 4-7 softmax warpgroup of query tile 0, warps 8-11 softmax warpgroup of query tile 1.
 // POLY: bit i set -> element i (mod 8) of every score row takes the MUFU-free exp2 (see k2_common.cuh: the softmax is
 // bound by the MUFU pipe; moving ~3/8 of the exponentials to the FMA pipe balances the two).
+// Diagnostics (POLY bit 0x8000 + tuning keys 7/8): CTA (0,0,0) stamps clock64() at the hand-over points of key blocks
+// TRACE_J0 .. TRACE_J0+3 into trace[role][block][point]; role 0/1 = first warp of each softmax warpgroup, 2 = MMA issuer.
+constexpr int TRACE_J0 = 4;
+template <int POLY>
+__device__ __forceinline__ void trace_pt(const AttnParams& p, int role, int j, int point) {
+  if constexpr ((POLY & 0x8000) != 0) {
+    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j >= TRACE_J0 && j < TRACE_J0 + 4)
+      p.trace[(role * 4 + (j - TRACE_J0)) * 8 + point] = static_cast<unsigned long long>(clock64());
+  }
+}
+
 template <int POLY>
 __global__ void __launch_bounds__(384, 1) attention_d64_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -66,8 +80,9 @@ __global__ void __launch_bounds__(384, 1) attention_d64_kernel(const __grid_cons
   uint64_t* kv_empty = kv_full + KV_STAGES;  // KV_STAGES
   uint64_t* s_full = kv_empty + KV_STAGES;   // QT
   uint64_t* p_full = s_full + QT;            // QT
-  uint64_t* o_full = p_full + QT;            // QT
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + QT);
+  uint64_t* pv_done = p_full + QT;           // QT: P_t(j) V(j) retired -> O_t current, P_t buffer reusable
+  uint64_t* s_free = pv_done + QT;           // QT: S_t(j) is in the warpgroup's registers -> S_t(j+1) may be issued
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(s_free + QT);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -92,7 +107,8 @@ __global__ void __launch_bounds__(384, 1) attention_d64_kernel(const __grid_cons
     for (int i = 0; i < QT; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);  // one arrival per softmax warp of the tile
-      mbar_init(&o_full[i], 1);
+      mbar_init(&pv_done[i], 1);
+      mbar_init(&s_free[i], 4);
     }
     fence_barrier_init();
   }
@@ -136,8 +152,8 @@ __global__ void __launch_bounds__(384, 1) attention_d64_kernel(const __grid_cons
     }
   } else if (warp_idx == 1) {
     // ===================================== MMA issuer ========================================
-    // program order per key block j:  for each tile t: [P_t(j-1) V(j-1) -> O_t]  then  [Q_t K(j)^T -> S_t]
-    // so the tensor core works on one tile's products while the other tile's warpgroup exponentiates.
+    // program order per key block j:  [Q_t K(j+1)^T -> S_t as soon as s_free_t(j)] for both tiles, then
+    // [P_t(j) V(j) -> O_t as soon as p_full_t(j)] for both tiles.
     if (elect_one()) {  // one lane, and ptxas KNOWS it is one: UTCHMMA / UTMALDG operands need no per-lane waterfall loop
       constexpr uint32_t idesc_s = make_idesc_f16(BQ, BKV, 0, 0);  // Q (K-major) x K (K-major)
       constexpr uint32_t idesc_o = make_idesc_f16(BQ, HD, 0, 1);   // P (K-major) x V (MN-major)
@@ -164,39 +180,50 @@ __global__ void __launch_bounds__(384, 1) attention_d64_kernel(const __grid_cons
         umma_commit(&s_full[t]);
       };
       mbar_wait(q_full, 0);
-      int stage = 0, pstage = 0;
-      uint32_t phase = 0;
-      for (int j = 0; j < nblk; ++j) {
-        mbar_wait(&kv_full[stage], phase);
-        tc_fence_after();
-        for (int t = 0; t < ntile; ++t) {
-          if (j > 0) {
-            mbar_wait(&p_full[t], (j - 1) & 1);
-            tc_fence_after();
-            issue_pv(t, j - 1, pstage);
-            if (t == ntile - 1) umma_commit(&kv_empty[pstage]);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      for (int t = 0; t < ntile; ++t) {
+        issue_s(t, 0);
+        if (t == 0 && ntile == 2 && p.stagger_cycles > 0) {
+          // optional de-phasing of the two softmax warpgroups (tuning key 5)
+          const long long t0 = clock64();
+          while (clock64() - t0 < p.stagger_cycles) {
           }
-          issue_s(t, stage);
-          if (j == 0 && t == 0 && ntile == 2) {
-            // De-phase the two softmax warpgroups by about half a block: if both exponentiate at the same time they
-            // share the MUFU pipe and then both wait for the tensor core (lock-step, measured 52 % MUFU utilisation);
-            // started half a period apart, each has the MUFU to itself while the other's products are issued.
-            const long long t0 = clock64();
-            while (clock64() - t0 < p.stagger_cycles) {
-            }
-          }
-        }
-        pstage = stage;
-        if (++stage == KV_STAGES) {
-          stage = 0;
-          phase ^= 1;
         }
       }
-      for (int t = 0; t < ntile; ++t) {
-        mbar_wait(&p_full[t], (nblk - 1) & 1);
-        tc_fence_after();
-        issue_pv(t, nblk - 1, pstage);
-        umma_commit(&o_full[t]);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < nblk; ++j) {
+        int nstage = stage + 1;
+        uint32_t nphase = phase;
+        if (nstage == KV_STAGES) {
+          nstage = 0;
+          nphase ^= 1;
+        }
+        if (j + 1 < nblk) {
+          // S_t(j+1) as soon as the warpgroup holds S_t(j) in registers: the next scores are ready long before the
+          // softmax of block j ends, so the warpgroups never wait for the tensor core in steady state
+          mbar_wait(&kv_full[nstage], nphase);
+          tc_fence_after();
+          for (int t = 0; t < ntile; ++t) {
+            trace_pt<POLY>(p, 2, j, t * 4 + 0);
+            mbar_wait(&s_free[t], j & 1);
+            tc_fence_after();
+            issue_s(t, nstage);
+            trace_pt<POLY>(p, 2, j, t * 4 + 1);
+          }
+        }
+        for (int t = 0; t < ntile; ++t) {
+          mbar_wait(&p_full[t], j & 1);
+          trace_pt<POLY>(p, 2, j, t * 4 + 2);
+          tc_fence_after();
+          issue_pv(t, j, stage);
+          umma_commit(&pv_done[t]);
+          if (t == ntile - 1) umma_commit(&kv_empty[stage]);
+          trace_pt<POLY>(p, 2, j, t * 4 + 3);
+        }
+        stage = nstage;
+        phase = nphase;
       }
     }
   } else if (warp_idx >= 4) {
@@ -215,7 +242,10 @@ __global__ void __launch_bounds__(384, 1) attention_d64_kernel(const __grid_cons
 
       for (int j = 0; j < nblk; ++j) {
         const int valid = (j < nctx) ? min(BKV, p.Tc - j * BKV) : min(BKV, p.T - (j - nctx) * BKV);
+        const bool tr = (ew == 0 && lane == 0);
+        if (tr) trace_pt<POLY>(p, t, j, 0);
         mbar_wait(&s_full[t], j & 1);
+        if (tr) trace_pt<POLY>(p, t, j, 1);
         tc_fence_after();
         uint32_t s0[32], s1[32], s2[32], s3[32];
         tmem_ld_32x32b_x32(s_addr, s0);
@@ -223,6 +253,10 @@ __global__ void __launch_bounds__(384, 1) attention_d64_kernel(const __grid_cons
         tmem_ld_32x32b_x32(s_addr + 64, s2);
         tmem_ld_32x32b_x32(s_addr + 96, s3);
         tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[t]);
+        if (tr) trace_pt<POLY>(p, t, j, 2);
         if (valid < BKV) {  // ragged tail / short encoder block (block-uniform branch): masked scores -> -inf
           const uint32_t ninf = __float_as_uint(-INFINITY);
 #pragma unroll
@@ -246,6 +280,8 @@ __global__ void __launch_bounds__(384, 1) attention_d64_kernel(const __grid_cons
         if (j == 0) {
           m_used = m_blk;
         } else {
+          mbar_wait(&pv_done[t], (j - 1) & 1);  // O_t holds blocks < j, and the P_t buffer is free again
+          tc_fence_after();
           // O_t lives in TMEM and is rescaled only when some row's maximum has outgrown the stale one by 2^8:
           // exact arithmetic either way (numerator and denominator share m_used), far fewer TMEM round trips.
           const bool grow = m_blk > m_used + RESCALE_GAP;
@@ -266,6 +302,7 @@ __global__ void __launch_bounds__(384, 1) attention_d64_kernel(const __grid_cons
             m_used = m_new;
           }
         }
+        if (tr) trace_pt<POLY>(p, t, j, 3);
         // P = exp2(S*c - m_used) -> fp16 -> swizzled shared memory (K-major A operand of the PV product)
         float l0 = 0.f, l1 = 0.f;
         auto emit = [&](const uint32_t (&sv)[32], int ch) {
@@ -296,14 +333,16 @@ __global__ void __launch_bounds__(384, 1) attention_d64_kernel(const __grid_cons
         emit(s2, 2);
         emit(s3, 3);
         l_run += l0 + l1;
+        if (tr) trace_pt<POLY>(p, t, j, 4);
         // P_t(j) visible to the async proxy, S_t / O_t accesses retired -> let the MMA warp go
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[t]);
+        if (tr) trace_pt<POLY>(p, t, j, 5);
       }
       // epilogue: O / l
-      mbar_wait(&o_full[t], 0);
+      mbar_wait(&pv_done[t], (nblk - 1) & 1);
       tc_fence_after();
       uint32_t o0[32], o1[32];
       tmem_ld_32x32b_x32(o_addr, o0);
@@ -351,6 +390,8 @@ int launch_attention_d64(const AttnParams& p, cudaStream_t stream) {
     K2_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<0x200>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     K2_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<0x400>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     K2_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<0x700>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    K2_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<0x8000>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
+    K2_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<0x8700>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     attr_set = true;
   }
   dim3 grid((p.T + QT * BQ - 1) / (QT * BQ), p.heads, p.B);
@@ -362,6 +403,8 @@ int launch_attention_d64(const AttnParams& p, cudaStream_t stream) {
     case 102: K2_CHECK_CUDA(launch_k(attention_d64_kernel<0x200>, grid, dim3(384), SMEM_TOTAL, stream, p)); break;
     case 104: K2_CHECK_CUDA(launch_k(attention_d64_kernel<0x400>, grid, dim3(384), SMEM_TOTAL, stream, p)); break;
     case 107: K2_CHECK_CUDA(launch_k(attention_d64_kernel<0x700>, grid, dim3(384), SMEM_TOTAL, stream, p)); break;
+    case 200: K2_CHECK_CUDA(launch_k(attention_d64_kernel<0x8000>, grid, dim3(384), SMEM_TOTAL, stream, p)); break;  // traced
+    case 207: K2_CHECK_CUDA(launch_k(attention_d64_kernel<0x8700>, grid, dim3(384), SMEM_TOTAL, stream, p)); break;
     default: K2_CHECK_CUDA(launch_k(attention_d64_kernel<0x52>, grid, dim3(384), SMEM_TOTAL, stream, p)); break;
   }
   return 0;
@@ -408,6 +451,7 @@ extern "C" int k2_attention_d64(const void* qkv, int ldq, int hs, int q_off, int
   p.ldo = ldo;
   p.scale_log2e = scale * 1.4426950408889634f;
   p.stagger_cycles = attention_stagger();
+  p.trace = attention_trace_buffer();
   int rc = launch_attention_d64(p, static_cast<cudaStream_t>(stream));
   if (rc == 0) count_launch();
   return rc;

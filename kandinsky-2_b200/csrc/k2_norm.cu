@@ -180,10 +180,11 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const __half* __restrict_
 // partial[(tile*4 + warp)][channel] = (sum, sumsq) over 32 output rows.  One block per (image, group): fixed-order
 // fp64 fold over the image's row groups and the group's channels (which may span the two concatenated sources).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) gn_finalize_kernel(const float2* __restrict__ part0, int C0, int rg0,
+constexpr int FIN_T = 512;  // the fold is latency-bound (short strided segments): many loads in flight per CTA
+__global__ void __launch_bounds__(FIN_T) gn_finalize_kernel(const float2* __restrict__ part0, int C0, int rg0,
                                                           const float2* __restrict__ part1, int C1, int rg1, int HW,
                                                           int groups, float eps, float* __restrict__ stats) {
-  __shared__ double red[2][4];
+  __shared__ double red[2][FIN_T / 32];
   const int n = blockIdx.y, g = blockIdx.x;
   const int C = C0 + C1;
   const int cpg = C / groups;
@@ -203,17 +204,17 @@ __global__ void __launch_bounds__(128) gn_finalize_kernel(const float2* __restri
       return __ldg(p0 + static_cast<long long>(rg) * Cs + (i - rg * w));
     };
     int i = threadIdx.x;
-    for (; i + 3 * 128 < items; i += 4 * 128) {
+    for (; i + 3 * FIN_T < items; i += 4 * FIN_T) {
       float2 t[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) t[u] = load(i + u * 128);
+      for (int u = 0; u < 4; ++u) t[u] = load(i + u * FIN_T);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         fs[u] += t[u].x;
         fq[u] += t[u].y;
       }
     }
-    for (; i < items; i += 128) {
+    for (; i < items; i += FIN_T) {
       const float2 t = load(i);
       fs[0] += t.x;
       fq[0] += t.y;
@@ -234,8 +235,13 @@ __global__ void __launch_bounds__(128) gn_finalize_kernel(const float2* __restri
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    s = (red[0][0] + red[0][1]) + (red[0][2] + red[0][3]);
-    q = (red[1][0] + red[1][1]) + (red[1][2] + red[1][3]);
+    s = 0.0;
+    q = 0.0;
+#pragma unroll
+    for (int w = 0; w < FIN_T / 32; ++w) {  // fixed order: deterministic
+      s += red[0][w];
+      q += red[1][w];
+    }
     const double cnt = static_cast<double>(HW) * cpg;
     const double mean = s / cnt;
     double var = q / cnt - mean * mean;
@@ -476,7 +482,7 @@ int k2_gn_finalize(const float* part0, int C0, int rg0, const float* part1, int 
   K2_REQUIRE(part0 && stats && C0 > 0 && (part1 || C1 == 0) && (C0 + C1) % groups == 0 && rg0 > 0 && (C1 == 0 || rg1 > 0),
              "gn_finalize: bad arguments");
   dim3 grid(groups, NB);
-  K2_CHECK_CUDA(launch_k(gn_finalize_kernel, grid, dim3(128), 0, static_cast<cudaStream_t>(stream),
+  K2_CHECK_CUDA(launch_k(gn_finalize_kernel, grid, dim3(FIN_T), 0, static_cast<cudaStream_t>(stream),
                          reinterpret_cast<const float2*>(part0), C0, rg0, reinterpret_cast<const float2*>(part1), C1, rg1, HW,
                          groups, eps, stats));
   count_launch();

@@ -10,12 +10,12 @@ import torch  # noqa: E402
 from kandinsky2 import ops  # noqa: E402
 
 g = torch.Generator(device="cuda").manual_seed(0)
-for (B, heads, T, Tc) in [(8, 12, 2304, 32)]:
+for (B, heads, T, Tc) in [(8, 12, 2304, 32), (8, 18, 576, 32), (8, 24, 144, 32)]:
     qkv = torch.randn(B, T, heads * 192, device="cuda", generator=g).half()
     enc = torch.randn(B, Tc, heads * 128, device="cuda", generator=g).half()
     out = torch.empty(B, T, heads * 64, device="cuda", dtype=torch.float16)
     flops = 4 * B * heads * T * (T + Tc) * 64
-    for delay in (0, 3, 101, 102, 104, 107):  # eighths of the exponentials on the FMA pipe (tuning key 6)
+    for delay in (0, 2, 3, 4):  # eighths of the exponentials on the FMA pipe (tuning key 6)
         ops.set_tuning(6, delay)
         for _ in range(3):
             ops.attention_d64(qkv, heads, enc, out=out)
