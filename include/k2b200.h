@@ -37,7 +37,7 @@ void k2_reset_launch_count(void);
  * key 2 = CTA-pair kernel (0 auto, 1 off, 2 on); key 3 = halo 3x3 kernel (0 off, 1-4 layout variants);
  * key 4 = programmatic dependent launch (0/1); key 5 = attention warpgroup de-phasing delay in cycles;
  * key 6 = eighths (0, 2, 3, 4) of the softmax exponentials evaluated on the FMA pipe instead of MUFU (1xx = ablations,
- * 2xx = traced variants); keys 7 / 8 = low / high 32 bits of a device buffer (96 x u64) that the traced attention
+ * 2xx = traced variants); keys 7 / 8 = low / high 32 bits of a device buffer (384 x u64) that the traced attention
  * variants fill with clock64 stamps of CTA (0,0,0) -- diagnostics only, see profiles/attn_probe.py. */
 int k2_set_tuning(int key, int value);
 

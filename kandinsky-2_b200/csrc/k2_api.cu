@@ -94,44 +94,48 @@ int encode_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t
 }
 
 // Pick the (TN, TH, TW) output box of one M tile (<= 128 pixels = the rows of one MMA tile): minimise the number of
-// tiles; boxes may span several images (TN > 1) when whole-image row blocks pack better -- e.g. 12x12 latents: 2 images
-// x 5 rows x 12 = 120 pixels per tile (12 tiles) instead of 1 image x 6 rows (16 tiles, 56 % of the MMA rows used).
+// tiles.  Boxes may span several images (TN > 1) when that packs at least 15 % fewer tiles than the best single-image
+// box -- e.g. 12x12 latents, 8 images: 8 images x 4 x 4 pixels = 128 rows per tile, 9 tiles with every MMA row used,
+// instead of 1 image x 6 rows x 12 (16 tiles, 56 % used).  Single-image boxes are preferred otherwise because the fused
+// GroupNorm statistics of the epilogue need them.
 static void choose_tile(int NB, int H, int W, int& TN, int& TH, int& TW) {
-  long long best_tiles = -1;
-  int bn = 1, bw = 1, bh = 1;
+  long long best_tiles[2] = {-1, -1};  // [0]: TN == 1 only, [1]: any TN
+  int bn[2] = {1, 1}, bw[2] = {1, 1}, bh[2] = {1, 1};
   const int wmax = W < 128 ? W : 128;
   for (int tw = 1; tw <= wmax; ++tw) {
     const long long tiles_w = (W + tw - 1) / tw;
     for (int tn = 1; tn <= NB && tn * tw <= 128; ++tn) {
-      if (tn > 1 && tw != W) continue;  // multi-image boxes only with full-width rows (keeps the halo reuse sane)
       int thmax = 128 / (tw * tn);
       if (thmax > H) thmax = H;
       if (thmax < 1) continue;
       const long long tiles_h = (H + thmax - 1) / thmax;
       const int th = static_cast<int>((H + tiles_h - 1) / tiles_h);  // balanced
       const long long tiles = tiles_h * tiles_w * ((NB + tn - 1) / tn);
-      bool better = best_tiles < 0 || tiles < best_tiles;
-      if (!better && tiles == best_tiles) {
-        // ties: fewer images per box (fused GroupNorm statistics need TN == 1), then the squarer box, then the wider
-        if (tn != bn) {
-          better = tn < bn;
-        } else {
-          const int d_new = tw > th ? tw - th : th - tw;
-          const int d_old = bw > bh ? bw - bh : bh - bw;
-          better = (d_new < d_old) || (d_new == d_old && tw > bw);
+      for (int k = (tn == 1 ? 0 : 1); k < 2; ++k) {
+        bool better = best_tiles[k] < 0 || tiles < best_tiles[k];
+        if (!better && tiles == best_tiles[k]) {
+          // ties: fewer images per box, then the squarer box, then the wider
+          if (tn != bn[k]) {
+            better = tn < bn[k];
+          } else {
+            const int d_new = tw > th ? tw - th : th - tw;
+            const int d_old = bw[k] > bh[k] ? bw[k] - bh[k] : bh[k] - bw[k];
+            better = (d_new < d_old) || (d_new == d_old && tw > bw[k]);
+          }
         }
-      }
-      if (better) {
-        best_tiles = tiles;
-        bn = tn;
-        bw = tw;
-        bh = th;
+        if (better) {
+          best_tiles[k] = tiles;
+          bn[k] = tn;
+          bw[k] = tw;
+          bh[k] = th;
+        }
       }
     }
   }
-  TN = bn;
-  TW = bw;
-  TH = bh;
+  const int k = (best_tiles[1] * 100 <= best_tiles[0] * 85) ? 1 : 0;
+  TN = bn[k];
+  TW = bw[k];
+  TH = bh[k];
 }
 
 }  // namespace k2

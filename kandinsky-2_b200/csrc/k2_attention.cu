@@ -42,7 +42,9 @@ constexpr int SMEM_Q = 0;
 constexpr int SMEM_KV = SMEM_Q + QT * TILE_BYTES;
 constexpr int SMEM_P = SMEM_KV + KV_STAGES * 2 * TILE_BYTES;
 constexpr int SMEM_BAR = SMEM_P + QT * P_BYTES;
-constexpr int SMEM_TOTAL = SMEM_BAR + 256 + 1024;
+constexpr int SMEM_XCH = SMEM_BAR + 256;   // fp32 [tile][parity][half][128] block maxima + [tile][half][128] row sums
+constexpr int SMEM_TOTAL = SMEM_XCH + 6144 + 1024;
+constexpr int NTHREADS = 128 + 512;      // 4 control warps + 16 softmax warps
 constexpr int TMEM_COLS = 512;  // S: 2 x 128, O: 2 x 64 -> 384, rounded to a power of two
 constexpr int TM_S = 0;         // S of tile t at TM_S + t*128
 constexpr int TM_O = 256;       // O of tile t at TM_O + t*64
@@ -54,23 +56,23 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-// 384 threads: warp0 TMA producer, warp1 MMA issuer, warp2 TMEM allocator, warp3 idle,
-// warps 4-7 softmax warpgroup of query tile 0, warps 8-11 softmax warpgroup of query tile 1.
-// POLY: bit i set -> element i (mod 8) of every score row takes the MUFU-free exp2 (see k2_common.cuh: the softmax is
-// bound by the MUFU pipe; moving ~3/8 of the exponentials to the FMA pipe balances the two).
+// 640 threads: warp0 TMA producer, warp1 MMA issuer, warp2 TMEM allocator, warp3 idle, warps 4-19 softmax
+// (query tile = (w-4)/8, key half = ((w-4)/4)%2, TMEM lane quarter = w%4).
+// POLY: bit i set -> element i (mod 8) of every score row takes the MUFU-free exp2 (k2_common.cuh), bit 15 -> traced.
 // Diagnostics (POLY bit 0x8000 + tuning keys 7/8): CTA (0,0,0) stamps clock64() at the hand-over points of key blocks
-// TRACE_J0 .. TRACE_J0+3 into trace[role][block][point]; role 0/1 = first warp of each softmax warpgroup, 2 = MMA issuer.
-constexpr int TRACE_J0 = 4;
+// TRACE_J0 .. TRACE_J0+TRACE_NJ-1 into trace[role][block][point]; role 0/1 = first warp of each softmax warpgroup, 2 = MMA issuer.
+constexpr int TRACE_J0 = 0;
+constexpr int TRACE_NJ = 16;
 template <int POLY>
 __device__ __forceinline__ void trace_pt(const AttnParams& p, int role, int j, int point) {
   if constexpr ((POLY & 0x8000) != 0) {
-    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j >= TRACE_J0 && j < TRACE_J0 + 4)
-      p.trace[(role * 4 + (j - TRACE_J0)) * 8 + point] = static_cast<unsigned long long>(clock64());
+    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && j >= TRACE_J0 && j < TRACE_J0 + TRACE_NJ)
+      p.trace[(role * TRACE_NJ + (j - TRACE_J0)) * 8 + point] = static_cast<unsigned long long>(clock64());
   }
 }
 
 template <int POLY>
-__global__ void __launch_bounds__(384, 1) attention_d64_kernel(const __grid_constant__ AttnParams p) {
+__global__ void __launch_bounds__(NTHREADS, 1) attention_d64_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -106,9 +108,9 @@ __global__ void __launch_bounds__(384, 1) attention_d64_kernel(const __grid_cons
     }
     for (int i = 0; i < QT; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 4);  // one arrival per softmax warp of the tile
+      mbar_init(&p_full[i], 8);  // one arrival per softmax warp of the tile
       mbar_init(&pv_done[i], 1);
-      mbar_init(&s_free[i], 4);
+      mbar_init(&s_free[i], 8);
     }
     fence_barrier_init();
   }
@@ -227,56 +229,67 @@ __global__ void __launch_bounds__(384, 1) attention_d64_kernel(const __grid_cons
       }
     }
   } else if (warp_idx >= 4) {
-    // ===================================== softmax warpgroups + epilogue ======================
-    const int t = (warp_idx - 4) >> 2;           // query tile of this warpgroup
+    // ===================================== softmax warps + epilogue ===========================
+    // 16 warps = 2 query tiles x 2 key halves x 4 TMEM lane quarters: thread (t, h, row) owns keys [64h, 64h+64) of one
+    // score row.  Four softmax warps per scheduler (instead of two) hide the MUFU / TMEM latencies of each other; the
+    // two halves of a row agree on the block maximum through shared memory and one 256-thread named barrier per block.
+    const int sw = warp_idx - 4;
+    const int t = sw >> 3;                        // query tile
+    const int h = (sw >> 2) & 1;                  // key half of the 128-key block
     const int ew = warp_idx & 3;                  // TMEM lane quarter
     const int row = ew * 32 + lane;               // query row in the tile == TMEM lane
     if (t < ntile) {
       const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
-      const uint32_t s_addr = lane_addr + TM_S + t * BKV;
-      const uint32_t o_addr = lane_addr + TM_O + t * HD;
-      uint8_t* p_row = smem + SMEM_P + t * P_BYTES + row * 128;
+      const uint32_t s_addr = lane_addr + TM_S + t * BKV + h * 64;
+      const uint32_t o_addr = lane_addr + TM_O + t * HD + h * 32;
+      const uint32_t p_row_s = smem_u32(smem + SMEM_P + t * P_BYTES + h * TILE_BYTES + row * 128);
+      float* xch = reinterpret_cast<float*>(smem + SMEM_XCH) + t * 512;  // [parity][half][row]
       float m_used = 0.f;   // the (possibly stale) maximum the exponentials are taken against, log2 domain
-      float l_run = 0.f;
+      float l_run = 0.f;    // this half's share of the row sum
       const float c = p.scale_log2e;
+      const bool tr = (ew == 0 && lane == 0 && h == 0);
+
+      // S_t(0) -> registers; from then on the loads of block j+1 are issued inside block j's exponentials (each 32-score
+      // quarter as soon as its registers are free), so neither the s_full hand-over nor the TMEM latency is exposed
+      uint32_t s0[32], s1[32];
+      mbar_wait(&s_full[t], 0);
+      tc_fence_after();
+      tmem_ld_32x32b_x32(s_addr, s0);
+      tmem_ld_32x32b_x32(s_addr + 32, s1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[t]);
 
       for (int j = 0; j < nblk; ++j) {
-        const int valid = (j < nctx) ? min(BKV, p.Tc - j * BKV) : min(BKV, p.T - (j - nctx) * BKV);
-        const bool tr = (ew == 0 && lane == 0);
+        const int valid = ((j < nctx) ? min(BKV, p.Tc - j * BKV) : min(BKV, p.T - (j - nctx) * BKV)) - h * 64;
+        const bool more = j + 1 < nblk;
         if (tr) trace_pt<POLY>(p, t, j, 0);
-        mbar_wait(&s_full[t], j & 1);
-        if (tr) trace_pt<POLY>(p, t, j, 1);
-        tc_fence_after();
-        uint32_t s0[32], s1[32], s2[32], s3[32];
-        tmem_ld_32x32b_x32(s_addr, s0);
-        tmem_ld_32x32b_x32(s_addr + 32, s1);
-        tmem_ld_32x32b_x32(s_addr + 64, s2);
-        tmem_ld_32x32b_x32(s_addr + 96, s3);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_free[t]);
-        if (tr) trace_pt<POLY>(p, t, j, 2);
-        if (valid < BKV) {  // ragged tail / short encoder block (block-uniform branch): masked scores -> -inf
+        if (valid < 64) {  // ragged tail / short encoder block (block-uniform branch): masked scores -> -inf
           const uint32_t ninf = __float_as_uint(-INFINITY);
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
             if (e >= valid) s0[e] = ninf;
             if (32 + e >= valid) s1[e] = ninf;
-            if (64 + e >= valid) s2[e] = ninf;
-            if (96 + e >= valid) s3[e] = ninf;
           }
         }
-        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-        if (POLY & 0x400) mx0 = __uint_as_float(s0[lane & 31]);
+        float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-        for (int e = 0; e < ((POLY & 0x400) ? 0 : 32); ++e) {
-          mx0 = fmaxf(mx0, __uint_as_float(s0[e]));
-          mx1 = fmaxf(mx1, __uint_as_float(s1[e]));
-          mx2 = fmaxf(mx2, __uint_as_float(s2[e]));
-          mx3 = fmaxf(mx3, __uint_as_float(s3[e]));
+        for (int e = 0; e < 32; e += 4) {  // 3-input maxima (FMNMX3): 32 instructions for the 64 scores
+          mx0 = fmax3(mx0, __uint_as_float(s0[e]), __uint_as_float(s0[e + 1]));
+          mx1 = fmax3(mx1, __uint_as_float(s0[e + 2]), __uint_as_float(s0[e + 3]));
         }
-        const float m_blk = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * c;
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) {
+          mx0 = fmax3(mx0, __uint_as_float(s1[e]), __uint_as_float(s1[e + 1]));
+          mx1 = fmax3(mx1, __uint_as_float(s1[e + 2]), __uint_as_float(s1[e + 3]));
+        }
+        const float m_half = fmaxf(mx0, mx1) * c;
+        float* slot = xch + (j & 1) * 256;
+        slot[h * 128 + row] = m_half;
+        named_bar_sync(1 + t, 256);
+        const float m_blk = fmaxf(m_half, slot[(h ^ 1) * 128 + row]);
+        if (tr) trace_pt<POLY>(p, t, j, 1);
         if (j == 0) {
           m_used = m_blk;
         } else {
@@ -284,74 +297,86 @@ __global__ void __launch_bounds__(384, 1) attention_d64_kernel(const __grid_cons
           tc_fence_after();
           // O_t lives in TMEM and is rescaled only when some row's maximum has outgrown the stale one by 2^8:
           // exact arithmetic either way (numerator and denominator share m_used), far fewer TMEM round trips.
+          // Both halves of a row see the same m_blk and m_used, so they take the same branch; each rescales 32 columns.
           const bool grow = m_blk > m_used + RESCALE_GAP;
           if (__any_sync(0xffffffffu, grow)) {
             const float m_new = grow ? m_blk : m_used;
             const float alpha = ex2(m_used - m_new);
 #pragma unroll 1
-            for (int hhalf = 0; hhalf < 2; ++hhalf) {  // 32 columns at a time: the score row stays live in registers
-              uint32_t o[32];
-              tmem_ld_32x32b_x32(o_addr + hhalf * 32, o);
+            for (int oc = 0; oc < 32; oc += 8) {  // rare path: 8 columns at a time so the score row stays in registers
+              uint32_t o[8];
+              tmem_ld_32x32b_x8(o_addr + oc, o);
               tmem_ld_wait();
 #pragma unroll
-              for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
-              tmem_st_32x32b_x32(o_addr + hhalf * 32, o);
+              for (int e = 0; e < 8; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+              tmem_st_32x32b_x8(o_addr + oc, o);
             }
             tmem_st_wait();
             l_run *= alpha;
             m_used = m_new;
           }
         }
-        if (tr) trace_pt<POLY>(p, t, j, 3);
+        if (tr) trace_pt<POLY>(p, t, j, 2);
         // P = exp2(S*c - m_used) -> fp16 -> swizzled shared memory (K-major A operand of the PV product)
         float l0 = 0.f, l1 = 0.f;
-        auto emit = [&](const uint32_t (&sv)[32], int ch) {
+        auto emit = [&](const uint32_t (&sv)[32], int half32) {
           uint32_t packed[16];
 #pragma unroll
           for (int e = 0; e < 32; e += 2) {
             const float a0 = fmaf(__uint_as_float(sv[e]), c, -m_used);
             const float a1 = fmaf(__uint_as_float(sv[e + 1]), c, -m_used);
-            const float p0 = (POLY & 0x100) ? a0 : (((POLY >> (e & 7)) & 1) ? ex2_poly(a0) : ex2(a0));
-            const float p1 = (POLY & 0x100) ? a1 : (((POLY >> ((e + 1) & 7)) & 1) ? ex2_poly(a1) : ex2(a1));
+            const float p0 = ((POLY >> (e & 7)) & 1) ? ex2_poly(a0) : ex2(a0);
+            const float p1 = ((POLY >> ((e + 1) & 7)) & 1) ? ex2_poly(a1) : ex2(a1);
             l0 += p0;
             l1 += p1;
-            __half2 h = __floats2half2_rn(p0, p1);
-            packed[e >> 1] = *reinterpret_cast<uint32_t*>(&h);
+            __half2 hh = __floats2half2_rn(p0, p1);
+            packed[e >> 1] = *reinterpret_cast<uint32_t*>(&hh);
           }
-          // 32 keys = 4 chunks of 16 B; key group ch -> swizzle atom (ch>>1), chunks (ch&1)*4 .. +3
-          uint8_t* atom = p_row + (ch >> 1) * TILE_BYTES;
+          // 32 keys = 4 chunks of 16 B inside this half's 64-key swizzle atom: chunks half32*4 .. +3
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const int cc = (ch & 1) * 4 + q;
-            if (!(POLY & 0x200) || packed[q * 4] == 0x12345678u)
-              *reinterpret_cast<uint4*>(atom + ((cc ^ (row & 7)) << 4)) =
-                  make_uint4(packed[q * 4], packed[q * 4 + 1], packed[q * 4 + 2], packed[q * 4 + 3]);
+            const int cc = half32 * 4 + q;
+            sts_v4(p_row_s + ((cc ^ (row & 7)) << 4), packed[q * 4], packed[q * 4 + 1], packed[q * 4 + 2], packed[q * 4 + 3]);
           }
         };
         emit(s0, 0);
+        if (more) {  // S_t(j+1) has been complete for a long time (issued right after s_free(j)): no stall here
+          mbar_wait(&s_full[t], (j + 1) & 1);
+          tc_fence_after();
+          tmem_ld_32x32b_x32(s_addr, s0);
+        }
+        if (tr) trace_pt<POLY>(p, t, j, 3);
         emit(s1, 1);
-        emit(s2, 2);
-        emit(s3, 3);
+        if (more) tmem_ld_32x32b_x32(s_addr + 32, s1);
         l_run += l0 + l1;
         if (tr) trace_pt<POLY>(p, t, j, 4);
-        // P_t(j) visible to the async proxy, S_t / O_t accesses retired -> let the MMA warp go
+        // P_t(j) visible to the async proxy, O_t accesses retired -> let the MMA warp go
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[t]);
+        if (more) {
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_free[t]);
+        }
         if (tr) trace_pt<POLY>(p, t, j, 5);
       }
-      // epilogue: O / l
+      // epilogue: O / l, each half writes 32 of the 64 channels
+      float* lx = reinterpret_cast<float*>(smem + SMEM_XCH) + 1024 + t * 256;
+      lx[h * 128 + row] = l_run;
       mbar_wait(&pv_done[t], (nblk - 1) & 1);
       tc_fence_after();
-      uint32_t o0[32], o1[32];
+      uint32_t o0[32];
       tmem_ld_32x32b_x32(o_addr, o0);
-      tmem_ld_32x32b_x32(o_addr + 32, o1);
       tmem_ld_wait();
+      named_bar_sync(1 + t, 256);
+      const float l_tot = lx[row] + lx[128 + row];
       const int q = q0 + t * BQ + row;
       if (q < p.T) {
-        const float inv = 1.f / l_run;
-        __half* orow = p.out + (static_cast<long long>(b) * p.T + q) * p.ldo + head * HD;
+        const float inv = 1.f / l_tot;
+        __half* orow = p.out + (static_cast<long long>(b) * p.T + q) * p.ldo + head * HD + h * 32;
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
           uint4 ov;
@@ -360,10 +385,6 @@ __global__ void __launch_bounds__(384, 1) attention_d64_kernel(const __grid_cons
           for (int e = 0; e < 4; ++e)
             oh[e] = __floats2half2_rn(__uint_as_float(o0[v * 8 + 2 * e]) * inv, __uint_as_float(o0[v * 8 + 2 * e + 1]) * inv);
           *reinterpret_cast<uint4*>(orow + v * 8) = ov;
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            oh[e] = __floats2half2_rn(__uint_as_float(o1[v * 8 + 2 * e]) * inv, __uint_as_float(o1[v * 8 + 2 * e + 1]) * inv);
-          *reinterpret_cast<uint4*>(orow + 32 + v * 8) = ov;
         }
       }
     }
@@ -386,26 +407,16 @@ int launch_attention_d64(const AttnParams& p, cudaStream_t stream) {
     K2_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<0x24>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     K2_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<0x52>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     K2_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<0x55>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    K2_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<0x100>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    K2_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<0x200>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    K2_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<0x400>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    K2_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<0x700>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     K2_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<0x8000>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
-    K2_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<0x8700>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL));
     attr_set = true;
   }
   dim3 grid((p.T + QT * BQ - 1) / (QT * BQ), p.heads, p.B);
   switch (attention_poly_mode()) {  // share of the exponentials taken off the MUFU pipe: 0, 2/8, 3/8, 4/8
-    case 0: K2_CHECK_CUDA(launch_k(attention_d64_kernel<0x00>, grid, dim3(384), SMEM_TOTAL, stream, p)); break;
-    case 2: K2_CHECK_CUDA(launch_k(attention_d64_kernel<0x24>, grid, dim3(384), SMEM_TOTAL, stream, p)); break;
-    case 4: K2_CHECK_CUDA(launch_k(attention_d64_kernel<0x55>, grid, dim3(384), SMEM_TOTAL, stream, p)); break;
-    case 101: K2_CHECK_CUDA(launch_k(attention_d64_kernel<0x100>, grid, dim3(384), SMEM_TOTAL, stream, p)); break;  // ablations
-    case 102: K2_CHECK_CUDA(launch_k(attention_d64_kernel<0x200>, grid, dim3(384), SMEM_TOTAL, stream, p)); break;
-    case 104: K2_CHECK_CUDA(launch_k(attention_d64_kernel<0x400>, grid, dim3(384), SMEM_TOTAL, stream, p)); break;
-    case 107: K2_CHECK_CUDA(launch_k(attention_d64_kernel<0x700>, grid, dim3(384), SMEM_TOTAL, stream, p)); break;
-    case 200: K2_CHECK_CUDA(launch_k(attention_d64_kernel<0x8000>, grid, dim3(384), SMEM_TOTAL, stream, p)); break;  // traced
-    case 207: K2_CHECK_CUDA(launch_k(attention_d64_kernel<0x8700>, grid, dim3(384), SMEM_TOTAL, stream, p)); break;
-    default: K2_CHECK_CUDA(launch_k(attention_d64_kernel<0x52>, grid, dim3(384), SMEM_TOTAL, stream, p)); break;
+    case 0: K2_CHECK_CUDA(launch_k(attention_d64_kernel<0x00>, grid, dim3(NTHREADS), SMEM_TOTAL, stream, p)); break;
+    case 2: K2_CHECK_CUDA(launch_k(attention_d64_kernel<0x24>, grid, dim3(NTHREADS), SMEM_TOTAL, stream, p)); break;
+    case 4: K2_CHECK_CUDA(launch_k(attention_d64_kernel<0x55>, grid, dim3(NTHREADS), SMEM_TOTAL, stream, p)); break;
+    case 200: K2_CHECK_CUDA(launch_k(attention_d64_kernel<0x8000>, grid, dim3(NTHREADS), SMEM_TOTAL, stream, p)); break;  // traced
+    default: K2_CHECK_CUDA(launch_k(attention_d64_kernel<0x52>, grid, dim3(NTHREADS), SMEM_TOTAL, stream, p)); break;
   }
   return 0;
 }

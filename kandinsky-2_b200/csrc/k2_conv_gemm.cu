@@ -31,6 +31,9 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 
+constexpr int EPI_STAGE_FLOATS = 32 * 33;              // per-warp staging: 4224 B (4096 used)
+constexpr int EPI_BYTES = 4 * EPI_STAGE_FLOATS * 4 + 4 * 256 * 4;  // + per-warp bias copy (<= 256 columns)
+
 template <int BN>
 struct Cfg {
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
@@ -38,7 +41,7 @@ struct Cfg {
   static constexpr int STAGES = (BN >= 256) ? 4 : (BN >= 192 ? 5 : (BN >= 128 ? 6 : 8));
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
   static constexpr int BAR_BYTES = 256;
-  static constexpr int STAT_BYTES = 4 * 32 * 33 * 4;  // epilogue transpose buffer for the fused GroupNorm statistics
+  static constexpr int STAT_BYTES = EPI_BYTES;  // epilogue staging (output transpose, residual, statistics) + bias copies
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + STAT_BYTES + 1024;  // +1024 alignment slack
 };
 
@@ -54,7 +57,17 @@ __device__ __forceinline__ void decode_m_tile(const ConvGemmParams& p, int m_idx
 }
 
 // Epilogue of one (128-row x BN-column) accumulator tile held in this CTA's TMEM at column `acc_col`:
-// tcgen05.ld -> + bias (+ residual) -> fp16 rows (out_mode 0) or fp32 NCHW (out_mode 1).
+// tcgen05.ld -> + bias (+ residual) -> fp16 rows (out_mode 0), fp32 split-K partials (out_mode 2) or fp32 NCHW
+// (out_mode 1).
+//
+// A thread owns one accumulator ROW (TMEM lane), so storing straight from registers makes every warp store touch 32
+// different cache lines with 16 bytes each (and every residual load likewise): with short K loops (the attention
+// qkv / proj GEMMs, 12..24 chunks) that epilogue, not the tensor core, set the pace (profiles/conv_small_k.py).  The
+// fp16 / split-K paths therefore go through a per-warp shared-memory transpose (32 rows x 128 B, 16-byte pieces XOR-
+// swizzled by the row): registers -> smem by row, smem -> global with 8 lanes per row, i.e. 4 complete 128-byte lines
+// per store instruction; the residual comes in the same way (coalesced load -> smem -> own row), the bias is read as
+// broadcast LDS.128 from a per-warp copy, and the fused GroupNorm statistics are column sums over the staged fp16 tile.
+
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t tmem_base, int acc_col, int ew, int lane,
                                               int n0, int y0, int x0, int n_idx, int split, int m_idx, float* stat_smem) {
@@ -68,6 +81,128 @@ __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t 
       const int n = n0 + tn, y = y0 + th, x = x0 + tw;
       const bool valid = (tn < p.TN) && (n < p.NB) && (y < p.H) && (x < p.W);
       const long long out_row = (static_cast<long long>(n) * p.H + y) * p.W + x;
+      if constexpr (BN % 64 == 0) {
+        if ((p.out_mode == 0 && p.Cout % 64 == 0) || (p.out_mode == 2 && p.Cout % 32 == 0)) {
+          const uint32_t stage = smem_u32(stat_smem + ew * EPI_STAGE_FLOATS);  // [32 rows][8 x 16 B], piece ^= row & 7
+          float* bsm = stat_smem + 4 * EPI_STAGE_FLOATS + ew * 256;
+          const int my_pix = valid ? static_cast<int>(out_row) : -1;
+          const int sub = lane >> 3, piece = lane & 7;
+          int pix[8];  // pixel (output row) of the 8 staged rows this lane copies out: rows i*4 + sub
+#pragma unroll
+          for (int i = 0; i < 8; ++i) pix[i] = __shfl_sync(0xffffffffu, my_pix, i * 4 + sub);
+          const uint32_t own = stage + lane * 128;
+          const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + static_cast<uint32_t>(acc_col);
+          if (p.out_mode == 2) {
+            // split-K: raw fp32 partial sums [split][M][Cout] (bias / residual / statistics in the finalize pass)
+            float* wsb = p.ws + static_cast<long long>(split) * p.M_total * p.Cout;
+#pragma unroll 1
+            for (int j = 0; j < BN / 32; ++j) {
+              const int col0 = n_idx * BN + j * 32;
+              if (col0 >= p.Cout) break;
+              uint32_t r[32];
+              tmem_ld_32x32b_x32(taddr0 + j * 32, r);
+              tmem_ld_wait();
+#pragma unroll
+              for (int v = 0; v < 8; ++v)
+                sts_v4(own + ((v ^ (lane & 7)) << 4), r[v * 4], r[v * 4 + 1], r[v * 4 + 2], r[v * 4 + 3]);
+              __syncwarp();
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int rr = i * 4 + sub;
+                const uint4 v4 = lds_v4(stage + rr * 128 + ((piece ^ (rr & 7)) << 4));
+                if (pix[i] >= 0)
+                  *reinterpret_cast<uint4*>(wsb + static_cast<long long>(pix[i]) * p.Cout + col0 + piece * 4) = v4;
+              }
+              __syncwarp();
+            }
+            return;
+          }
+          if (p.bias) {
+#pragma unroll
+            for (int c = lane; c < BN; c += 32) bsm[c] = (n_idx * BN + c < p.Cout) ? __ldg(p.bias + n_idx * BN + c) : 0.f;
+            __syncwarp();
+          }
+          __half* outb = reinterpret_cast<__half*>(p.out);
+#pragma unroll 1
+          for (int jp = 0; jp < BN / 64; ++jp) {
+            const int col0 = n_idx * BN + jp * 64;
+            if (col0 >= p.Cout) break;
+            if (p.residual) {  // coalesced: 8 lanes x 16 B per row, 4 rows per instruction -> staged by row
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int rr = i * 4 + sub;
+                uint4 v4 = make_uint4(0u, 0u, 0u, 0u);
+                if (pix[i] >= 0)
+                  v4 = *reinterpret_cast<const uint4*>(p.residual + static_cast<long long>(pix[i]) * p.ldr + col0 + piece * 8);
+                sts_v4(stage + rr * 128 + ((piece ^ (rr & 7)) << 4), v4.x, v4.y, v4.z, v4.w);
+              }
+              __syncwarp();
+            }
+            uint32_t r[64];
+            {
+              uint32_t(&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
+              uint32_t(&r1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[32]);
+              tmem_ld_32x32b_x32(taddr0 + jp * 64, r0);
+              tmem_ld_32x32b_x32(taddr0 + jp * 64 + 32, r1);
+              tmem_ld_wait();
+            }
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {  // 8 columns = one 16-byte piece of the staged row
+              float f[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(r[v * 8 + e]);
+              if (p.bias) {
+                const float4 b0 = *reinterpret_cast<const float4*>(bsm + jp * 64 + v * 8);
+                const float4 b1 = *reinterpret_cast<const float4*>(bsm + jp * 64 + v * 8 + 4);
+                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+              }
+              const uint32_t slot = own + ((v ^ (lane & 7)) << 4);
+              if (p.residual) {
+                const uint4 rv = lds_v4(slot);
+                const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 t = __half22float2(rh[e]);
+                  f[2 * e] += t.x;
+                  f[2 * e + 1] += t.y;
+                }
+              }
+              uint32_t o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const __half2 hh = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+                o[e] = valid ? *reinterpret_cast<const uint32_t*>(&hh) : 0u;  // rows outside the image count as zeros
+              }
+              sts_v4(slot, o[0], o[1], o[2], o[3]);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = i * 4 + sub;
+              const uint4 v4 = lds_v4(stage + rr * 128 + ((piece ^ (rr & 7)) << 4));
+              if (pix[i] >= 0) *reinterpret_cast<uint4*>(outb + static_cast<long long>(pix[i]) * p.ldo + col0 + piece * 8) = v4;
+            }
+            if (p.gn_part) {
+              // fused GroupNorm statistics of the fp16-ROUNDED stored values: lane l sums columns 2l, 2l+1 over the 32 rows
+              float s1a = 0.f, s2a = 0.f, s1b = 0.f, s2b = 0.f;
+#pragma unroll
+              for (int rr = 0; rr < 32; ++rr) {
+                const uint32_t w = lds_u32(stage + rr * 128 + (((lane >> 2) ^ (rr & 7)) << 4) + ((lane & 3) << 2));
+                const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w));
+                s1a += t.x;
+                s2a = fmaf(t.x, t.x, s2a);
+                s1b += t.y;
+                s2b = fmaf(t.y, t.y, s2b);
+              }
+              *reinterpret_cast<float4*>(p.gn_part + (static_cast<long long>(m_idx) * 4 + ew) * p.Cout + col0 + 2 * lane) =
+                  make_float4(s1a, s2a, s1b, s2b);
+            }
+            __syncwarp();
+          }
+          return;
+        }
+      }
 #pragma unroll 1
       for (int j = 0; j < BN / CH; ++j) {
         const uint32_t taddr =
@@ -351,7 +486,7 @@ struct Cfg2 {
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = (BN >= 256) ? 6 : (BN >= 192 ? 7 : 8);
   static constexpr int TMEM_COLS = 512;                      // 2 accumulator buffers at columns 0 and 256
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 4 * 32 * 33 * 4 + 1024;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + EPI_BYTES + 1024;
 };
 
 template <int BN>
@@ -549,7 +684,7 @@ struct Cfg3 {
   static constexpr int B_STAGES = (BN >= 256) ? 4 : 5;
   static constexpr int BAR_OFF = A_STAGES * A_STAGE + B_STAGES * B_STAGE;
   static constexpr int STAT_OFF = BAR_OFF + 256;
-  static constexpr int SMEM_BYTES = STAT_OFF + 4 * 32 * 33 * 4 + 1024;
+  static constexpr int SMEM_BYTES = STAT_OFF + EPI_BYTES + 1024;
 };
 
 template <int BN>

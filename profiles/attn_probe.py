@@ -15,8 +15,10 @@ for (B, heads, T, Tc) in [(8, 12, 2304, 32), (8, 18, 576, 32), (8, 24, 144, 32)]
     enc = torch.randn(B, Tc, heads * 128, device="cuda", generator=g).half()
     out = torch.empty(B, T, heads * 64, device="cuda", dtype=torch.float16)
     flops = 4 * B * heads * T * (T + Tc) * 64
-    for delay in (0, 2, 3, 4):  # eighths of the exponentials on the FMA pipe (tuning key 6)
+    # tuning key 6: eighths of the exponentials on the FMA pipe; key 5: initial de-phasing of the two query tiles (cycles)
+    for delay, stag in ((0, 0), (0, 300), (0, 1000), (0, 1400), (0, 1800), (2, 1400), (3, 1400), (4, 1400)):
         ops.set_tuning(6, delay)
+        ops.set_tuning(5, stag)
         for _ in range(3):
             ops.attention_d64(qkv, heads, enc, out=out)
         torch.cuda.synchronize()
@@ -27,4 +29,4 @@ for (B, heads, T, Tc) in [(8, 12, 2304, 32), (8, 18, 576, 32), (8, 24, 144, 32)]
         e.record()
         torch.cuda.synchronize()
         us = s.elapsed_time(e) / 20 * 1e3
-        print(f"T={T} heads={heads} poly={delay}/8: {us:.1f} us {flops / us / 1e6:.0f} TF/s", flush=True)
+        print(f"T={T} heads={heads} poly={delay}/8 stagger={stag}: {us:.1f} us {flops / us / 1e6:.0f} TF/s", flush=True)
