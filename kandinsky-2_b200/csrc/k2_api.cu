@@ -323,9 +323,9 @@ int k2_conv_gemm(const K2ConvSrc* srcs, int nsrc, int NB, int H, int W, const vo
   const long long HWl = static_cast<long long>(H) * W;
   int fuse_stats = 0, row_groups = 0;
   if (gn_partial && out_mode == 0 && Cout % 8 == 0) {
-    if (splits == 1 && p.TN == 1 && BN >= 32 && Cout % 32 == 0) {
+    if (splits == 1 && p.TN == 1 && BN >= 64 && Cout % 64 == 0) {
       fuse_stats = 1;
-      row_groups = p.m_tiles * 4;
+      row_groups = p.m_tiles;  // one partial per M tile (the epilogue folds its four warps)
     } else if (splits > 1 && HWl % 16 == 0) {
       fuse_stats = 2;
       row_groups = static_cast<int>(p.M_total / 16);

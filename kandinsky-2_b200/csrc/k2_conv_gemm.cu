@@ -123,82 +123,116 @@ __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t 
             __syncwarp();
           }
           __half* outb = reinterpret_cast<__half*>(p.out);
-#pragma unroll 1
-          for (int jp = 0; jp < BN / 64; ++jp) {
+          constexpr int NP = BN / 64;
+          float4 st[NP];   // fused GroupNorm statistics of this warp's 32 rows: (sum, sumsq) of columns 2l, 2l+1 per pair
+          uint4 rpre[8];   // residual of the NEXT 64-column pair, in flight while the current one is processed
+          auto load_res = [&](int jp) {
+            const int c0 = n_idx * BN + jp * 64;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              rpre[i] = make_uint4(0u, 0u, 0u, 0u);
+              if (pix[i] >= 0 && c0 < p.Cout)
+                rpre[i] = *reinterpret_cast<const uint4*>(p.residual + static_cast<long long>(pix[i]) * p.ldr + c0 + piece * 8);
+            }
+          };
+          if (p.residual) load_res(0);
+#pragma unroll
+          for (int jp = 0; jp < NP; ++jp) {
             const int col0 = n_idx * BN + jp * 64;
-            if (col0 >= p.Cout) break;
-            if (p.residual) {  // coalesced: 8 lanes x 16 B per row, 4 rows per instruction -> staged by row
+            st[jp] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (col0 < p.Cout) {
+              if (p.residual) {  // coalesced: 8 lanes x 16 B per row, 4 rows per instruction -> staged by row
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  const int rr = i * 4 + sub;
+                  sts_v4(stage + rr * 128 + ((piece ^ (rr & 7)) << 4), rpre[i].x, rpre[i].y, rpre[i].z, rpre[i].w);
+                }
+                __syncwarp();
+              }
+              uint32_t r[64];
+              {
+                uint32_t(&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
+                uint32_t(&r1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[32]);
+                tmem_ld_32x32b_x32(taddr0 + jp * 64, r0);
+                tmem_ld_32x32b_x32(taddr0 + jp * 64 + 32, r1);
+                if (p.residual && jp + 1 < NP) load_res(jp + 1);
+                tmem_ld_wait();
+              }
+#pragma unroll
+              for (int v = 0; v < 8; ++v) {  // 8 columns = one 16-byte piece of the staged row
+                float f[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(r[v * 8 + e]);
+                if (p.bias) {
+                  const float4 b0 = *reinterpret_cast<const float4*>(bsm + jp * 64 + v * 8);
+                  const float4 b1 = *reinterpret_cast<const float4*>(bsm + jp * 64 + v * 8 + 4);
+                  f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                  f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+                }
+                const uint32_t slot = own + ((v ^ (lane & 7)) << 4);
+                if (p.residual) {
+                  const uint4 rv = lds_v4(slot);
+                  const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 t = __half22float2(rh[e]);
+                    f[2 * e] += t.x;
+                    f[2 * e + 1] += t.y;
+                  }
+                }
+                uint32_t o[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const __half2 hh = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
+                  o[e] = valid ? *reinterpret_cast<const uint32_t*>(&hh) : 0u;  // rows outside the image count as zeros
+                }
+                sts_v4(slot, o[0], o[1], o[2], o[3]);
+              }
+              __syncwarp();
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const int rr = i * 4 + sub;
-                uint4 v4 = make_uint4(0u, 0u, 0u, 0u);
+                const uint4 v4 = lds_v4(stage + rr * 128 + ((piece ^ (rr & 7)) << 4));
                 if (pix[i] >= 0)
-                  v4 = *reinterpret_cast<const uint4*>(p.residual + static_cast<long long>(pix[i]) * p.ldr + col0 + piece * 8);
-                sts_v4(stage + rr * 128 + ((piece ^ (rr & 7)) << 4), v4.x, v4.y, v4.z, v4.w);
+                  *reinterpret_cast<uint4*>(outb + static_cast<long long>(pix[i]) * p.ldo + col0 + piece * 8) = v4;
+              }
+              if (p.gn_part) {
+                // statistics of the fp16-ROUNDED stored values: lane l sums columns 2l, 2l+1 over the warp's 32 rows
+                float s1a = 0.f, s2a = 0.f, s1b = 0.f, s2b = 0.f;
+#pragma unroll
+                for (int rr = 0; rr < 32; ++rr) {
+                  const uint32_t w = lds_u32(stage + rr * 128 + (((lane >> 2) ^ (rr & 7)) << 4) + ((lane & 3) << 2));
+                  const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w));
+                  s1a += t.x;
+                  s2a = fmaf(t.x, t.x, s2a);
+                  s1b += t.y;
+                  s2b = fmaf(t.y, t.y, s2b);
+                }
+                st[jp] = make_float4(s1a, s2a, s1b, s2b);
               }
               __syncwarp();
             }
-            uint32_t r[64];
-            {
-              uint32_t(&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
-              uint32_t(&r1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[32]);
-              tmem_ld_32x32b_x32(taddr0 + jp * 64, r0);
-              tmem_ld_32x32b_x32(taddr0 + jp * 64 + 32, r1);
-              tmem_ld_wait();
-            }
+          }
+          if (p.gn_part) {
+            // one partial per (M tile, column): the four warps' sums are folded in a fixed order through the (now idle)
+            // staging buffers, so k2_gn_finalize reads a quarter of what per-warp partials would cost
+            float4* mine = reinterpret_cast<float4*>(stat_smem + ew * EPI_STAGE_FLOATS);
 #pragma unroll
-            for (int v = 0; v < 8; ++v) {  // 8 columns = one 16-byte piece of the staged row
-              float f[8];
+            for (int jp = 0; jp < NP; ++jp) mine[jp * 32 + lane] = st[jp];
+            named_bar_sync(1, 128);
+            if (ew < NP) {
+              const int col0 = n_idx * BN + ew * 64;
+              if (col0 < p.Cout) {
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-              for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(r[v * 8 + e]);
-              if (p.bias) {
-                const float4 b0 = *reinterpret_cast<const float4*>(bsm + jp * 64 + v * 8);
-                const float4 b1 = *reinterpret_cast<const float4*>(bsm + jp * 64 + v * 8 + 4);
-                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-              }
-              const uint32_t slot = own + ((v ^ (lane & 7)) << 4);
-              if (p.residual) {
-                const uint4 rv = lds_v4(slot);
-                const __half2* rh = reinterpret_cast<const __half2*>(&rv);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 t = __half22float2(rh[e]);
-                  f[2 * e] += t.x;
-                  f[2 * e + 1] += t.y;
+                for (int w = 0; w < 4; ++w) {
+                  const float4 t = reinterpret_cast<const float4*>(stat_smem + w * EPI_STAGE_FLOATS)[ew * 32 + lane];
+                  acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
                 }
+                *reinterpret_cast<float4*>(p.gn_part + static_cast<long long>(m_idx) * p.Cout + col0 + 2 * lane) = acc;
               }
-              uint32_t o[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const __half2 hh = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
-                o[e] = valid ? *reinterpret_cast<const uint32_t*>(&hh) : 0u;  // rows outside the image count as zeros
-              }
-              sts_v4(slot, o[0], o[1], o[2], o[3]);
             }
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int rr = i * 4 + sub;
-              const uint4 v4 = lds_v4(stage + rr * 128 + ((piece ^ (rr & 7)) << 4));
-              if (pix[i] >= 0) *reinterpret_cast<uint4*>(outb + static_cast<long long>(pix[i]) * p.ldo + col0 + piece * 8) = v4;
-            }
-            if (p.gn_part) {
-              // fused GroupNorm statistics of the fp16-ROUNDED stored values: lane l sums columns 2l, 2l+1 over the 32 rows
-              float s1a = 0.f, s2a = 0.f, s1b = 0.f, s2b = 0.f;
-#pragma unroll
-              for (int rr = 0; rr < 32; ++rr) {
-                const uint32_t w = lds_u32(stage + rr * 128 + (((lane >> 2) ^ (rr & 7)) << 4) + ((lane & 3) << 2));
-                const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w));
-                s1a += t.x;
-                s2a = fmaf(t.x, t.x, s2a);
-                s1b += t.y;
-                s2b = fmaf(t.y, t.y, s2b);
-              }
-              *reinterpret_cast<float4*>(p.gn_part + (static_cast<long long>(m_idx) * 4 + ew) * p.Cout + col0 + 2 * lane) =
-                  make_float4(s1a, s2a, s1b, s2b);
-            }
-            __syncwarp();
+            named_bar_sync(1, 128);
           }
           return;
         }
@@ -255,16 +289,6 @@ __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t 
 #pragma unroll
                 for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(f[2 * e], f[2 * e + 1]);
                 *reinterpret_cast<uint4*>(orow + v * 8) = ov;
-                if constexpr (CH == 32) {
-                  if (p.gn_part) {  // keep the fp16-ROUNDED values: GroupNorm statistics are those of the stored tensor
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                      const float2 t = __half22float2(oh[e]);
-                      r[v * 8 + 2 * e] = __float_as_uint(t.x);
-                      r[v * 8 + 2 * e + 1] = __float_as_uint(t.y);
-                    }
-                  }
-                }
               }
             } else {
 #pragma unroll
@@ -288,26 +312,6 @@ __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t 
                 o[((static_cast<long long>(n) * p.Cout + (col0 + e)) * p.H + y) * p.W + x] = f;
               }
             }
-          }
-        }
-        if constexpr (CH == 32) {
-          // Fused GroupNorm statistics (replaces a separate read of the output tensor): per-column (sum, sum of
-          // squares) of this warp's 32 rows via a padded shared-memory transpose, written as one coalesced float2 row
-          // partial[(m_tile*4 + warp)][column]; k2_gn_finalize folds them per (image, group) in a fixed order.
-          if (p.gn_part && p.out_mode == 0 && col0 + CH <= p.Cout) {
-            float* sm = stat_smem + ew * (32 * 33);
-#pragma unroll
-            for (int e = 0; e < 32; ++e) sm[lane * 33 + e] = valid ? __uint_as_float(r[e]) : 0.f;
-            __syncwarp();
-            float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-            for (int q = 0; q < 32; ++q) {
-              const float t = sm[q * 33 + lane];
-              s1 += t;
-              s2 = fmaf(t, t, s2);
-            }
-            __syncwarp();
-            p.gn_part[(static_cast<long long>(m_idx) * 4 + ew) * p.Cout + col0 + lane] = make_float2(s1, s2);
           }
         }
       }
