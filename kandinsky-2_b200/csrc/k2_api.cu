@@ -252,52 +252,67 @@ int k2_conv_gemm(const K2ConvSrc* srcs, int nsrc, int NB, int H, int W, const vo
   K2_REQUIRE(kchunks * 64 == Ktot, "conv_gemm: Ktot does not match the sources (taps * ceil(C/64)*64 summed)");
   p.num_k_chunks = kchunks;
 
-  // Tile shape and split-K factor from a cycle model of one SM: a K chunk costs max(MMA time, smem traffic time);
-  // the launch costs (waves of tiles) x (chunks per tile) x chunk cost + per-tile epilogue (+ the split-K second pass).
-  // Tile shape, CTA-pair mode and split-K factor.  Fitted to the B200 sweep in profiles/conv_sweep_r1.txt: the kernel
-  // is bound by L2->SM operand bandwidth (~64 B/clk/SM), so the CTA-pair kernel (half of the weight tile per CTA) with
-  // the widest N tile wins everywhere it applies; N = 192 only where it divides Cout and 256 would waste a third of a
-  // tile; K is split 2-3 ways when the tile count would leave most SM pairs idle (levels 2-3 of the U).
+  // Tile width N, CTA-pair mode and split-K factor from a cycle model fitted to the B200 sweeps
+  // (profiles/conv_sweep_r1.txt, conv_sweep_small_r1.txt, conv_small_k.py):
+  //   one K chunk of a work unit costs 2*BN + 60 cycles in the CTA-pair kernel (MMA time of the 256 x BN x 64 product +
+  //   pipeline hand-over), a unit adds ~2000 cycles of exposed prologue / epilogue, the launch takes
+  //   ceil(units / slots) waves of those, and a split-K launch pays the second pass (fixed ~4000 cycles + its traffic at
+  //   ~2200 B/cycle).  The CTA-pair kernel wins wherever Cout > 64 (half of the weight tile per CTA); among its N tiles
+  //   the model picks 192 / 128 where they divide Cout better or give a fuller last wave, and splits K only where the
+  //   tile count would leave most SM pairs idle (level 3 of the U).
   int BN = g_force_bn;
   int splits = 1;
   int two_cta = (Cout > 64 && g_force_2cta != 1) ? 1 : 0;
   if (g_force_2cta == 2 && Cout > 64) two_cta = 1;
+  if (halo_pitch) two_cta = 1;
+  const long long M_total = static_cast<long long>(NB) * H * W;
+  const bool can_split = !halo_pitch && workspace && out_mode == 0 && Cout % 8 == 0;
+  auto split_ok = [&](int bn, int sp) {
+    (void)bn;
+    if (sp == 1) return true;
+    const int kps = (kchunks + sp - 1) / sp;
+    return can_split && kps >= 8 && (sp - 1) * kps < kchunks &&
+           static_cast<long long>(sp) * M_total * Cout * 4 <= workspace_bytes;
+  };
+  auto model = [&](int bn, int sp, bool pair) {
+    const long long nt = (Cout + bn - 1) / bn;
+    const long long units = static_cast<long long>(pair ? (p.m_tiles + 1) / 2 : p.m_tiles) * nt * sp;
+    const long long slots = pair ? num_sms() / 2 : num_sms();
+    const long long waves = (units + slots - 1) / slots;
+    const long long kps = (kchunks + sp - 1) / sp;
+    const long long chunk = pair ? 2 * bn + 60 : (bn >= 256 ? 768 : 2 * bn + 160);  // 1-CTA: operand-bandwidth bound
+    long long cost = waves * (kps * chunk + 2000);
+    if (sp > 1) cost += 4000 + (static_cast<long long>(sp) + 1) * M_total * Cout * 4 / 2200;
+    return cost;
+  };
   if (BN == 0) {
     if (Cout <= 16) BN = 16;
     else if (Cout <= 64) BN = 64;
     else if (Cout <= 128) BN = 128;
-    else if (Cout <= 384 && Cout % 192 == 0) BN = 192;
-    else BN = 256;
+    else BN = 0;  // chosen below together with the split factor
   }
-  if (two_cta && BN < 128) two_cta = 0;
-  if (halo_pitch) two_cta = 1;
-  if (!halo_pitch) {
-    const long long M_total = static_cast<long long>(NB) * H * W;
-    const int nt = (Cout + BN - 1) / BN;
-    const long long units = static_cast<long long>(two_cta ? (p.m_tiles + 1) / 2 : p.m_tiles) * nt;
-    const int slots = two_cta ? num_sms() / 2 : num_sms();
-    // split-K factor: waves of work units x (K chunks per unit + ~12 chunk-times of per-unit ramp / epilogue) + the
-    // second pass; this ranking reproduces the measured order on every small-M shape of profiles/conv_sweep_small_r1.txt
-    int want = 1;
-    {
-      long long best = -1;
+  if (two_cta && BN != 0 && BN < 128) two_cta = 0;
+  {
+    const int cand[3] = {256, 192, 128};
+    long long best = -1;
+    int best_bn = BN ? BN : 256, best_sp = 1;
+    for (int ci = 0; ci < 3; ++ci) {
+      const int bn = BN ? BN : cand[ci];
+      if (BN && ci > 0) break;
       for (int sp = 1; sp <= 8; ++sp) {
-        const int kps = (kchunks + sp - 1) / sp;
-        if (sp > 1 && (kps < 8 || (sp - 1) * kps >= kchunks)) continue;
-        const long long waves = (units * sp + slots - 1) / slots;
-        const long long cost = waves * (kps + 12) + 2 * (sp - 1);
-        if (best < 0 || cost < best) {
-          best = cost;
-          want = sp;
+        if (g_force_split > 0 && sp != g_force_split) continue;
+        if (halo_pitch && sp > 1) continue;
+        if (!split_ok(bn, sp)) continue;
+        const long long c = model(bn, sp, two_cta != 0);
+        if (best < 0 || c < best) {  // ties keep the wider tile / the smaller split (visited first)
+          best = c;
+          best_bn = bn;
+          best_sp = sp;
         }
       }
     }
-    if (g_force_split > 0) want = g_force_split;
-    const bool can = workspace && out_mode == 0 && Cout % 8 == 0;
-    if (want > 1 && can) {
-      const int kps = (kchunks + want - 1) / want;
-      if ((want - 1) * kps < kchunks && static_cast<long long>(want) * M_total * Cout * 4 <= workspace_bytes) splits = want;
-    }
+    BN = best_bn;
+    splits = best_sp;
   }
   p.two_cta = two_cta;
   p.splits = splits;
@@ -323,15 +338,18 @@ int k2_conv_gemm(const K2ConvSrc* srcs, int nsrc, int NB, int H, int W, const vo
   const long long HWl = static_cast<long long>(H) * W;
   int fuse_stats = 0, row_groups = 0;
   if (gn_partial && out_mode == 0 && Cout % 8 == 0) {
-    if (splits == 1 && p.TN == 1 && BN >= 64 && Cout % 64 == 0) {
+    if (splits == 1 && BN >= 64 && Cout % 64 == 0 && (p.TN == 1 || p.TH * p.TW == 16)) {
       fuse_stats = 1;
-      row_groups = p.m_tiles;  // one partial per M tile (the epilogue folds its four warps)
+      // TN == 1: one partial per M tile (the epilogue folds its four warps); 16-pixel multi-image tiles: one partial per
+      // (image, spatial tile) -- every half warp of the epilogue holds exactly one image's 16 pixels
+      row_groups = (p.TN == 1) ? p.m_tiles : NB * p.tiles_h * p.tiles_w;
     } else if (splits > 1 && HWl % 16 == 0) {
       fuse_stats = 2;
       row_groups = static_cast<int>(p.M_total / 16);
     }
   }
   p.gn_part = (fuse_stats == 1) ? reinterpret_cast<float2*>(gn_partial) : nullptr;
+  p.gn_mode = (fuse_stats == 1) ? (p.TN == 1 ? 1 : 2) : 0;
   if (info) {
     info[0] = BN; info[1] = two_cta; info[2] = splits; info[3] = p.m_tiles; info[4] = p.TN; info[5] = fuse_stats;
     info[6] = row_groups;

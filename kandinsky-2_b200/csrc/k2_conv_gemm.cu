@@ -197,23 +197,35 @@ __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t 
                   *reinterpret_cast<uint4*>(outb + static_cast<long long>(pix[i]) * p.ldo + col0 + piece * 8) = v4;
               }
               if (p.gn_part) {
-                // statistics of the fp16-ROUNDED stored values: lane l sums columns 2l, 2l+1 over the warp's 32 rows
-                float s1a = 0.f, s2a = 0.f, s1b = 0.f, s2b = 0.f;
+                // statistics of the fp16-ROUNDED stored values: lane l sums columns 2l, 2l+1 over the warp's rows
+                float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f), h1 = make_float4(0.f, 0.f, 0.f, 0.f);  // rows 0-15 / 16-31
 #pragma unroll
                 for (int rr = 0; rr < 32; ++rr) {
                   const uint32_t w = lds_u32(stage + rr * 128 + (((lane >> 2) ^ (rr & 7)) << 4) + ((lane & 3) << 2));
                   const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w));
-                  s1a += t.x;
-                  s2a = fmaf(t.x, t.x, s2a);
-                  s1b += t.y;
-                  s2b = fmaf(t.y, t.y, s2b);
+                  float4& hacc = (rr < 16) ? h0 : h1;
+                  hacc.x += t.x;
+                  hacc.y = fmaf(t.x, t.x, hacc.y);
+                  hacc.z += t.y;
+                  hacc.w = fmaf(t.y, t.y, hacc.w);
                 }
-                st[jp] = make_float4(s1a, s2a, s1b, s2b);
+                if (p.gn_mode == 2) {
+                  // 16-pixel x 8-image tiles: half warp h of warp ew holds image n0 + 2*ew + h of spatial tile sp
+                  const int per = p.tiles_h * p.tiles_w;
+                  const int sp = m_idx % per;
+                  const int img = n0 + 2 * ew;
+                  if (2 * ew < p.TN && img < p.NB)
+                    *reinterpret_cast<float4*>(p.gn_part + (static_cast<long long>(img) * per + sp) * p.Cout + col0 + 2 * lane) = h0;
+                  if (2 * ew + 1 < p.TN && img + 1 < p.NB)
+                    *reinterpret_cast<float4*>(p.gn_part + (static_cast<long long>(img + 1) * per + sp) * p.Cout + col0 + 2 * lane) = h1;
+                } else {
+                  st[jp] = make_float4(h0.x + h1.x, h0.y + h1.y, h0.z + h1.z, h0.w + h1.w);
+                }
               }
               __syncwarp();
             }
           }
-          if (p.gn_part) {
+          if (p.gn_part && p.gn_mode == 1) {
             // one partial per (M tile, column): the four warps' sums are folded in a fixed order through the (now idle)
             // staging buffers, so k2_gn_finalize reads a quarter of what per-warp partials would cost
             float4* mine = reinterpret_cast<float4*>(stat_smem + ew * EPI_STAGE_FLOATS);

@@ -73,7 +73,8 @@ struct ConvGemmParams {
   float* ws;           // [splits][M_total][Cout] fp32 partial sums (out_mode 2)
   long long M_total;
   int two_cta;         // 1: CTA-pair kernel (cta_group::2, 256-row tiles)
-  float2* gn_part;     // [m_tiles*4][Cout] per-32-row (sum, sumsq) of the fp16-rounded output, or null
+  float2* gn_part;     // fused GroupNorm partials (sum, sumsq) of the fp16-rounded output, or null:
+  int gn_mode;         //   1: [m_tiles][Cout], one per M tile (TN == 1); 2: [image][spatial tile][Cout] for 16-pixel x 8-image tiles
   int halo_pitch;      // 0: per-tap boxes; 10 / 16: halo kernel, pixels per halo row in shared memory
   int halo_bo;         // halo kernel: 1 = put (start >> 7) & 7 into the descriptor's base-offset field
 };

@@ -124,7 +124,7 @@ def test_splitk_small_m(split):
 @pytest.mark.parametrize("two_cta", [1, 2])
 @pytest.mark.parametrize("NB,H,W,Cin,Cout,C1", [(2, 24, 24, 128, 256, 0), (3, 16, 12, 64, 384, 128), (1, 96, 96, 64, 192, 0)])
 def test_conv_fused_groupnorm_partials(two_cta, NB, H, W, Cin, Cout, C1):
-    """The conv epilogue's per-32-row (sum, sumsq) partials + k2_gn_finalize == a statistics pass over the stored output
+    """The conv epilogue's per-tile (sum, sumsq) partials + k2_gn_finalize == a statistics pass over the stored output
     (also over the concat with a second producer's output)."""
     from kandinsky2 import ops
     g = torch.Generator(device="cuda").manual_seed(8)
@@ -163,10 +163,45 @@ def test_splitk_fused_groupnorm_partials():
     b = torch.randn(Cout, device="cuda", generator=g)
     part = torch.zeros(ops.gn_part_floats(NB, H, W, Cout), device="cuda")
     info = [0] * 7
-    y = ops.conv_gemm([(x, 9)], ops.pack_conv_weight(w), Cout, bias=b, gn_part=part, info=info)
-    assert info[2] > 1 and info[5] == 2 and info[6] == NB * H * W // 16, info
+    ops.set_tuning(1, 2)  # force a 2-way K split (the heuristic keeps this shape unsplit)
+    try:
+        y = ops.conv_gemm([(x, 9)], ops.pack_conv_weight(w), Cout, bias=b, gn_part=part, info=info)
+    finally:
+        ops.set_tuning(1, 0)
+    assert info[2] == 2 and info[5] == 2 and info[6] == NB * H * W // 16, info
     st = torch.empty(NB, 32, 2, device="cuda")
     ops.gn_finalize(part, Cout, None, 0, NB, info[6] // NB, H * W, st)
     ref = ops.gn_stats(y, None)
     torch.cuda.synchronize()
     assert torch.allclose(st[..., 0], ref[..., 0], atol=2e-5) and torch.allclose(st[..., 1], ref[..., 1], rtol=2e-5)
+
+
+@pytest.mark.parametrize("NB", [8, 5])
+def test_multi_image_tile_fused_groupnorm_partials(NB):
+    """12x12 latents use (4 x 4 pixels x 8 images) tiles: the epilogue emits one partial per (image, spatial tile) from each
+    half warp; also with a ragged last image group (NB = 5)."""
+    from kandinsky2 import ops
+    g = torch.Generator(device="cuda").manual_seed(10)
+    H, W, Cin, Cout = 12, 12, 256, 512
+    x = torch.randn(NB, H, W, Cin, device="cuda", generator=g).half()
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) / (3 * Cin ** 0.5)
+    b = torch.randn(Cout, device="cuda", generator=g)
+    res = torch.randn(NB, H, W, Cout, device="cuda", generator=g).half()
+    part = torch.zeros(ops.gn_part_floats(NB, H, W, Cout), device="cuda")
+    info = [0] * 7
+    ops.set_tuning(1, 1)
+    try:
+        y = ops.conv_gemm([(x, 9)], ops.pack_conv_weight(w), Cout, bias=b, residual=res, gn_part=part, info=info)
+    finally:
+        ops.set_tuning(1, 0)
+    ref_y = F.conv2d(x.float().permute(0, 3, 1, 2), w.half().float(), b, padding=1).permute(0, 2, 3, 1) + res.float()
+    assert ((y.float() - ref_y).norm() / ref_y.norm()).item() < 1e-3
+    if NB == 8:
+        assert info[4] == 8 and info[5] == 1, info  # (4 x 4 x 8) tiles, statistics fused
+    if info[5] == 1:
+        assert info[6] % NB == 0, info
+        st = torch.empty(NB, 32, 2, device="cuda")
+        ops.gn_finalize(part, Cout, None, 0, NB, info[6] // NB, H * W, st)
+        ref = ops.gn_stats(y, None)
+        torch.cuda.synchronize()
+        assert torch.allclose(st[..., 0], ref[..., 0], atol=2e-5) and torch.allclose(st[..., 1], ref[..., 1], rtol=2e-5)
