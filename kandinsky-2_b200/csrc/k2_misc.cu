@@ -67,15 +67,46 @@ __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x
 #pragma unroll
       for (int i = 0; i < LIN_MT; ++i) acc[cb][i] = 0.f;
     const int K8 = vec_ok ? (K & ~7) : 0;
+    // weights are streamed once from HBM: the raw 16-byte pieces of the NEXT k step are requested before the FMAs of the
+    // current one (one warp would otherwise expose a full memory round trip per step)
+    constexpr int RW = W_HALF ? 1 : 2;
+    uint4 raw[LIN_CB][RW], nxt[LIN_CB][RW];
+    auto fetch = [&](int k, uint4 (&dst)[LIN_CB][RW]) {
+#pragma unroll
+      for (int cb = 0; cb < LIN_CB; ++cb) {
+#pragma unroll
+        for (int q = 0; q < RW; ++q) dst[cb][q] = make_uint4(0u, 0u, 0u, 0u);
+        if (n0 + cb < N) {
+          const long long off = static_cast<long long>(n0 + cb) * K + k;
+          if (W_HALF) {
+            dst[cb][0] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(Wv) + off));
+          } else {
+            const uint4* wp = reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(Wv) + off);
+            dst[cb][0] = __ldg(wp);
+            dst[cb][RW - 1] = __ldg(wp + (RW - 1));
+          }
+        }
+      }
+    };
+    if (lane * 8 < K8) fetch(lane * 8, raw);
+#pragma unroll 2
     for (int k = lane * 8; k < K8; k += 256) {
+      if (k + 256 < K8) fetch(k + 256, nxt);
       float w[LIN_CB][8];
 #pragma unroll
       for (int cb = 0; cb < LIN_CB; ++cb) {
-        if (n0 + cb < N) {
-          load_w8<W_HALF>(Wv, static_cast<long long>(n0 + cb) * K + k, w[cb]);
-        } else {
+        if (W_HALF) {
+          const __half2* h2 = reinterpret_cast<const __half2*>(&raw[cb][0]);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) w[cb][e] = 0.f;
+          for (int e = 0; e < 4; ++e) {
+            const float2 t = __half22float2(h2[e]);
+            w[cb][2 * e] = t.x;
+            w[cb][2 * e + 1] = t.y;
+          }
+        } else {
+          const float* f = reinterpret_cast<const float*>(&raw[cb][0]);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) w[cb][e] = f[e];
         }
       }
 #pragma unroll
@@ -88,6 +119,10 @@ __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x
 #pragma unroll
           for (int e = 0; e < 8; ++e) acc[cb][i] = fmaf(xv[e], w[cb][e], acc[cb][i]);
       }
+#pragma unroll
+      for (int cb = 0; cb < LIN_CB; ++cb)
+#pragma unroll
+        for (int q = 0; q < RW; ++q) raw[cb][q] = nxt[cb][q];
     }
     for (int k = K8 + lane; k < K; k += 32) {
 #pragma unroll
