@@ -55,13 +55,16 @@ int k2_set_tuning(int key, int value);
  * out_mode 0: fp16 rows [M, ldo]; out_mode 1: fp32 NCHW [NB, Cout, H, W] (output heads).
  * ldw is the row stride of Wp in elements (0 = Ktot); a strided Wp lets an ACTIVATION matrix be the B operand
  * (MoVQ attention: scores = q k^T with k rows as "weights").
- * workspace (may be NULL): caller-owned scratch for split-K.  When the tile count would leave SMs idle (small M, huge K:
- * the bottom of the U) K is split over several CTAs that write fp32 partial tiles [split][M][Cout] there, and a second
- * launch sums them in a fixed order (+bias, +residual) -- deterministic, no atomics.
- * gn_partial (may be NULL): fp32 [m_tiles*4][Cout][2]; when given and the launch qualifies (no split-K, a tile lies
- * inside one image, fp16 output, Cout % 32 == 0) the epilogue also emits per-32-row (sum, sum of squares) of the rounded
- * output, which k2_gn_finalize turns into GroupNorm statistics -- the consumer's statistics pass disappears.
- * With split-K the second pass emits them instead (16-row groups).  gn_partial must hold max(M tiles*4, M/16)*Cout*2 floats.
+ * workspace (may be NULL): caller-owned scratch for split-K.  Where a cycle model of the launch (waves of work units x
+ * K chunks per unit, plus the second pass) says so -- small M with a huge K -- K is split over several CTAs that write
+ * fp32 partial tiles [split][M][Cout] there, and a second launch sums them in a fixed order (+bias, +residual) --
+ * deterministic, no atomics.
+ * gn_partial (may be NULL): fp32 [row groups][Cout][2]; when given and the launch qualifies (fp16 output, Cout % 64 == 0,
+ * N tile >= 64) the launch also emits (sum, sum of squares) partials of the ROUNDED output, image-major, which
+ * k2_gn_finalize turns into GroupNorm statistics -- the consumer's statistics pass disappears.  Row groups: one per M tile
+ * when a tile lies inside one image; one per (image, spatial tile) for the (16 pixel x 8 image) tiles of tiny images; 16-row
+ * groups from the second pass of a split-K launch.  gn_partial must hold max(M tiles*4, M/16)*Cout*2 floats
+ * (k2_gn_scratch_floats); info[5] / info[6] tell what was written.
  * info (HOST pointer, may be NULL): int[7] = {N tile, CTA-pair mode, split-K factor, M tiles, images per tile,
  * gn_partial written (0 no / 1 epilogue / 2 split-K pass), row groups written in total}.
  * A plain GEMM [M,K]x[K,N] is the call with NB=1, H=1, W=M, one source with taps=1.

@@ -163,7 +163,7 @@ def gn_stats(x0, x1=None, groups=32, eps=1e-5, stats=None):
 
 
 def gn_part_floats(NB, H, W, cout):
-    """Upper bound of the fp32 count of a conv's fused-statistics partial buffer ([m_tiles*4][cout][2])."""
+    """Upper bound of the fp32 count of a conv's fused-statistics partial buffer ([row groups][cout][2], k2b200.h)."""
     tiles = NB * ((H * W + 63) // 64 + 2 * H)  # generous: boxes are >= 64 pixels except at ragged edges
     return max(tiles * 4, (NB * H * W + 15) // 16) * cout * 2
 
