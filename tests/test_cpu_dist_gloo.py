@@ -25,7 +25,9 @@ def _worker(rank, world_size, port, q):
     parallel.broadcast_conditioning(cond, src=0)
     lo, hi = parallel.shard_range(B, rank, world_size)
     noise = parallel.sample_noise(range(lo, hi), (4, 2, 2), base_seed=99)
-    q.put((rank, lo, hi, cond["image_emb"].clone(), cond["pooled"].clone(), noise))
+    # numpy arrays travel by value (torch tensors travel as file descriptors served by THIS process, which may have
+    # exited by the time the parent unpickles them)
+    q.put((rank, lo, hi, cond["image_emb"].numpy().copy(), cond["pooled"].numpy().copy(), noise.numpy().copy()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -49,6 +51,7 @@ def test_shard_and_broadcast_world2():
     ref_noise = parallel.sample_noise(range(5), (4, 2, 2), base_seed=99)
     covered = []
     for rank, lo, hi, e, p, noise in got:
+        e, p, noise = torch.from_numpy(e), torch.from_numpy(p), torch.from_numpy(noise)
         assert torch.equal(e, emb) and torch.equal(p, pooled)          # one broadcast delivered everything
         assert torch.equal(noise, ref_noise[lo:hi])                    # per-global-sample seeds: world-size independent
         covered += list(range(lo, hi))
