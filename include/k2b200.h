@@ -81,6 +81,13 @@ int k2_conv_gemm(const K2ConvSrc* srcs, int nsrc, int NB, int H, int W, const vo
                  int out_mode, void* workspace, long long workspace_bytes, float* gn_partial, int* info,
                  k2_stream_t stream);
 
+/* The decisions k2_conv_gemm takes for a geometry -- M tile box, N tile, CTA-pair mode, split-K factor, how the GroupNorm
+ * partials come out -- without touching a pointer or the GPU (host arithmetic only; for tests, tooling and the caller's
+ * scratch sizing).  taps: 9 if any source is a 3x3, else 1; Ktot as for k2_conv_gemm; workspace_bytes 0 = no workspace;
+ * info = int[7] with the meaning given above. */
+int k2_conv_plan(int NB, int H, int W, int taps, int Ktot, int Cout, int out_mode, long long workspace_bytes,
+                 int want_gn_partial, int* info);
+
 /* ---------------------------------------------------------------------------------------------
  * GroupNorm (32 groups in the UNet) statistics + fused apply.
  * Replaces GroupNorm32.forward (nn.py:31-37), the FiLM  norm(h)*(1+scale)+shift  and SiLU of

@@ -138,6 +138,126 @@ static void choose_tile(int NB, int H, int W, int& TN, int& TH, int& TW) {
   TH = bh[k];
 }
 
+
+// Everything k2_conv_gemm decides before it touches a pointer: the M tile box, N tile, CTA-pair mode, split-K factor and
+// how the fused GroupNorm partials come out.  Pure host arithmetic (k2_conv_plan exposes it for tests and tooling).
+struct ConvPlan {
+  int TN, TH, TW, tiles_w, tiles_h, tiles_n, m_tiles;
+  int halo_pitch, halo_bo;
+  int BN, two_cta, splits;
+  int fuse_stats, row_groups;
+};
+
+static void plan_conv(int NB, int H, int W, bool any9, int kchunks, int Cout, int out_mode, bool has_workspace,
+                      long long workspace_bytes, bool want_gn, ConvPlan& pl) {
+  // halo kernel (one (8+2)x(16+2) activation box per K chunk instead of nine shifted boxes): 3x3 convolutions whose
+  // image tiles exactly into 8 x 16 pixel boxes -- measured slower than nine shifted boxes, tuning knob 3, off by default
+  pl.halo_pitch = 0;
+  pl.halo_bo = 0;
+  if (g_halo_mode > 0 && any9 && W % 8 == 0 && H % 16 == 0 && out_mode == 0 && Cout > 64 && g_force_2cta != 1) {
+    pl.halo_pitch = (g_halo_mode <= 2) ? 10 : 16;
+    pl.halo_bo = (g_halo_mode == 2 || g_halo_mode == 4) ? 1 : 0;
+  }
+  if (pl.halo_pitch) {
+    pl.TN = 1;
+    pl.TH = 16;
+    pl.TW = 8;
+  } else {
+    choose_tile(NB, H, W, pl.TN, pl.TH, pl.TW);
+  }
+  pl.tiles_w = (W + pl.TW - 1) / pl.TW;
+  pl.tiles_h = (H + pl.TH - 1) / pl.TH;
+  pl.tiles_n = (NB + pl.TN - 1) / pl.TN;
+  pl.m_tiles = pl.tiles_w * pl.tiles_h * pl.tiles_n;
+
+  // Tile width N, CTA-pair mode and split-K factor from a cycle model fitted to the B200 sweeps
+  // (profiles/conv_sweep_r1.txt, conv_sweep_small_r1.txt, conv_small_k_r1.txt):
+  //   one K chunk of a work unit costs 2*BN + 60 cycles in the CTA-pair kernel (MMA time of the 256 x BN x 64 product +
+  //   pipeline hand-over), a unit adds ~2000 cycles of exposed prologue / epilogue, the launch takes
+  //   ceil(units / slots) waves of those, and a split-K launch pays the second pass (fixed ~4000 cycles + its traffic at
+  //   ~2200 B/cycle).  The CTA-pair kernel wins wherever Cout > 64 (half of the weight tile per CTA); among its N tiles
+  //   the model picks 192 / 128 where they divide Cout better or give a fuller last wave, and splits K only where the
+  //   tile count would leave most SM pairs idle.
+  int BN = g_force_bn;
+  int splits = 1;
+  int two_cta = (Cout > 64 && g_force_2cta != 1) ? 1 : 0;
+  if (g_force_2cta == 2 && Cout > 64) two_cta = 1;
+  if (pl.halo_pitch) two_cta = 1;
+  const long long M_total = static_cast<long long>(NB) * H * W;
+  const bool can_split = !pl.halo_pitch && has_workspace && out_mode == 0 && Cout % 8 == 0;
+  auto split_ok = [&](int sp) {
+    if (sp == 1) return true;
+    const int kps = (kchunks + sp - 1) / sp;
+    return can_split && kps >= 8 && (sp - 1) * kps < kchunks &&
+           static_cast<long long>(sp) * M_total * Cout * 4 <= workspace_bytes;
+  };
+  auto model = [&](int bn, int sp, bool pair) {
+    const long long nt = (Cout + bn - 1) / bn;
+    const long long units = static_cast<long long>(pair ? (pl.m_tiles + 1) / 2 : pl.m_tiles) * nt * sp;
+    const long long slots = pair ? num_sms() / 2 : num_sms();
+    const long long waves = (units + slots - 1) / slots;
+    const long long kps = (kchunks + sp - 1) / sp;
+    const long long chunk = pair ? 2 * bn + 60 : (bn >= 256 ? 768 : 2 * bn + 160);  // 1-CTA: operand-bandwidth bound
+    long long cost = waves * (kps * chunk + 2000);
+    if (sp > 1) cost += 4000 + (static_cast<long long>(sp) + 1) * M_total * Cout * 4 / 2200;
+    return cost;
+  };
+  if (BN == 0) {
+    if (Cout <= 16) BN = 16;
+    else if (Cout <= 64) BN = 64;
+    else if (Cout <= 128) BN = 128;
+    else BN = 0;  // chosen below together with the split factor
+  }
+  if (two_cta && BN != 0 && BN < 128) two_cta = 0;
+  {
+    const int cand[3] = {256, 192, 128};
+    long long best = -1;
+    int best_bn = BN ? BN : 256, best_sp = 1;
+    for (int ci = 0; ci < 3; ++ci) {
+      const int bn = BN ? BN : cand[ci];
+      if (BN && ci > 0) break;
+      for (int sp = 1; sp <= 8; ++sp) {
+        if (g_force_split > 0 && sp != g_force_split) continue;
+        if (pl.halo_pitch && sp > 1) continue;
+        if (!split_ok(sp)) continue;
+        const long long c = model(bn, sp, two_cta != 0);
+        if (best < 0 || c < best) {  // ties keep the wider tile / the smaller split (visited first)
+          best = c;
+          best_bn = bn;
+          best_sp = sp;
+        }
+      }
+    }
+    BN = best_bn;
+    splits = best_sp;
+  }
+  pl.BN = BN;
+  pl.two_cta = two_cta;
+  pl.splits = splits;
+
+  // fused GroupNorm partial statistics: from the epilogue when a tile never straddles two images (one partial per M
+  // tile: the epilogue folds its four warps) or when it holds 16 pixels of each of 8 images (one partial per (image,
+  // spatial tile): every half warp of the epilogue holds exactly one image's pixels); split-K launches produce them in
+  // the second pass instead, as 16-row groups of the flat pixel order
+  pl.fuse_stats = 0;
+  pl.row_groups = 0;
+  if (want_gn && out_mode == 0 && Cout % 8 == 0) {
+    if (splits == 1 && BN >= 64 && Cout % 64 == 0 && (pl.TN == 1 || pl.TH * pl.TW == 16)) {
+      pl.fuse_stats = 1;
+      pl.row_groups = (pl.TN == 1) ? pl.m_tiles : NB * pl.tiles_h * pl.tiles_w;
+    } else if (splits > 1 && (static_cast<long long>(H) * W) % 16 == 0) {
+      pl.fuse_stats = 2;
+      pl.row_groups = static_cast<int>(M_total / 16);
+    }
+  }
+}
+
+static void plan_to_info(const ConvPlan& pl, int* info) {
+  if (!info) return;
+  info[0] = pl.BN; info[1] = pl.two_cta; info[2] = pl.splits; info[3] = pl.m_tiles; info[4] = pl.TN;
+  info[5] = pl.fuse_stats; info[6] = pl.row_groups;
+}
+
 }  // namespace k2
 
 using namespace k2;
@@ -205,115 +325,48 @@ int k2_conv_gemm(const K2ConvSrc* srcs, int nsrc, int NB, int H, int W, const vo
   p.NB = NB;
   p.H = H;
   p.W = W;
-  // halo kernel (one (8+2)x(16+2) activation box per K chunk instead of nine shifted boxes): 3x3 convolutions whose
-  // image tiles exactly into 8 x 16 pixel boxes -- levels 0-1 of the UNet, where ~70 % of the conv FLOPs are
   bool any9 = false;
-  for (int s = 0; s < nsrc; ++s) any9 = any9 || srcs[s].taps == 9;
-  int halo_pitch = 0, halo_bo = 0;
-  if (g_halo_mode > 0 && any9 && W % 8 == 0 && H % 16 == 0 && out_mode == 0 && Cout > 64 && g_force_2cta != 1) {
-    halo_pitch = (g_halo_mode <= 2) ? 10 : 16;
-    halo_bo = (g_halo_mode == 2 || g_halo_mode == 4) ? 1 : 0;
-  }
-  if (halo_pitch) {
-    p.TN = 1;
-    p.TH = 16;
-    p.TW = 8;
-  } else {
-    choose_tile(NB, H, W, p.TN, p.TH, p.TW);
-  }
-  p.halo_pitch = halo_pitch;
-  p.halo_bo = halo_bo;
-  p.tiles_w = (W + p.TW - 1) / p.TW;
-  p.tiles_h = (H + p.TH - 1) / p.TH;
-  p.tiles_n = (NB + p.TN - 1) / p.TN;
-  p.m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-  p.a_box_bytes = static_cast<uint32_t>(p.TN * p.TH * p.TW * 128);
-
   int kchunks = 0;
   for (int s = 0; s < nsrc; ++s) {
     const K2ConvSrc& src = srcs[s];
     K2_REQUIRE(src.taps == 9 || src.taps == 1, "conv_gemm: taps must be 9 or 1");
     K2_REQUIRE(src.C > 0 && src.C % 8 == 0 && src.ld % 8 == 0 && src.ld >= src.C, "conv_gemm: bad source C/ld");
     K2_REQUIRE((reinterpret_cast<uintptr_t>(src.ptr) & 15) == 0, "conv_gemm: source not 16B aligned");
+    any9 = any9 || src.taps == 9;
     p.seg_taps[s] = src.taps;
     p.seg_kchunks[s] = (src.C + 63) / 64;
     kchunks += src.taps * p.seg_kchunks[s];
+  }
+  K2_REQUIRE(kchunks * 64 == Ktot, "conv_gemm: Ktot does not match the sources (taps * ceil(C/64)*64 summed)");
+  p.num_k_chunks = kchunks;
+
+  ConvPlan pl;
+  plan_conv(NB, H, W, any9, kchunks, Cout, out_mode, workspace != nullptr, workspace_bytes, gn_partial != nullptr, pl);
+  plan_to_info(pl, info);
+  p.TN = pl.TN;
+  p.TH = pl.TH;
+  p.TW = pl.TW;
+  p.halo_pitch = pl.halo_pitch;
+  p.halo_bo = pl.halo_bo;
+  p.tiles_w = pl.tiles_w;
+  p.tiles_h = pl.tiles_h;
+  p.tiles_n = pl.tiles_n;
+  p.m_tiles = pl.m_tiles;
+  p.a_box_bytes = static_cast<uint32_t>(p.TN * p.TH * p.TW * 128);
+  for (int s = 0; s < nsrc; ++s) {
+    const K2ConvSrc& src = srcs[s];
     uint64_t dims[4] = {static_cast<uint64_t>(src.C), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
                         static_cast<uint64_t>(NB)};
     uint64_t str[3] = {static_cast<uint64_t>(src.ld) * 2, static_cast<uint64_t>(src.ld) * 2 * W,
                        static_cast<uint64_t>(src.ld) * 2 * W * H};
     uint32_t box[4] = {64, static_cast<uint32_t>(p.TW), static_cast<uint32_t>(p.TH), static_cast<uint32_t>(p.TN)};
-    if (halo_pitch && src.taps == 9) {
-      box[1] = static_cast<uint32_t>(halo_pitch);
+    if (pl.halo_pitch && src.taps == 9) {
+      box[1] = static_cast<uint32_t>(pl.halo_pitch);
       box[2] = 18;
     }
     if (encode_tmap_f16(&p.tmA[s], src.ptr, 4, dims, str, box)) return -1;
   }
-  K2_REQUIRE(kchunks * 64 == Ktot, "conv_gemm: Ktot does not match the sources (taps * ceil(C/64)*64 summed)");
-  p.num_k_chunks = kchunks;
-
-  // Tile width N, CTA-pair mode and split-K factor from a cycle model fitted to the B200 sweeps
-  // (profiles/conv_sweep_r1.txt, conv_sweep_small_r1.txt, conv_small_k.py):
-  //   one K chunk of a work unit costs 2*BN + 60 cycles in the CTA-pair kernel (MMA time of the 256 x BN x 64 product +
-  //   pipeline hand-over), a unit adds ~2000 cycles of exposed prologue / epilogue, the launch takes
-  //   ceil(units / slots) waves of those, and a split-K launch pays the second pass (fixed ~4000 cycles + its traffic at
-  //   ~2200 B/cycle).  The CTA-pair kernel wins wherever Cout > 64 (half of the weight tile per CTA); among its N tiles
-  //   the model picks 192 / 128 where they divide Cout better or give a fuller last wave, and splits K only where the
-  //   tile count would leave most SM pairs idle (level 3 of the U).
-  int BN = g_force_bn;
-  int splits = 1;
-  int two_cta = (Cout > 64 && g_force_2cta != 1) ? 1 : 0;
-  if (g_force_2cta == 2 && Cout > 64) two_cta = 1;
-  if (halo_pitch) two_cta = 1;
-  const long long M_total = static_cast<long long>(NB) * H * W;
-  const bool can_split = !halo_pitch && workspace && out_mode == 0 && Cout % 8 == 0;
-  auto split_ok = [&](int bn, int sp) {
-    (void)bn;
-    if (sp == 1) return true;
-    const int kps = (kchunks + sp - 1) / sp;
-    return can_split && kps >= 8 && (sp - 1) * kps < kchunks &&
-           static_cast<long long>(sp) * M_total * Cout * 4 <= workspace_bytes;
-  };
-  auto model = [&](int bn, int sp, bool pair) {
-    const long long nt = (Cout + bn - 1) / bn;
-    const long long units = static_cast<long long>(pair ? (p.m_tiles + 1) / 2 : p.m_tiles) * nt * sp;
-    const long long slots = pair ? num_sms() / 2 : num_sms();
-    const long long waves = (units + slots - 1) / slots;
-    const long long kps = (kchunks + sp - 1) / sp;
-    const long long chunk = pair ? 2 * bn + 60 : (bn >= 256 ? 768 : 2 * bn + 160);  // 1-CTA: operand-bandwidth bound
-    long long cost = waves * (kps * chunk + 2000);
-    if (sp > 1) cost += 4000 + (static_cast<long long>(sp) + 1) * M_total * Cout * 4 / 2200;
-    return cost;
-  };
-  if (BN == 0) {
-    if (Cout <= 16) BN = 16;
-    else if (Cout <= 64) BN = 64;
-    else if (Cout <= 128) BN = 128;
-    else BN = 0;  // chosen below together with the split factor
-  }
-  if (two_cta && BN != 0 && BN < 128) two_cta = 0;
-  {
-    const int cand[3] = {256, 192, 128};
-    long long best = -1;
-    int best_bn = BN ? BN : 256, best_sp = 1;
-    for (int ci = 0; ci < 3; ++ci) {
-      const int bn = BN ? BN : cand[ci];
-      if (BN && ci > 0) break;
-      for (int sp = 1; sp <= 8; ++sp) {
-        if (g_force_split > 0 && sp != g_force_split) continue;
-        if (halo_pitch && sp > 1) continue;
-        if (!split_ok(bn, sp)) continue;
-        const long long c = model(bn, sp, two_cta != 0);
-        if (best < 0 || c < best) {  // ties keep the wider tile / the smaller split (visited first)
-          best = c;
-          best_bn = bn;
-          best_sp = sp;
-        }
-      }
-    }
-    BN = best_bn;
-    splits = best_sp;
-  }
+  const int BN = pl.BN, splits = pl.splits, two_cta = pl.two_cta, fuse_stats = pl.fuse_stats;
   p.two_cta = two_cta;
   p.splits = splits;
   p.k_per_split = (kchunks + splits - 1) / splits;
@@ -333,27 +386,8 @@ int k2_conv_gemm(const K2ConvSrc* srcs, int nsrc, int NB, int H, int W, const vo
   p.out = out;
   p.ldo = ldo;
   p.out_mode = (splits > 1) ? 2 : out_mode;
-  // fused GroupNorm partial statistics: only when a tile never straddles two images and the tile holds final values
-  // (split-K launches produce them in the second pass instead, as 16-row groups of the flat pixel order)
-  const long long HWl = static_cast<long long>(H) * W;
-  int fuse_stats = 0, row_groups = 0;
-  if (gn_partial && out_mode == 0 && Cout % 8 == 0) {
-    if (splits == 1 && BN >= 64 && Cout % 64 == 0 && (p.TN == 1 || p.TH * p.TW == 16)) {
-      fuse_stats = 1;
-      // TN == 1: one partial per M tile (the epilogue folds its four warps); 16-pixel multi-image tiles: one partial per
-      // (image, spatial tile) -- every half warp of the epilogue holds exactly one image's 16 pixels
-      row_groups = (p.TN == 1) ? p.m_tiles : NB * p.tiles_h * p.tiles_w;
-    } else if (splits > 1 && HWl % 16 == 0) {
-      fuse_stats = 2;
-      row_groups = static_cast<int>(p.M_total / 16);
-    }
-  }
   p.gn_part = (fuse_stats == 1) ? reinterpret_cast<float2*>(gn_partial) : nullptr;
   p.gn_mode = (fuse_stats == 1) ? (p.TN == 1 ? 1 : 2) : 0;
-  if (info) {
-    info[0] = BN; info[1] = two_cta; info[2] = splits; info[3] = p.m_tiles; info[4] = p.TN; info[5] = fuse_stats;
-    info[6] = row_groups;
-  }
   if (out_mode == 0) {
     K2_REQUIRE(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "conv_gemm: out alignment");
     if (residual)
@@ -368,6 +402,16 @@ int k2_conv_gemm(const K2ConvSrc* srcs, int nsrc, int NB, int H, int W, const vo
     if (rc == 0) g_launches.fetch_add(1, std::memory_order_relaxed);
   }
   return rc;
+}
+
+int k2_conv_plan(int NB, int H, int W, int taps, int Ktot, int Cout, int out_mode, long long workspace_bytes,
+                 int want_gn_partial, int* info) {
+  K2_REQUIRE(NB > 0 && H > 0 && W > 0 && Cout > 0 && info, "conv_plan: bad arguments");
+  K2_REQUIRE(Ktot > 0 && Ktot % 64 == 0, "conv_plan: Ktot must be a positive multiple of 64");
+  ConvPlan pl;
+  plan_conv(NB, H, W, taps == 9, Ktot / 64, Cout, out_mode, workspace_bytes > 0, workspace_bytes, want_gn_partial != 0, pl);
+  plan_to_info(pl, info);
+  return 0;
 }
 
 }  // extern "C"

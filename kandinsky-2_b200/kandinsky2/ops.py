@@ -108,6 +108,15 @@ def conv_gemm(srcs, w_packed, cout, bias=None, residual=None, out=None, out_mode
     return out
 
 
+def conv_plan(NB, H, W, taps, ktot, cout, out_mode=0, workspace_bytes=1 << 28, want_gn_partial=True):
+    """What k2_conv_gemm would decide for this geometry (host arithmetic only, no GPU): dict of the info[7] fields."""
+    lib = nat.load()
+    info = (ctypes.c_int * 7)()
+    check(lib.k2_conv_plan(NB, H, W, taps, ktot, cout, out_mode, workspace_bytes, int(want_gn_partial), info))
+    keys = ("n_tile", "cta_pair", "splits", "m_tiles", "images_per_tile", "gn_partial_mode", "row_groups")
+    return dict(zip(keys, list(info)))
+
+
 def gemm_rows(x, w_packed, cout, bias=None, residual=None, out=None):
     """x: fp16 [..., K] rows -> fp16 [..., cout]; one 1x1 'conv' over M = prod(leading dims) rows."""
     lead = x.shape[:-1]

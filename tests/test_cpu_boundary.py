@@ -72,3 +72,38 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports the oracle"
+
+
+def test_conv_plan_host_logic():
+    """k2_conv_plan = the decisions k2_conv_gemm takes before touching a pointer (tile box, N tile, CTA pair, split-K,
+    GroupNorm-partial layout); pure host arithmetic, so the shapes of the 768x768 step are pinned here without a GPU."""
+    from kandinsky2 import ops
+    # level 0, 384 -> 384 3x3 at 96x96, UNet batch 8: (8 x 16)-pixel tiles, N tile 192 (divides 384), CTA pair, no split,
+    # one GroupNorm partial per M tile
+    pl = ops.conv_plan(8, 96, 96, 9, 9 * 384, 384)
+    assert pl == dict(n_tile=192, cta_pair=1, splits=1, m_tiles=576, images_per_tile=1, gn_partial_mode=1, row_groups=576)
+    # level 1, 768 -> 768: widest tile
+    pl = ops.conv_plan(8, 48, 48, 9, 9 * 768, 768)
+    assert (pl["n_tile"], pl["splits"], pl["m_tiles"]) == (256, 1, 144)
+    # level 2 (24 x 24): unsplit, N tile 192 (1152 = 6 x 192), 5-row tiles inside one image
+    pl = ops.conv_plan(8, 24, 24, 9, 9 * 1152, 1152)
+    assert (pl["n_tile"], pl["splits"], pl["m_tiles"], pl["images_per_tile"], pl["gn_partial_mode"]) == (192, 1, 40, 1, 1)
+    # level 3 (12 x 12): (4 x 4 pixels x 8 images) tiles with every MMA row used, partials per (image, spatial tile)
+    pl = ops.conv_plan(8, 12, 12, 9, 9 * 1536, 1536)
+    assert (pl["m_tiles"], pl["images_per_tile"], pl["splits"], pl["gn_partial_mode"], pl["row_groups"]) == (9, 8, 1, 1, 72)
+    # attention qkv as a flat-row GEMM, and the 4-channel fp32 NCHW output head (single-CTA kernel, N tile 16)
+    assert ops.conv_plan(1, 1, 18432, 1, 768, 2304, want_gn_partial=False)["n_tile"] == 256
+    pl = ops.conv_plan(8, 96, 96, 9, 9 * 384, 8, out_mode=1, want_gn_partial=False)
+    assert (pl["n_tile"], pl["cta_pair"], pl["gn_partial_mode"]) == (16, 0, 0)
+    # a forced 2-way split moves the statistics to the second pass (16-row groups); without a workspace it cannot split
+    ops.set_tuning(1, 2)
+    try:
+        pl = ops.conv_plan(8, 12, 12, 9, 9 * 1536, 1536)
+        assert (pl["splits"], pl["gn_partial_mode"], pl["row_groups"]) == (2, 2, 8 * 144 // 16)
+        assert ops.conv_plan(8, 12, 12, 9, 9 * 1536, 1536, workspace_bytes=0)["splits"] == 1
+    finally:
+        ops.set_tuning(1, 0)
+    # ragged geometry: tiles never exceed 128 pixels and cover the image
+    for (nb, h, w) in [(3, 16, 12), (1, 7, 5), (5, 12, 12), (2, 100, 36)]:
+        pl = ops.conv_plan(nb, h, w, 9, 9 * 64, 64)
+        assert pl["m_tiles"] * 128 >= nb * h * w
