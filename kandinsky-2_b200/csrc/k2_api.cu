@@ -1,6 +1,7 @@
 // k2_api.cu -- C-ABI plumbing: error state, launch counter, TMA descriptor encoding, and the
 // k2_conv_gemm entry point (geometry selection + tensor maps) declared in include/k2b200.h.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -33,6 +34,14 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 bool pdl_enabled() { return g_pdl != 0; }
 int attention_stagger() { return g_attn_stagger; }
 int attention_poly_mode() { return g_attn_poly; }
+static int g_attn_issue = -1;  // -1: take K2_ATTN_ISSUE from the environment at first use (default 0)
+int attention_issue_mode() {
+  if (g_attn_issue < 0) {
+    const char* e = getenv("K2_ATTN_ISSUE");
+    g_attn_issue = (e && e[0] == '1') ? 1 : 0;
+  }
+  return g_attn_issue;
+}
 static unsigned long long g_attn_trace = 0;
 unsigned long long* attention_trace_buffer() { return reinterpret_cast<unsigned long long*>(g_attn_trace); }
 
@@ -295,6 +304,10 @@ int k2_set_tuning(int key, int value) {
   }
   if (key == 6) {
     g_attn_poly = value;
+    return 0;
+  }
+  if (key == 9) {  // attention MMA issue order: 0 fixed, 1 event driven
+    g_attn_issue = value ? 1 : 0;
     return 0;
   }
   if (key == 7) {  // diagnostics: device address of the attention trace buffer, low / high 32 bits

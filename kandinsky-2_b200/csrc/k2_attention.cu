@@ -193,39 +193,83 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_d64_kernel(const __grid
           }
         }
       }
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int j = 0; j < nblk; ++j) {
-        int nstage = stage + 1;
-        uint32_t nphase = phase;
-        if (nstage == KV_STAGES) {
-          nstage = 0;
-          nphase ^= 1;
-        }
-        if (j + 1 < nblk) {
-          // S_t(j+1) as soon as the warpgroup holds S_t(j) in registers: the next scores are ready long before the
-          // softmax of block j ends, so the warpgroups never wait for the tensor core in steady state
-          mbar_wait(&kv_full[nstage], nphase);
-          tc_fence_after();
-          for (int t = 0; t < ntile; ++t) {
-            trace_pt<POLY>(p, 2, j, t * 4 + 0);
-            mbar_wait(&s_free[t], j & 1);
-            tc_fence_after();
-            issue_s(t, nstage);
-            trace_pt<POLY>(p, 2, j, t * 4 + 1);
+      if (p.issue_mode == 1) {
+        // Event-driven order: poll both query tiles' barriers and issue whatever is ready.  The fixed order below makes
+        // S_0(j+2) wait for P_1(j), which pulls the two tiles' phases together within one key block; polling lets them run
+        // half a period apart (initial offset = stagger_cycles) so one tile's exponentials overlap the other's max /
+        // barrier / hand-over phases.  Every barrier is at most one phase ahead of its consumer (p_full(j+1) needs
+        // pv_done(j), s_free(j+1) needs S(j+1), kv_full is refilled only after kv_empty), so parity tests are unambiguous.
+        int s_next[QT] = {1, 1}, pv_next[QT] = {0, 0};
+        int kv_seen = 1;  // key blocks whose K / V have landed
+        long long t_last = clock64();
+        while (pv_next[0] < nblk || (ntile == 2 && pv_next[1] < nblk)) {
+          bool progress = false;
+#pragma unroll
+          for (int t = 0; t < QT; ++t) {
+            if (t >= ntile) continue;
+            int j = pv_next[t];
+            if (j < nblk && mbar_try_wait(&p_full[t], j & 1)) {
+              tc_fence_after();
+              issue_pv(t, j, j % KV_STAGES);
+              umma_commit(&pv_done[t]);
+              pv_next[t] = j + 1;
+              const int other = (ntile == 2) ? pv_next[t ^ 1] : j + 1;
+              if (other > j) umma_commit(&kv_empty[j % KV_STAGES]);  // both tiles are done with K(j) / V(j)
+              progress = true;
+            }
+            j = s_next[t];
+            if (j < nblk && mbar_try_wait(&s_free[t], (j - 1) & 1)) {
+              if (j >= kv_seen && mbar_try_wait(&kv_full[j % KV_STAGES], (j / KV_STAGES) & 1)) kv_seen = j + 1;
+              if (j < kv_seen) {
+                tc_fence_after();
+                issue_s(t, j % KV_STAGES);
+                s_next[t] = j + 1;
+                progress = true;
+              }
+            }
+          }
+          if (progress) {
+            t_last = clock64();
+          } else if (clock64() - t_last > 4000000000LL) {  // a pipeline bug traps instead of hanging the GPU
+            printf("k2b200: attention issuer stalled (block %d,%d,%d)\n", blockIdx.x, blockIdx.y, blockIdx.z);
+            __trap();
           }
         }
-        for (int t = 0; t < ntile; ++t) {
-          mbar_wait(&p_full[t], j & 1);
-          trace_pt<POLY>(p, 2, j, t * 4 + 2);
-          tc_fence_after();
-          issue_pv(t, j, stage);
-          umma_commit(&pv_done[t]);
-          if (t == ntile - 1) umma_commit(&kv_empty[stage]);
-          trace_pt<POLY>(p, 2, j, t * 4 + 3);
+      } else {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int j = 0; j < nblk; ++j) {
+          int nstage = stage + 1;
+          uint32_t nphase = phase;
+          if (nstage == KV_STAGES) {
+            nstage = 0;
+            nphase ^= 1;
+          }
+          if (j + 1 < nblk) {
+            // S_t(j+1) as soon as the warpgroup holds S_t(j) in registers: the next scores are ready long before the
+            // softmax of block j ends, so the warpgroups never wait for the tensor core in steady state
+            mbar_wait(&kv_full[nstage], nphase);
+            tc_fence_after();
+            for (int t = 0; t < ntile; ++t) {
+              trace_pt<POLY>(p, 2, j, t * 4 + 0);
+              mbar_wait(&s_free[t], j & 1);
+              tc_fence_after();
+              issue_s(t, nstage);
+              trace_pt<POLY>(p, 2, j, t * 4 + 1);
+            }
+          }
+          for (int t = 0; t < ntile; ++t) {
+            mbar_wait(&p_full[t], j & 1);
+            trace_pt<POLY>(p, 2, j, t * 4 + 2);
+            tc_fence_after();
+            issue_pv(t, j, stage);
+            umma_commit(&pv_done[t]);
+            if (t == ntile - 1) umma_commit(&kv_empty[stage]);
+            trace_pt<POLY>(p, 2, j, t * 4 + 3);
+          }
+          stage = nstage;
+          phase = nphase;
         }
-        stage = nstage;
-        phase = nphase;
       }
     }
   } else if (warp_idx >= 4) {
@@ -463,6 +507,7 @@ extern "C" int k2_attention_d64(const void* qkv, int ldq, int hs, int q_off, int
   p.scale_log2e = scale * 1.4426950408889634f;
   p.stagger_cycles = attention_stagger();
   p.trace = attention_trace_buffer();
+  p.issue_mode = attention_issue_mode();
   int rc = launch_attention_d64(p, static_cast<cudaStream_t>(stream));
   if (rc == 0) count_launch();
   return rc;

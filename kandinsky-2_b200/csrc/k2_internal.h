@@ -93,10 +93,12 @@ struct AttnParams {
   int ldo;
   float scale_log2e;   // softmax scale * log2(e)
   int stagger_cycles;  // initial delay of the second query tile's first score product (de-phases the warpgroups)
-  unsigned long long* trace;  // diagnostics: 3 x 4 x 8 clock64 stamps of CTA (0,0,0), or null
+  unsigned long long* trace;  // diagnostics: 3 x 16 x 8 clock64 stamps of CTA (0,0,0), or null
+  int issue_mode;      // MMA issuer: 0 = fixed program order per key block, 1 = event driven (polls both query tiles)
 };
 int attention_stagger();
 unsigned long long* attention_trace_buffer();
+int attention_issue_mode();
 int attention_poly_mode();  // eighths of the softmax exponentials evaluated without MUFU: 0, 2, 3, 4
 int launch_attention_d64(const AttnParams& p, cudaStream_t stream);
 

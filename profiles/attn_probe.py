@@ -16,7 +16,9 @@ for (B, heads, T, Tc) in [(8, 12, 2304, 32), (8, 18, 576, 32), (8, 24, 144, 32)]
     out = torch.empty(B, T, heads * 64, device="cuda", dtype=torch.float16)
     flops = 4 * B * heads * T * (T + Tc) * 64
     # tuning key 6: eighths of the exponentials on the FMA pipe; key 5: initial de-phasing of the two query tiles (cycles)
-    for delay, stag in ((0, 0), (0, 300), (0, 1000), (0, 1400), (0, 1800), (2, 1400), (3, 1400), (4, 1400)):
+    # key 9: MMA issue order (0 fixed per key block, 1 event driven)
+    for mode, delay, stag in ((0, 0, 300), (1, 0, 0), (1, 0, 300), (1, 0, 1000), (1, 0, 1700), (1, 0, 2400), (1, 2, 1700), (1, 3, 1700)):
+        ops.set_tuning(9, mode)
         ops.set_tuning(6, delay)
         ops.set_tuning(5, stag)
         for _ in range(3):
@@ -29,4 +31,8 @@ for (B, heads, T, Tc) in [(8, 12, 2304, 32), (8, 18, 576, 32), (8, 24, 144, 32)]
         e.record()
         torch.cuda.synchronize()
         us = s.elapsed_time(e) / 20 * 1e3
-        print(f"T={T} heads={heads} poly={delay}/8 stagger={stag}: {us:.1f} us {flops / us / 1e6:.0f} TF/s", flush=True)
+        print(f"T={T} heads={heads} issue={mode} poly={delay}/8 stagger={stag}: {us:.1f} us {flops / us / 1e6:.0f} TF/s", flush=True)
+
+ops.set_tuning(9, 0)
+ops.set_tuning(6, 0)
+ops.set_tuning(5, 300)
