@@ -102,3 +102,54 @@ def ddim_step(x, eps, a_t, a_prev):
     """p_sample_ddim with sigma = 0 (model/samplers.py:311-330)."""
     pred_x0 = (x - (1.0 - a_t) ** 0.5 * eps) / a_t ** 0.5
     return a_prev ** 0.5 * pred_x0 + (1.0 - a_prev) ** 0.5 * eps
+
+
+def _cfg_eps(unet_fn, x, t_value, guidance):
+    """CFG closure of the DDIM / PLMS path (kandinsky2_1_model.py:222-233, sampler != "p_sampler"): the UNet runs on
+    [x, x] with [cond, uncond] conditioning, only the guided epsilon (4 channels) is returned."""
+    B = x.shape[0]
+    ts = torch.full((2 * B,), float(t_value), dtype=torch.float32, device=x.device)
+    out = unet_fn(torch.cat([x, x], dim=0), ts)
+    eps = out[:, :4]
+    cond, uncond = eps[:B], eps[B:]
+    return uncond + guidance * (cond - uncond)
+
+
+def ddim_sample_loop(unet_fn, x_T, num_steps, guidance):
+    """DDIMSampler.sample / ddim_sampling / p_sample_ddim with eta = 0 (model/samplers.py:150-330).
+    unet_fn(x[2B], t[2B]) -> [2B, 8, H, W] with the cond rows first; x_T: [B, 4, H, W]."""
+    tt, al, alp = ddim_schedule(num_steps)
+    x = x_T
+    for i in range(len(tt))[::-1]:  # np.flip(timesteps), index = total_steps - i - 1
+        eps = _cfg_eps(unet_fn, x, tt[i], guidance)
+        x = ddim_step(x, eps, float(np.float32(al[i])), float(np.float32(alp[i])))
+    return x
+
+
+def plms_sample_loop(unet_fn, x_T, num_steps, guidance):
+    """PLMSSampler.sample / plms_sampling / p_sample_plms with eta = 0 (model/samplers.py:416-637): pseudo improved Euler
+    for the first step (a second UNet call at the next timestep), then Adams-Bashforth of order 2, 3, 4 over the history
+    of guided epsilons (at most 3 kept)."""
+    tt, al, alp = ddim_schedule(num_steps)
+    order = list(range(len(tt)))[::-1]
+    x = x_T
+    old = []
+    for n, i in enumerate(order):
+        a_t, a_prev = float(np.float32(al[i])), float(np.float32(alp[i]))
+        e_t = _cfg_eps(unet_fn, x, tt[i], guidance)
+        if len(old) == 0:
+            x_prev = ddim_step(x, e_t, a_t, a_prev)
+            t_next = tt[order[min(n + 1, len(order) - 1)]]
+            e_next = _cfg_eps(unet_fn, x_prev, t_next, guidance)
+            e_prime = (e_t + e_next) / 2
+        elif len(old) == 1:
+            e_prime = (3 * e_t - old[-1]) / 2
+        elif len(old) == 2:
+            e_prime = (23 * e_t - 16 * old[-1] + 5 * old[-2]) / 12
+        else:
+            e_prime = (55 * e_t - 59 * old[-1] + 37 * old[-2] - 9 * old[-3]) / 24
+        x = ddim_step(x, e_prime, a_t, a_prev)
+        old.append(e_t)
+        if len(old) >= 4:
+            old.pop(0)
+    return x

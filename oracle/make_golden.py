@@ -171,6 +171,53 @@ def golden_trajectory(name, cfg, B, H, W, ntext, steps, guidance, wseed, iseed):
     print(f"{name}: final latent std {out.std():.4f}, oracle-vs-reference max abs {err:.2e}")
 
 
+def golden_sampler(name, which, cfg, B, H, W, ntext, steps, guidance, wseed, iseed):
+    """Reference DDIMSampler / PLMSSampler (model/samplers.py, the non-p_sampler branch of Kandinsky2_1.generate_img,
+    kandinsky2_1_model.py:222-281) on the tiny reference UNet.  The classes hard-code "cuda"; ref_shim.cuda_as_cpu maps
+    that device to the CPU without touching the reference source."""
+    from oracle import diffusion_oracle as do
+    model = build_ref_unet(cfg)
+    sd = synth.synth_state_dict(uo.unet_param_spec(cfg), seed=wseed)
+    model.load_state_dict(sd, strict=True)
+    inp = unet_inputs(cfg, 2 * B, H, W, ntext, iseed)
+    g = torch.Generator().manual_seed(iseed + 200)
+    x_T = torch.randn(B, 4, H, W, generator=g)
+    kw = dict(full_emb=inp["full_emb"], pooled_emb=inp["pooled_emb"], image_emb=inp["image_emb"])
+    with ref_shim.reference_modules() as R, ref_shim.cuda_as_cpu():
+        mc = R.load("model.model_creation")
+        sm = R.load("model.samplers")
+        diffusion = mc.create_gaussian_diffusion(steps=1000, learn_sigma=True, sigma_small=False, noise_schedule="linear",
+                                                 use_kl=False, predict_xstart=False, rescale_timesteps=True,
+                                                 rescale_learned_sigmas=True, timestep_respacing="",
+                                                 linear_start=0.00085, linear_end=0.012)
+
+        def model_fn(x_t, ts, **kwargs):  # kandinsky2_1_model.py:222-233, sampler != "p_sampler"
+            half = x_t[: len(x_t) // 2]
+            combined = torch.cat([half, half], dim=0)
+            model_out = model(combined, ts, **kwargs)
+            eps = model_out[:, :4]
+            cond_eps, uncond_eps = torch.split(eps, len(eps) // 2, dim=0)
+            half_eps = uncond_eps + guidance * (cond_eps - uncond_eps)
+            return torch.cat([half_eps, half_eps], dim=0)
+
+        cls = sm.DDIMSampler if which == "ddim" else sm.PLMSSampler
+        sampler = cls(model=model_fn, old_diffusion=diffusion, schedule="linear")
+        model.del_cache()
+        with torch.no_grad():
+            out, _ = sampler.sample(steps, 2 * B, (4, H, W), conditioning=kw, x_T=torch.cat([x_T, x_T]), verbose=False)
+        out = out[:B].clone()
+        ddim_t = np.asarray(sampler.ddim_timesteps).copy()
+    loop = do.ddim_sample_loop if which == "ddim" else do.plms_sample_loop
+    with torch.no_grad():
+        orc = loop(lambda xx, tt: uo.unet_forward(sd, cfg, xx, tt, **kw), x_T, steps, guidance)
+    err = (out - orc).abs().max().item()
+    assert np.array_equal(ddim_t, do.ddim_schedule(steps)[0]), "DDIM timesteps differ"
+    assert err <= 1e-4, f"{name}: oracle {which} loop deviates from the reference by {err}"
+    torch.save(dict(cfg=cfg, weight_seed=wseed, cond=kw, x_T=x_T.clone(), steps=steps, guidance=guidance, out=out,
+                    sampler=which), os.path.join(GOLD, name + ".pt"))
+    print(f"{name}: final latent std {out.std():.4f}, oracle-vs-reference max abs {err:.2e}")
+
+
 def golden_schedule():
     """Known-answer constants of the reference schedule code."""
     with ref_shim.reference_modules() as R:
@@ -202,6 +249,8 @@ EXTRA = [
     lambda: golden_movq("movq_tiny", __import__("oracle.movq_oracle", fromlist=["x"]).DDCONFIG_TINY, 2, 8, 8, wseed=4, iseed=3),
     lambda: golden_trajectory("traj_tiny", uo.CONFIG_TINY, 2, 16, 16, 7, steps=5, guidance=4.0, wseed=1, iseed=21),
     golden_schedule,
+    lambda: golden_sampler("ddim_tiny", "ddim", uo.CONFIG_TINY, 2, 16, 16, 7, steps=4, guidance=3.0, wseed=1, iseed=21),
+    lambda: golden_sampler("plms_tiny", "plms", uo.CONFIG_TINY, 2, 16, 16, 7, steps=5, guidance=2.0, wseed=1, iseed=21),
 ]
 
 if __name__ == "__main__":

@@ -53,6 +53,20 @@ def test_trajectory_oracle_matches_reference_golden():
     assert (out - fx["out"]).abs().max().item() <= 1e-4
 
 
+@pytest.mark.parametrize("name", ["ddim_tiny", "plms_tiny"])
+def test_ddim_plms_oracle_matches_reference_golden(name):
+    """The oracle's DDIM / PLMS loops vs the output of the reference's own DDIMSampler / PLMSSampler classes
+    (model/samplers.py, executed by oracle/make_golden.py through the cuda->cpu device shim)."""
+    from oracle import diffusion_oracle as do, synth, unet_oracle as uo
+    fx = _load(name)
+    cfg = fx["cfg"]
+    sd = synth.synth_state_dict(uo.unet_param_spec(cfg), seed=fx["weight_seed"])
+    loop = do.ddim_sample_loop if fx["sampler"] == "ddim" else do.plms_sample_loop
+    with torch.no_grad():
+        out = loop(lambda xx, tt: uo.unet_forward(sd, cfg, xx, tt, **fx["cond"]), fx["x_T"], fx["steps"], fx["guidance"])
+    assert (out - fx["out"]).abs().max().item() <= 1e-4
+
+
 def test_schedule_known_answers():
     """Constants obtained by running the reference + the product's host schedule code."""
     from oracle import diffusion_oracle as do
