@@ -181,8 +181,9 @@ class DDIMSampler:
     with e the CFG-combined epsilon (no clamp, no threshold, no noise).  The UNet sees the raw DDIM timestep (model_fn is
     called directly, not through _WrappedModel).  The update is linear in (x0, x), so it runs on the same fused step
     kernel with coefficients  c2 = sqrt(a_prev) - sqrt(1-a_prev) sqrt(a_t) / sqrt(1-a_t),  c3 = sqrt(1-a_prev) / sqrt(1-a_t).
-    The reference's samplers hard-code "cuda" (:78-79,101,226) and cannot be run in the build container: the schedule
-    helpers are pinned against it (tests/golden/schedule_kat.pt), the 4-line update rule is restated ("parity unpinned")."""
+    Pinned: the schedule helpers against tests/golden/schedule_kat.pt, the whole loop against the final latents of the
+    reference's own DDIMSampler / PLMSSampler classes (tests/golden/ddim_tiny.pt, plms_tiny.pt; their hard-coded "cuda"
+    device, :78-79,101,226, is remapped to the CPU by the generating script, oracle/make_golden.py)."""
 
     def __init__(self, model, old_diffusion, schedule="linear", **kwargs):
         self.model = model
