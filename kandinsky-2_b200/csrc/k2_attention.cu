@@ -6,20 +6,25 @@
 // flash-attn path (:303-332).  Keys/values are read from TWO buffers -- encoder tokens first, then the
 // spatial tokens -- so the concat never exists.
 //
-// One CTA = one (batch, head, 2 x 128-query tiles): two softmax warpgroups ping-pong on the tensor core, K/V tiles are
-// shared by both.  Per query tile and 128-key block j:
-//     S_j = Q K_j^T            tcgen05.mma  M128 N128 K64   -> TMEM  (S double-buffered, 2 x 128 columns)
-//     P_j = exp2(S_j*c - m)    4 softmax warps, one query row per thread: tcgen05.ld -> registers ->
-//                              fp16 -> shared memory in the 128B-swizzled K-major layout the MMA reads
-//     O_j = P_j V_j            tcgen05.mma  M128 N64 K128   -> TMEM  (O double-buffered, 2 x 64 columns)
-//     acc = acc*alpha + O_j    in registers (fp32), normalised by the row sum at the end.
-// V tiles are used as an MN-major B operand exactly as TMA lands them ([key][64 d] rows), so V is never
-// transposed.  Warp roles: warp0 TMA producer (Q once, K/V ring of 3 stages), warp1 MMA issuer, warp2 TMEM
-// allocator, warps 4-7 / 8-11 softmax + epilogue of query tile 0 / 1.  A warpgroup releases S_t as soon as the scores
-// sit in its registers (s_free), and the issuer answers with S_t(j+1) right away: the next scores are complete long
-// before the exponentials of block j are, so in steady state the warpgroups never wait for the tensor core (measured
-// with the clock64 trace, profiles/attn_trace.py: the old order P_t(j) -> PV_t(j) -> S_t(j+1) left each warpgroup idle
-// for ~1000 of every ~3450 cycles).  pv_done tells the warpgroup that O_t is current and the P_t buffer is free.
+// One CTA = one (batch, head, 2 x 128-query tiles); K/V tiles are shared by both query tiles.  Per query tile t and
+// 128-key block j:
+//     S_t(j) = Q_t K(j)^T        tcgen05.mma  M128 N128 K64   -> TMEM  (one 128-column S buffer per tile)
+//     P_t(j) = exp2(S*c - m)     8 softmax warps per tile, HALF a score row (64 keys) per thread: tcgen05.ld -> registers,
+//                                row maximum = FMNMX3 over the half row, exchanged between the two halves through shared
+//                                memory + one 256-thread named barrier, -> fp16 -> shared memory in the 128B-swizzled
+//                                K-major layout the MMA reads as its A operand
+//     O_t   += P_t(j) V(j)       tcgen05.mma  M128 N64 K128   -> TMEM  (O accumulated THERE; the softmax warps rescale it
+//                                only when a row maximum has outgrown the stale one by 2^8 -- exact either way)
+//     out = O_t / l              at the end, l = the two halves' row sums folded through shared memory.
+// V tiles are used as an MN-major B operand exactly as TMA lands them ([key][64 d] rows), so V is never transposed.
+// Warp roles (640 threads): warp0 TMA producer (Q once, K/V ring of 3 stages), warp1 MMA issuer, warp2 TMEM allocator,
+// warps 4-19 softmax + epilogue (tile = (w-4)/8, key half = ((w-4)/4)%2, TMEM lane quarter = w%4).  A tile's warps
+// release S_t as soon as the scores sit in their registers (s_free) and the issuer answers with S_t(j+1) right away; the
+// warps load it inside block j's exponentials (each 32-score quarter as soon as its registers are free), so neither the
+// hand-over nor the TMEM latency is exposed (measured with the clock64 trace, profiles/attn_trace.py: the first design's
+// order P_t(j) -> PV_t(j) -> S_t(j+1) left every warpgroup idle for ~1000 of each ~3450 cycles).  pv_done tells the
+// warps that O_t is current and the P_t buffer is free.  What bounds the kernel now is the exponential itself (MUFU
+// 16/clk/SM) plus the per-block latency chain max -> barrier -> exp -> store -> fence -> arrive (profiles/README.md).
 #include <string.h>
 
 #include <algorithm>
