@@ -19,24 +19,6 @@ constexpr int LIN_CB = 4;   // output columns per warp pass (register blocking o
 constexpr int LIN_NI = 4;   // column groups per warp (amortises the staging of x)
 
 template <bool W_HALF>
-__device__ __forceinline__ void load_w8(const void* Wv, long long off, float (&w)[8]) {
-  if (W_HALF) {
-    uint4 raw = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(Wv) + off));
-    const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      float2 t = __half22float2(h2[e]);
-      w[2 * e] = t.x;
-      w[2 * e + 1] = t.y;
-    }
-  } else {
-    const float4* wp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(Wv) + off);
-    float4 a = __ldg(wp), c = __ldg(wp + 1);
-    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = c.x; w[5] = c.y; w[6] = c.z; w[7] = c.w;
-  }
-}
-
-template <bool W_HALF>
 __global__ void __launch_bounds__(256) linear_kernel(const float* __restrict__ x, int ldx, const void* __restrict__ Wv,
                                                      const float* __restrict__ b, const float* __restrict__ add,
                                                      int ldadd, float* __restrict__ y, int ldy, int M, int N, int K,
