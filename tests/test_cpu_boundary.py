@@ -107,3 +107,33 @@ def test_conv_plan_host_logic():
     for (nb, h, w) in [(3, 16, 12), (1, 7, 5), (5, 12, 12), (2, 100, 36)]:
         pl = ops.conv_plan(nb, h, w, 9, 9 * 64, 64)
         assert pl["m_tiles"] * 128 >= nb * h * w
+
+
+def test_diffusers_key_remap_roundtrip_and_head_interleave():
+    """kandinsky2/checkpoints.py: the 2.2 (diffusers-layout) <-> package key maps are inverse bijections onto the exact key
+    set of Text2ImUNet(cond_version="2.2"), and the head-interleaved qkv packing equals separate q / k / v projections
+    under the reference's own split (`unet.py:296-307`)."""
+    from kandinsky2 import checkpoints as ck
+    from oracle import unet_oracle as uo
+    cfg = uo.CONFIG_2_2
+    spec = uo.unet_param_spec(cfg)
+    g = torch.Generator().manual_seed(3)
+    sd = {k: torch.randn(*s, generator=g) for k, s in spec}
+    kw = dict(in_channels=cfg["in_channels"], model_channels=cfg["model_channels"], channel_mult=tuple(cfg["channel_mult"]),
+              num_res_blocks=cfg["num_res_blocks"], attention_ds=tuple(cfg["attention_ds"]))
+    dsd = ck.k2_to_diffusers_unet(sd, **kw)
+    assert len(dsd) > len(sd)                      # qkv / encoder_kv split into 5 tensors each
+    assert any(k.startswith("down_blocks.0.downsamplers.0.conv1") for k in dsd)
+    assert "down_blocks.1.attentions.0.add_k_proj.weight" in dsd and "up_blocks.0.upsamplers.0.norm1.weight" in dsd
+    back = ck.diffusers_unet_to_k2(dsd, **kw)
+    assert sorted(back) == sorted(sd)
+    assert all(torch.equal(back[k], sd[k]) for k in sd)
+    # numerics of the interleave: Conv1d(qkv) + the reference's per-head split == three separate Linear projections
+    C, heads, T = 128, 2, 5
+    wq, wk, wv = (torch.randn(C, C, generator=g) for _ in range(3))
+    x = torch.randn(3, C, T, generator=g)
+    qkv = torch.nn.functional.conv1d(x, ck.pack_heads([wq, wk, wv]).unsqueeze(-1))          # [B, 3C, T]
+    q, k, v = qkv.reshape(3 * heads, 3 * 64, T).split(64, dim=1)                             # unet.py:298-299
+    for got, w in ((q, wq), (k, wk), (v, wv)):
+        ref = torch.einsum("oc,bct->bot", w, x).reshape(3 * heads, 64, T)
+        assert torch.allclose(got, ref, atol=1e-5)
