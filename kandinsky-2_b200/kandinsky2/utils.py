@@ -44,6 +44,9 @@ def q_sample(x_start, t, schedule_name="linear", num_steps=1000, noise=None):
     ac = np.cumprod(1.0 - betas, axis=0)
     if noise is None:
         noise = torch.randn_like(x_start)
-    a = float(np.float32(np.sqrt(ac[int(t)])))
-    b = float(np.float32(np.sqrt(1.0 - ac[int(t)])))
+    assert noise.shape == x_start.shape
+    tt = torch.as_tensor(t).long().reshape(-1).cpu()           # 0-d (the pipelines' call) or one timestep per sample
+    shape = (-1,) + (1,) * (x_start.dim() - 1)                 # _extract_into_tensor: float32 table values, broadcast
+    a = torch.from_numpy(np.sqrt(ac)).float()[tt].to(x_start.device).reshape(shape)
+    b = torch.from_numpy(np.sqrt(1.0 - ac)).float()[tt].to(x_start.device).reshape(shape)
     return a * x_start + b * noise

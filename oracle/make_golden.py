@@ -218,6 +218,26 @@ def golden_sampler(name, which, cfg, B, H, W, ntext, steps, guidance, wseed, ise
     print(f"{name}: final latent std {out.std():.4f}, oracle-vs-reference max abs {err:.2e}")
 
 
+def golden_host_utils():
+    """Reference host pre-processing of the img2img / inpainting entry points (`kandinsky2/utils.py:11-54`): prepare_mask
+    (python-loop erosion), prepare_image (PIL bicubic + scaling) and q_sample, on seeded inputs."""
+    from PIL import Image
+    g = torch.Generator().manual_seed(77)
+    mask = (torch.rand(1, 1, 24, 20, generator=g) > 0.3).float()
+    mask[:, :, 5:9, 4:12] = 0
+    img = (torch.rand(37, 53, 3, generator=g) * 255).to(torch.uint8).numpy()
+    x0 = torch.randn(2, 4, 8, 8, generator=g)
+    noise = torch.randn(2, 4, 8, 8, generator=g)
+    t = torch.tensor([10, 700])
+    with ref_shim.reference_modules() as R:
+        ut = R.load("utils")
+        out = dict(mask_in=mask.clone(), mask_out=ut.prepare_mask(mask.clone()), img_in=img,
+                   img_out=ut.prepare_image(Image.fromarray(img), w=64, h=48), x0=x0, noise=noise, t=t,
+                   q_out=ut.q_sample(x0, t, noise=noise))
+    torch.save(out, os.path.join(GOLD, "host_utils.pt"))
+    print("host_utils: mask kept", float(out["mask_out"].mean()), "q_sample std", float(out["q_out"].std()))
+
+
 def golden_schedule():
     """Known-answer constants of the reference schedule code."""
     with ref_shim.reference_modules() as R:
@@ -249,6 +269,7 @@ EXTRA = [
     lambda: golden_movq("movq_tiny", __import__("oracle.movq_oracle", fromlist=["x"]).DDCONFIG_TINY, 2, 8, 8, wseed=4, iseed=3),
     lambda: golden_trajectory("traj_tiny", uo.CONFIG_TINY, 2, 16, 16, 7, steps=5, guidance=4.0, wseed=1, iseed=21),
     golden_schedule,
+    golden_host_utils,
     lambda: golden_sampler("ddim_tiny", "ddim", uo.CONFIG_TINY, 2, 16, 16, 7, steps=4, guidance=3.0, wseed=1, iseed=21),
     lambda: golden_sampler("plms_tiny", "plms", uo.CONFIG_TINY, 2, 16, 16, 7, steps=5, guidance=2.0, wseed=1, iseed=21),
 ]

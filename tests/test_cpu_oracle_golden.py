@@ -134,3 +134,16 @@ def test_param_counts_and_flops():
     assert abs(uo.algorithmic_flops(uo.CONFIG_2_1, 2, 32, 32, 87) / 1e12 - 0.433) < 0.002
     fm = mo.decode_flops(mo.DDCONFIG_2_1, 4, 96, 96)
     assert abs(fm / 1e12 - 19.54) < 0.3  # 19.542 TFLOP per B=4 768^2 decode
+
+
+def test_host_preprocessing_matches_reference_golden():
+    """kandinsky2/utils.py of the product (prepare_mask, prepare_image, q_sample -- the host side of generate_img2img /
+    generate_inpainting) against the outputs of the reference's own functions (`utils.py:11-54`, host_utils.pt)."""
+    from PIL import Image
+    sys.path.insert(0, os.path.join(ROOT, "kandinsky-2_b200"))
+    from kandinsky2 import utils as ku
+    fx = _load("host_utils")
+    assert torch.equal(ku.prepare_mask(fx["mask_in"].clone()), fx["mask_out"])
+    assert torch.equal(ku.prepare_image(Image.fromarray(fx["img_in"]), w=64, h=48), fx["img_out"])
+    got = ku.q_sample(fx["x0"], fx["t"], noise=fx["noise"])
+    assert torch.allclose(got, fx["q_out"], rtol=0, atol=1e-6)
