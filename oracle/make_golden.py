@@ -238,6 +238,76 @@ def golden_host_utils():
     print("host_utils: mask kept", float(out["mask_out"].mean()), "q_sample std", float(out["q_out"].std()))
 
 
+def golden_prior(name, cfg, B, steps, guidance, wseed, iseed):
+    """Reference PriorTransformer.forward and PriorDiffusionModel.forward (`model/prior.py:159-384`) on synthetic weights.
+    `clip` (tokenizer only) is stubbed; the config is a SimpleNamespace with the fields prior.py reads."""
+    import types
+    from oracle import prior_oracle as po
+    spec = po.prior_param_spec(cfg)
+    sd = synth.synth_state_dict(spec, seed=wseed)
+    g = torch.Generator().manual_seed(iseed)
+    D, n_txt = cfg["clip_dim"], cfg["text_ctx"]
+    x = torch.randn(2 * B, D, generator=g)
+    t = torch.tensor([999.0, 500.0, 20.0, 0.0][:2 * B])
+    text_emb = torch.randn(2 * B, D, generator=g)
+    text_enc = torch.randn(2 * B, n_txt, cfg["clip_xf_width"], generator=g)
+    mask = torch.ones(2 * B, n_txt, dtype=torch.bool)
+    mask[0, 3:] = False
+    mask[B:, 1:] = False                                   # the unconditional rows: only the start token is real
+    x_T = torch.randn(B, D, generator=g)
+    step_noise = torch.randn(steps, B, D, generator=g)
+    clip_mean, clip_std = torch.randn(D, generator=g), torch.rand(D, generator=g) + 0.5
+    saved = {k: sys.modules.get(k) for k in ("clip", "clip.simple_tokenizer")}
+    clip_stub, tok_stub = types.ModuleType("clip"), types.ModuleType("clip.simple_tokenizer")
+    tok_stub.SimpleTokenizer = object
+    tok_stub.default_bpe = lambda: None
+    sys.modules["clip"], sys.modules["clip.simple_tokenizer"] = clip_stub, tok_stub
+    try:
+        with ref_shim.reference_modules() as R:
+            pr = R.load("model.prior")
+            gdm = R.load("model.gaussian_diffusion")
+            ns = types.SimpleNamespace
+            conf = ns(model=ns(hparams=ns(**cfg)),
+                      diffusion=ns(steps=1000, learn_sigma=False, sigma_small=True, noise_schedule="cosine", use_kl=False,
+                                   predict_xstart=True, rescale_learned_sigmas=False, timestep_respacing=""))
+            tok = ns(padded_tokens_and_mask=lambda texts, n: (torch.zeros(1, n, dtype=torch.long), torch.zeros(1, n, dtype=torch.bool)))
+            pdm = pr.PriorDiffusionModel(conf, tok, clip_mean, clip_std).eval()
+            assert [(k, tuple(v.shape)) for k, v in pdm.model.state_dict().items()] == [(k, tuple(s_)) for k, s_ in spec], \
+                "oracle prior parameter spec != reference state_dict"
+            pdm.model.load_state_dict(sd, strict=True)
+            with torch.no_grad():
+                y_ref = pdm.model(x, t, text_emb=text_emb, text_enc=text_enc, mask=mask, causal_mask=pdm.causal_mask)
+            # sampling loop with injected noise: first th.randn = x_T (both halves), th.randn_like = the per-step noise
+            it = iter(step_noise)
+            o_randn, o_like = gdm.th.randn, gdm.th.randn_like
+            gdm.th.randn = lambda *a, **k: torch.cat([x_T, x_T])
+            gdm.th.randn_like = lambda v: (lambda nz: torch.cat([nz, nz]))(next(it))
+            try:
+                with torch.no_grad():
+                    s_ref = pdm(text_emb, text_enc, mask, cf_guidance_scales=torch.full((B,), guidance),
+                                timestep_respacing=str(steps))
+            finally:
+                gdm.th.randn, gdm.th.randn_like = o_randn, o_like
+            rs = R.load("model.respace")
+            use_steps = sorted(rs.space_timesteps(1000, str(steps)))
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    with torch.no_grad():
+        y_orc = po.prior_forward(sd, cfg, x, t, text_emb, text_enc, mask)
+        s_orc = po.prior_sample(lambda xx, tt: po.prior_forward(sd, cfg, xx, tt, text_emb, text_enc, mask), x_T, step_noise,
+                                use_steps, guidance, clip_mean, clip_std)
+    e1, e2 = (y_ref - y_orc).abs().max().item(), (s_ref - s_orc).abs().max().item()
+    assert e1 <= 1e-4 and e2 <= 1e-4, f"{name}: oracle prior deviates from the reference: forward {e1}, sample {e2}"
+    torch.save(dict(cfg=cfg, weight_seed=wseed, x=x, t=t, text_emb=text_emb, text_enc=text_enc, mask=mask, out=y_ref,
+                    x_T=x_T, step_noise=step_noise, use_steps=use_steps, guidance=guidance, clip_mean=clip_mean,
+                    clip_std=clip_std, sample=s_ref), os.path.join(GOLD, name + ".pt"))
+    print(f"{name}: forward std {y_ref.std():.4f} (oracle err {e1:.2e}), sample std {s_ref.std():.4f} (oracle err {e2:.2e})")
+
+
 def golden_schedule():
     """Known-answer constants of the reference schedule code."""
     with ref_shim.reference_modules() as R:
@@ -270,6 +340,8 @@ EXTRA = [
     lambda: golden_trajectory("traj_tiny", uo.CONFIG_TINY, 2, 16, 16, 7, steps=5, guidance=4.0, wseed=1, iseed=21),
     golden_schedule,
     golden_host_utils,
+    lambda: golden_prior("prior_tiny", __import__("oracle.prior_oracle", fromlist=["x"]).CONFIG_PRIOR_TINY, 2, steps=4,
+                         guidance=4.0, wseed=5, iseed=31),
     lambda: golden_sampler("ddim_tiny", "ddim", uo.CONFIG_TINY, 2, 16, 16, 7, steps=4, guidance=3.0, wseed=1, iseed=21),
     lambda: golden_sampler("plms_tiny", "plms", uo.CONFIG_TINY, 2, 16, 16, 7, steps=5, guidance=2.0, wseed=1, iseed=21),
 ]

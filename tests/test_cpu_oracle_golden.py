@@ -147,3 +147,22 @@ def test_host_preprocessing_matches_reference_golden():
     assert torch.equal(ku.prepare_image(Image.fromarray(fx["img_in"]), w=64, h=48), fx["img_out"])
     got = ku.q_sample(fx["x0"], fx["t"], noise=fx["noise"])
     assert torch.allclose(got, fx["q_out"], rtol=0, atol=1e-6)
+
+
+def test_prior_oracle_matches_reference_golden():
+    """Groundwork for SURVEY.md 8f rank 3: the oracle's restatement of the diffusion prior (transformer forward and the
+    predict-x0 / cosine-schedule sampling loop with classifier-free guidance) against the outputs of the reference's own
+    PriorTransformer / PriorDiffusionModel classes (prior_tiny.pt)."""
+    from oracle import prior_oracle as po, synth
+    fx = _load("prior_tiny")
+    cfg = fx["cfg"]
+    sd = synth.synth_state_dict(po.prior_param_spec(cfg), seed=fx["weight_seed"])
+    with torch.no_grad():
+        y = po.prior_forward(sd, cfg, fx["x"], fx["t"], fx["text_emb"], fx["text_enc"], fx["mask"])
+        s = po.prior_sample(lambda xx, tt: po.prior_forward(sd, cfg, xx, tt, fx["text_emb"], fx["text_enc"], fx["mask"]),
+                            fx["x_T"], fx["step_noise"], fx["use_steps"], fx["guidance"], fx["clip_mean"], fx["clip_std"])
+    assert (y - fx["out"]).abs().max().item() <= 1e-5
+    assert (s - fx["sample"]).abs().max().item() <= 1e-4
+    # full-size parameter count of the 2.1 prior (20 layers, width 2048)
+    n = sum(int(np.prod(shape)) for _, shape in po.prior_param_spec(po.CONFIG_PRIOR))
+    assert 1.0e9 < n < 1.1e9, n
