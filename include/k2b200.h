@@ -203,6 +203,21 @@ int k2_nchw_to_nhwc_f32(const float* x, float* y, int NB, int C, int H, int W, k
 int k2_images_to_u8(const float* x_nchw, uint8_t* out_nhwc, int NB, int C, int H, int W, int crop_h,
                     int crop_w, k2_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Diffusion prior (kandinsky2/model/prior.py:46-127) -- GROUNDWORK: compiled, not yet validated on a
+ * GPU, not on the measured path.  The transformer's Linear layers are k2_conv_gemm flat-row GEMMs; these are the rest:
+ *   k2_layernorm_f16   LayerNorm over the last dim of fp16 rows, fp32 statistics / gain / bias (prior.py:46-53)
+ *   k2_gelu_f16        nn.GELU (exact erf) on n fp16 elements, may run in place (prior.py:74-83)
+ *   k2_attention_small QKVMultiheadAttention for T <= 128 tokens, head dim 64 (prior.py:86-103): qkv rows
+ *                      [B, T, >= heads*192] with per-head [q | k | v]; additive mask = causal (if set) AND key keep-mask
+ *                      (uint8 [B, T], may be NULL); fp32 softmax; out rows [B, T, >= heads*64].
+ * ------------------------------------------------------------------------------------------- */
+int k2_layernorm_f16(const void* x, int ldx, const float* gamma, const float* beta, void* y, int ldy, int M, int N, float eps,
+                     k2_stream_t stream);
+int k2_gelu_f16(const void* x, void* y, long long n, k2_stream_t stream);
+int k2_attention_small(const void* qkv, int ldq, const unsigned char* keep_mask, int causal, void* out, int ldo, int B, int T,
+                       int heads, float scale, k2_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

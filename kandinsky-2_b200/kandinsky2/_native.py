@@ -39,6 +39,9 @@ SIGNATURES = {
     "k2_upsample2x_nhwc": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _P]),
     "k2_subsample2_nhwc": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "k2_softmax_rows": (_I, [_P, _I, _P, _I, _LL, _I, _F, _P]),
+    "k2_layernorm_f16": (_I, [_P, _I, _P, _P, _P, _I, _I, _I, _F, _P]),
+    "k2_gelu_f16": (_I, [_P, _P, _LL, _P]),
+    "k2_attention_small": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _F, _P]),
     "k2_conv_plan": (_I, [_I, _I, _I, _I, _I, _I, _I, _LL, _I, _P]),
     "k2_gn_scratch_floats": (_LL, [_I, _I, _I]),
     "k2_gn_stats": (_I, [_P, _I, _I, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P]),

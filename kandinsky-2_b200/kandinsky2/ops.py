@@ -395,3 +395,38 @@ def launch_count():
 
 def reset_launch_count():
     nat.load().k2_reset_launch_count()
+
+
+# ------------------------------------------------------------------------------------------------
+# diffusion prior helpers (groundwork, see k2b200.h)
+# ------------------------------------------------------------------------------------------------
+def layernorm_f16(x, gamma, beta, eps=1e-5, out=None):
+    """LayerNorm over the last dim of fp16 rows [..., N] (fp32 gain / bias) -> fp16."""
+    lib = nat.load()
+    N = x.shape[-1]
+    M = x.numel() // N
+    assert x.dtype == torch.float16 and x.stride(-1) == 1
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib.k2_layernorm_f16(ptr(x), _row_stride(x), ptr(gamma), ptr(beta), ptr(out), _row_stride(out), M, N, eps,
+                               stream_ptr()))
+    return out
+
+
+def gelu_f16_(x):
+    """Exact GELU in place on a contiguous fp16 tensor."""
+    lib = nat.load()
+    assert x.dtype == torch.float16 and x.is_contiguous()
+    check(lib.k2_gelu_f16(ptr(x), ptr(x), x.numel(), stream_ptr()))
+    return x
+
+
+def attention_small(qkv, heads, keep_mask=None, causal=True, scale=0.125, out=None):
+    """qkv fp16 [B, T, heads*192] (per head [q|k|v]), keep_mask uint8 [B, T] or None -> fp16 [B, T, heads*64]; T <= 128."""
+    lib = nat.load()
+    B, T = qkv.shape[:2]
+    if out is None:
+        out = torch.empty((B, T, heads * 64), dtype=torch.float16, device=qkv.device)
+    check(lib.k2_attention_small(ptr(qkv), _row_stride(qkv), ptr(keep_mask), int(causal), ptr(out), _row_stride(out), B, T,
+                                 heads, scale, stream_ptr()))
+    return out

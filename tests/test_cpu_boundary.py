@@ -137,3 +137,13 @@ def test_diffusers_key_remap_roundtrip_and_head_interleave():
     for got, w in ((q, wq), (k, wk), (v, wv)):
         ref = torch.einsum("oc,bct->bot", w, x).reshape(3 * heads, 64, T)
         assert torch.allclose(got, ref, atol=1e-5)
+
+
+def test_prior_state_dict_keys_match_reference_spec():
+    """The prior groundwork module keeps the reference's parameter names and shapes (prior.py:191-228), i.e. the key set the
+    oracle spec was checked against when tests/golden/prior_tiny.pt was written from the reference's own classes."""
+    from kandinsky2.model.prior import PriorTransformer
+    from oracle import prior_oracle as po
+    for cfg in (po.CONFIG_PRIOR_TINY, dict(po.CONFIG_PRIOR, xf_layers=2)):
+        m = PriorTransformer(**cfg)
+        assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == [(k, tuple(s)) for k, s in po.prior_param_spec(cfg)]
