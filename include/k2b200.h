@@ -204,8 +204,8 @@ int k2_images_to_u8(const float* x_nchw, uint8_t* out_nhwc, int NB, int C, int H
                     int crop_w, k2_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Diffusion prior (kandinsky2/model/prior.py:46-127) -- GROUNDWORK: compiled, not yet validated on a
- * GPU, not on the measured path.  The transformer's Linear layers are k2_conv_gemm flat-row GEMMs; these are the rest:
+ * Diffusion prior (kandinsky2/model/prior.py:46-127), not on the measured denoising path and not
+ * tuned.  The transformer's Linear layers are k2_conv_gemm flat-row GEMMs; these are the rest:
  *   k2_layernorm_f16   LayerNorm over the last dim of fp16 rows, fp32 statistics / gain / bias (prior.py:46-53)
  *   k2_gelu_f16        nn.GELU (exact erf) on n fp16 elements, may run in place (prior.py:74-83)
  *   k2_attention_small QKVMultiheadAttention for T <= 128 tokens, head dim 64 (prior.py:86-103): qkv rows

@@ -2,8 +2,8 @@
 // on top of the GEMM (k2_conv_gemm as a flat-row GEMM): LayerNorm on fp16 rows, exact GELU, and a masked multi-head
 // attention over a SHORT sequence (81 tokens, head dim 64).
 //
-// STATUS (end of round 1): compiled, NOT yet validated on a GPU -- nothing on the measured path calls these entry points;
-// their parity tests (tests/test_gpu_zz_prior.py, against tests/golden/prior_tiny.pt) are opt-in (K2_TEST_PRIOR=1).
+// Parity: tests/test_gpu_zz_prior.py (each kernel against torch fp32, the whole prior against tests/golden/prior_tiny.pt = the
+// reference's own classes).  Nothing on the measured denoising path calls these entry points; they are not tuned.
 #include <math.h>
 
 #include "../../include/k2b200.h"

@@ -1,8 +1,9 @@
-"""Diffusion prior of Kandinsky 2.1 (reference: kandinsky2/model/prior.py) -- GROUNDWORK.
+"""Diffusion prior of Kandinsky 2.1 (reference: kandinsky2/model/prior.py) -- SURVEY.md 8f rank 3.
 
-STATUS at the end of round 1: written against the oracle (oracle/prior_oracle.py, pinned to the reference's own classes by
-tests/golden/prior_tiny.pt) but NOT yet run on a GPU; its parity tests are opt-in (tests/test_gpu_zz_prior.py, K2_TEST_PRIOR=1)
-and nothing on the measured path imports this module.
+Parity: tests/test_gpu_zz_prior.py compares the transformer forward and the guided x0-prediction sampling loop with the
+outputs of the reference's own PriorTransformer / PriorDiffusionModel classes (tests/golden/prior_tiny.pt; the oracle,
+oracle/prior_oracle.py, reproduces them exactly).  Not yet wired into the pipelines (they take synthetic / user-supplied
+image embeddings) and not benchmarked.
 
 `PriorTransformer` keeps the reference's parameter names (prior.py:191-228), so `prior_fp16.ckpt` state dicts load as they
 are.  Compute: the Linear layers are flat-row tcgen05 GEMMs (`ops.gemm_rows`, fp16 storage / fp32 accumulate, bias and
