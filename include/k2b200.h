@@ -117,6 +117,14 @@ int k2_gn_apply(const void* src0, int C0, int ld0, const void* src1, int C1, int
                 int groups, const float* stats, const float* gamma, const float* beta, const float* film,
                 int film_ld, int act, int resample, void* y, int ldy, void* xres, int ldx, const float* zq, int zh,
                 int zw, const float* sn_w, k2_stream_t stream);
+/* k2_gn_apply with the statistics pass folded in: instead of `stats` the producers' partial sums (the part0 / rg0 / part1 / rg1
+ * / eps arguments of k2_gn_finalize) are given and every block derives mean / rstd of the groups it touches itself -- one
+ * launch less per GroupNorm where an image has few row groups.  No SpatialNorm inputs.  NOT YET VALIDATED ON A GPU (added at
+ * the end of round 1 for round 2; the kernels k2_gn_apply launches are bit-for-bit the ones that were validated). */
+int k2_gn_apply_fold(const void* src0, int C0, int ld0, const void* src1, int C1, int ld1, int NB, int H, int W, int groups,
+                     const float* part0, int rg0, const float* part1, int rg1, float eps, const float* gamma,
+                     const float* beta, const float* film, int film_ld, int act, int resample, void* y, int ldy, void* xres,
+                     int ldx, k2_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Attention, head dim 64, online softmax, on tcgen05 (QK^T and PV) with encoder K/V prepended.

@@ -273,10 +273,19 @@ struct ApplyParams {
   int zh, zw;
   const float* sn_w;  // [C, 10]
   int chunk;          // work pixels per block
+  // FOLD variant only (appended: the layout of everything above is what the validated kernels read)
+  const float2* part0;  // producer partials [n][rg0][C0] (sum, sumsq), as for k2_gn_finalize
+  const float2* part1;  // second source's partials [n][rg1][C1] or null
+  int rg0, rg1;
+  float eps;
 };
 
 // RESAMPLE 0: same size; 1: 2x2 average pool (work items = output pixels); 2: nearest 2x (work = input pixels)
-template <int RESAMPLE, bool SPATIAL>
+// FOLD: the block derives mean / rstd of the groups it touches from the producers' partial sums itself (the work of
+// k2_gn_finalize, redone per block: worthwhile where an image has few row groups -- levels 1-3 of the U with one partial per
+// conv M tile -- because it removes a launch per GroupNorm).  Same fold as gn_finalize_kernel, warp-wide instead of block-wide.
+constexpr int FOLD_MAXG = 34;  // groups one block of 128 channels can touch: 128 / 4 + 2
+template <int RESAMPLE, bool SPATIAL, bool FOLD = false>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const ApplyParams p) {
   const int C = p.C0 + p.C1;
   const int CV = C / 8;
@@ -286,6 +295,47 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const ApplyParams p) {
   const int n = blockIdx.z;
   pdl_wait();
   pdl_launch();
+  __shared__ float2 s_fold[FOLD ? FOLD_MAXG : 1];
+  int g_lo = 0;
+  if constexpr (FOLD) {
+    const int cpg = C / p.groups;
+    const int c_lo = blockIdx.y * VX * 8;
+    const int c_hi = min(C, c_lo + VX * 8);
+    g_lo = c_lo / cpg;
+    const int g_hi = (c_hi - 1) / cpg;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int g = g_lo + warp; g <= g_hi; g += 8) {
+      float fs = 0.f, fq = 0.f;
+      auto fold = [&](const float2* part, int Cs, int base, int rgs) {
+        const int lo = max(g * cpg, base), hi = min((g + 1) * cpg, base + Cs);
+        const int w = hi - lo;
+        if (w <= 0) return;
+        const float2* p0 = part + static_cast<long long>(n) * rgs * Cs + (lo - base);
+        for (int i = lane; i < rgs * w; i += 32) {
+          const int rg = i / w;
+          const float2 t = __ldg(p0 + static_cast<long long>(rg) * Cs + (i - rg * w));
+          fs += t.x;
+          fq += t.y;
+        }
+      };
+      fold(p.part0, p.C0, 0, p.rg0);
+      if (p.C1 > 0) fold(p.part1, p.C1, p.C0, p.rg1);
+      double s = fs, q = fq;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_down_sync(0xffffffffu, s, o);
+        q += __shfl_down_sync(0xffffffffu, q, o);
+      }
+      if (lane == 0) {
+        const double cnt = static_cast<double>(p.H) * p.W * cpg;
+        const double mean = s / cnt;
+        double var = q / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_fold[g - g_lo] = make_float2(static_cast<float>(mean), static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.eps))));
+      }
+    }
+    __syncthreads();
+  }
   if (v >= CV) return;
   const int c0 = v * 8;
   const int Hw = (RESAMPLE == 1) ? p.H / 2 : p.H;
@@ -302,7 +352,12 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const ApplyParams p) {
     for (int e = 0; e < 8; ++e) {
       const int c = c0 + e;
       const int g = c / cpg;
-      const float2 st = __ldg(reinterpret_cast<const float2*>(p.stats + (static_cast<long long>(n) * p.groups + g) * 2));
+      float2 st;
+      if constexpr (FOLD) {
+        st = s_fold[g - g_lo];
+      } else {
+        st = __ldg(reinterpret_cast<const float2*>(p.stats + (static_cast<long long>(n) * p.groups + g) * 2));
+      }
       float ga = __ldg(p.gamma + c) * st.y;
       float be = __ldg(p.beta + c) - st.x * ga;
       if (p.film) {
@@ -509,6 +564,7 @@ int k2_gn_apply(const void* src0, int C0, int ld0, const void* src1, int C1, int
   p.y = reinterpret_cast<__half*>(y); p.ldy = ldy;
   p.xres = reinterpret_cast<__half*>(xres); p.ldx = ldx;
   p.zq = zq; p.zh = zh; p.zw = zw; p.sn_w = sn_w;
+  p.part0 = nullptr; p.part1 = nullptr; p.rg0 = 0; p.rg1 = 0; p.eps = 0.f;  // FOLD variant only
   const int Hw = (resample == 1) ? H / 2 : H;
   const int Ww = (resample == 1) ? W / 2 : W;
   const int ctiles = (C / 8 + VX - 1) / VX;
@@ -526,6 +582,45 @@ int k2_gn_apply(const void* src0, int C0, int ld0, const void* src1, int C1, int
     if (sp) K2_CHECK_CUDA(launch_k(gn_apply_kernel<2, true>, grid, dim3(256), 0, st, p));
     else K2_CHECK_CUDA(launch_k(gn_apply_kernel<2, false>, grid, dim3(256), 0, st, p));
   }
+  K2_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// Round-2 candidate (not yet run on a GPU): same launch as k2_gn_apply, statistics folded from the producers' partials inside
+// the kernel.  Kept as a separate entry point so that the validated k2_gn_apply path above is textually what was tested.
+int k2_gn_apply_fold(const void* src0, int C0, int ld0, const void* src1, int C1, int ld1, int NB, int H, int W, int groups,
+                     const float* part0, int rg0, const float* part1, int rg1, float eps, const float* gamma,
+                     const float* beta, const float* film, int film_ld, int act, int resample, void* y, int ldy, void* xres,
+                     int ldx, k2_stream_t stream) {
+  const int C = C0 + C1;
+  K2_REQUIRE(src0 && y && gamma && beta, "gn_apply_fold: null pointer");
+  K2_REQUIRE(C0 % 8 == 0 && C1 % 8 == 0 && C % groups == 0 && C / groups >= 4, "gn_apply_fold: bad channel counts");
+  K2_REQUIRE(resample >= 0 && resample <= 2, "gn_apply_fold: resample in {0,1,2}");
+  K2_REQUIRE(resample != 1 || (H % 2 == 0 && W % 2 == 0), "gn_apply_fold: avg-pool needs even H, W");
+  K2_REQUIRE(part0 && rg0 > 0 && (C1 == 0 || (src1 && part1 && rg1 > 0)), "gn_apply_fold: partial buffers");
+  ApplyParams p;
+  p.s0 = reinterpret_cast<const __half*>(src0);
+  p.s1 = reinterpret_cast<const __half*>(src1);
+  p.C0 = C0; p.ld0 = ld0; p.C1 = C1; p.ld1 = ld1;
+  p.NB = NB; p.H = H; p.W = W; p.groups = groups;
+  p.stats = nullptr; p.gamma = gamma; p.beta = beta; p.film = film; p.film_ld = film_ld;
+  p.act = act;
+  p.y = reinterpret_cast<__half*>(y); p.ldy = ldy;
+  p.xres = reinterpret_cast<__half*>(xres); p.ldx = ldx;
+  p.zq = nullptr; p.zh = 0; p.zw = 0; p.sn_w = nullptr;
+  p.part0 = reinterpret_cast<const float2*>(part0);
+  p.part1 = reinterpret_cast<const float2*>(part1);
+  p.rg0 = rg0; p.rg1 = rg1; p.eps = eps;
+  const int Hw = (resample == 1) ? H / 2 : H;
+  const int Ww = (resample == 1) ? W / 2 : W;
+  const int ctiles = (C / 8 + VX - 1) / VX;
+  p.chunk = pick_chunk(Hw * Ww, ctiles, NB);
+  dim3 grid((Hw * Ww + p.chunk - 1) / p.chunk, ctiles, NB);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (resample == 0) K2_CHECK_CUDA(launch_k(gn_apply_kernel<0, false, true>, grid, dim3(256), 0, st, p));
+  else if (resample == 1) K2_CHECK_CUDA(launch_k(gn_apply_kernel<1, false, true>, grid, dim3(256), 0, st, p));
+  else K2_CHECK_CUDA(launch_k(gn_apply_kernel<2, false, true>, grid, dim3(256), 0, st, p));
   K2_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;

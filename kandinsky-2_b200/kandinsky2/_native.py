@@ -47,6 +47,8 @@ SIGNATURES = {
     "k2_gn_stats": (_I, [_P, _I, _I, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P]),
     "k2_gn_apply": (_I, [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _I, _P, _I, _P, _I, _P,
                          _I, _I, _P, _P]),
+    "k2_gn_apply_fold": (_I, [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _F, _P, _P, _P, _I, _I, _I, _P, _I, _P,
+                              _I, _P]),
     "k2_attention_d64": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P, _I, _P]),
     "k2_linear": (_I, [_P, _I, _P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P]),
     "k2_layernorm": (_I, [_P, _P, _P, _P, _I, _I, _F, _P]),

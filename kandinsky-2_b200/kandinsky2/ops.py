@@ -210,6 +210,23 @@ def gn_apply(x0, x1, stats, gamma, beta, film=None, act=1, resample=0, groups=32
     return (y, xres) if want_xres else y
 
 
+def gn_apply_fold(x0, x1, part0, rg0, part1, rg1, gamma, beta, film=None, act=1, resample=0, groups=32, eps=1e-5, y=None,
+                  xres=None):
+    """gn_apply that folds the producers' partial sums itself (no gn_finalize launch); round-2 candidate, see k2b200.h."""
+    lib = nat.load()
+    NB, H, W, C0 = x0.shape
+    C1 = x1.shape[-1] if x1 is not None else 0
+    Ho, Wo = (H, W) if resample == 0 else ((H // 2, W // 2) if resample == 1 else (H * 2, W * 2))
+    if y is None:
+        y = torch.empty((NB, Ho, Wo, C0 + C1), dtype=torch.float16, device=x0.device)
+    check(lib.k2_gn_apply_fold(ptr(x0), C0, _row_stride(x0), ptr(x1), C1, _row_stride(x1) if x1 is not None else 0,
+                               NB, H, W, groups, ptr(part0), rg0, ptr(part1), rg1 if part1 is not None else 0, eps,
+                               ptr(gamma), ptr(beta), ptr(film), film.stride(0) if film is not None else 0, act, resample,
+                               ptr(y), _row_stride(y), ptr(xres), _row_stride(xres) if xres is not None else 0,
+                               stream_ptr()))
+    return y
+
+
 # ------------------------------------------------------------------------------------------------
 # attention
 # ------------------------------------------------------------------------------------------------
