@@ -39,7 +39,9 @@ void k2_reset_launch_count(void);
  * key 6 = eighths (0, 2, 3, 4) of the softmax exponentials evaluated on the FMA pipe instead of MUFU (1xx = ablations,
  * 2xx = traced variants); keys 7 / 8 = low / high 32 bits of a device buffer (384 x u64) that the traced attention
  * variants fill with clock64 stamps of CTA (0,0,0) -- diagnostics only, see profiles/attn_trace.py; key 9 = order of the
- * attention MMA issuer (0 fixed per key block, 1 event driven; default from the environment variable K2_ATTN_ISSUE, else 0). */
+ * attention MMA issuer (0 fixed per key block, 1 event driven; default from the environment variable K2_ATTN_ISSUE, else 0);
+ * key 10 = epilogue warp sets of the CTA-pair conv kernel (1 = validated; 2 = 384-thread variant whose second set drains the
+ * other half of the 64-column pairs -- round-2 candidate, NOT yet validated on a GPU). */
 int k2_set_tuning(int key, int value);
 
 /* ---------------------------------------------------------------------------------------------

@@ -32,6 +32,8 @@ int fail(const std::string& msg) {
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 bool pdl_enabled() { return g_pdl != 0; }
+static int g_conv_epi_sets = 1;
+int conv_epilogue_sets() { return g_conv_epi_sets; }
 int attention_stagger() { return g_attn_stagger; }
 int attention_poly_mode() { return g_attn_poly; }
 static int g_attn_issue = -1;  // -1: take K2_ATTN_ISSUE from the environment at first use (default 0)
@@ -304,6 +306,10 @@ int k2_set_tuning(int key, int value) {
   }
   if (key == 6) {
     g_attn_poly = value;
+    return 0;
+  }
+  if (key == 10) {  // epilogue warp sets of the CTA-pair conv kernel: 1 (validated) or 2 (round-2 candidate)
+    g_conv_epi_sets = (value == 2) ? 2 : 1;
     return 0;
   }
   if (key == 9) {  // attention MMA issue order: 0 fixed, 1 event driven

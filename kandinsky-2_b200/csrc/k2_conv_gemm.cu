@@ -68,9 +68,14 @@ __device__ __forceinline__ void decode_m_tile(const ConvGemmParams& p, int m_idx
 // per store instruction; the residual comes in the same way (coalesced load -> smem -> own row), the bias is read as
 // broadcast LDS.128 from a per-warp copy, and the fused GroupNorm statistics are column sums over the staged fp16 tile.
 
-template <int BN>
+// ES = number of epilogue warp SETS (each set = 4 warps covering the 4 TMEM lane quarters).  ES = 1 is the validated
+// configuration; with ES = 2 (384-thread variant of the CTA-pair kernel, tuning key 10, round-2 candidate) set `es` handles
+// the 64-column pairs jp with jp % 2 == es, so two warps per scheduler drain the accumulator.
+template <int BN, int ES = 1>
 __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t tmem_base, int acc_col, int ew, int lane,
-                                              int n0, int y0, int x0, int n_idx, int split, int m_idx, float* stat_smem) {
+                                              int n0, int y0, int x0, int n_idx, int split, int m_idx, float* stat_smem,
+                                              int es_arg = 0) {
+  const int es = (ES == 1) ? 0 : es_arg;
   const int row = ew * 32 + lane;
   const int thw = p.TH * p.TW;
   constexpr int CH = (BN >= 32) ? 32 : 16;  // columns per tcgen05.ld
@@ -83,8 +88,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t 
       const long long out_row = (static_cast<long long>(n) * p.H + y) * p.W + x;
       if constexpr (BN % 64 == 0) {
         if ((p.out_mode == 0 && p.Cout % 64 == 0) || (p.out_mode == 2 && p.Cout % 32 == 0)) {
-          const uint32_t stage = smem_u32(stat_smem + ew * EPI_STAGE_FLOATS);  // [32 rows][8 x 16 B], piece ^= row & 7
-          float* bsm = stat_smem + 4 * EPI_STAGE_FLOATS + ew * 256;
+          const uint32_t stage = smem_u32(stat_smem + (es * 4 + ew) * EPI_STAGE_FLOATS);  // [32 rows][8 x 16 B], piece ^= row & 7
+          float* bsm = stat_smem + 4 * ES * EPI_STAGE_FLOATS + (es * 4 + ew) * 256;
           const int my_pix = valid ? static_cast<int>(out_row) : -1;
           const int sub = lane >> 3, piece = lane & 7;
           int pix[8];  // pixel (output row) of the 8 staged rows this lane copies out: rows i*4 + sub
@@ -99,6 +104,9 @@ __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t 
             for (int j = 0; j < BN / 32; ++j) {
               const int col0 = n_idx * BN + j * 32;
               if (col0 >= p.Cout) break;
+              if constexpr (ES > 1) {
+                if ((j % ES) != es) continue;
+              }
               uint32_t r[32];
               tmem_ld_32x32b_x32(taddr0 + j * 32, r);
               tmem_ld_wait();
@@ -135,12 +143,17 @@ __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t 
                 rpre[i] = *reinterpret_cast<const uint4*>(p.residual + static_cast<long long>(pix[i]) * p.ldr + c0 + piece * 8);
             }
           };
-          if (p.residual) load_res(0);
+          if constexpr (ES == 1) {
+            if (p.residual) load_res(0);
+          }
 #pragma unroll
           for (int jp = 0; jp < NP; ++jp) {
             const int col0 = n_idx * BN + jp * 64;
             st[jp] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (col0 < p.Cout) {
+            if (col0 < p.Cout && (ES == 1 || (jp % ES) == es)) {
+              if constexpr (ES > 1) {
+                if (p.residual) load_res(jp);  // no prefetch registers: the second warp set hides the latency instead
+              }
               if (p.residual) {  // coalesced: 8 lanes x 16 B per row, 4 rows per instruction -> staged by row
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -155,7 +168,9 @@ __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t 
                 uint32_t(&r1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[32]);
                 tmem_ld_32x32b_x32(taddr0 + jp * 64, r0);
                 tmem_ld_32x32b_x32(taddr0 + jp * 64 + 32, r1);
-                if (p.residual && jp + 1 < NP) load_res(jp + 1);
+                if constexpr (ES == 1) {
+                  if (p.residual && jp + 1 < NP) load_res(jp + 1);
+                }
                 tmem_ld_wait();
               }
 #pragma unroll
@@ -228,23 +243,46 @@ __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t 
           if (p.gn_part && p.gn_mode == 1) {
             // one partial per (M tile, column): the four warps' sums are folded in a fixed order through the (now idle)
             // staging buffers, so k2_gn_finalize reads a quarter of what per-warp partials would cost
-            float4* mine = reinterpret_cast<float4*>(stat_smem + ew * EPI_STAGE_FLOATS);
+            if constexpr (ES == 1) {
+              float4* mine = reinterpret_cast<float4*>(stat_smem + ew * EPI_STAGE_FLOATS);
 #pragma unroll
-            for (int jp = 0; jp < NP; ++jp) mine[jp * 32 + lane] = st[jp];
-            named_bar_sync(1, 128);
-            if (ew < NP) {
-              const int col0 = n_idx * BN + ew * 64;
-              if (col0 < p.Cout) {
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+              for (int jp = 0; jp < NP; ++jp) mine[jp * 32 + lane] = st[jp];
+              named_bar_sync(1, 128);
+              if (ew < NP) {
+                const int col0 = n_idx * BN + ew * 64;
+                if (col0 < p.Cout) {
+                  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                  const float4 t = reinterpret_cast<const float4*>(stat_smem + w * EPI_STAGE_FLOATS)[ew * 32 + lane];
-                  acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+                  for (int w = 0; w < 4; ++w) {
+                    const float4 t = reinterpret_cast<const float4*>(stat_smem + w * EPI_STAGE_FLOATS)[ew * 32 + lane];
+                    acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+                  }
+                  *reinterpret_cast<float4*>(p.gn_part + static_cast<long long>(m_idx) * p.Cout + col0 + 2 * lane) = acc;
                 }
-                *reinterpret_cast<float4*>(p.gn_part + static_cast<long long>(m_idx) * p.Cout + col0 + 2 * lane) = acc;
               }
+              named_bar_sync(1, 128);
+            } else {
+              // each warp set folds the pairs it owns (jp % ES == es) among its own four warps: barrier 1 + es
+              float4* mine = reinterpret_cast<float4*>(stat_smem + (es * 4 + ew) * EPI_STAGE_FLOATS);
+#pragma unroll
+              for (int jp = 0; jp < NP; ++jp) mine[jp * 32 + lane] = st[jp];
+              named_bar_sync(1 + es, 128);
+              const int jp_f = es + ew * ES;  // warp ew of the set folds the set's ew-th pair
+              if (jp_f < NP) {
+                const int col0 = n_idx * BN + jp_f * 64;
+                if (col0 < p.Cout) {
+                  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                  for (int w = 0; w < 4; ++w) {
+                    const float4 t =
+                        reinterpret_cast<const float4*>(stat_smem + (es * 4 + w) * EPI_STAGE_FLOATS)[jp_f * 32 + lane];
+                    acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+                  }
+                  *reinterpret_cast<float4*>(p.gn_part + static_cast<long long>(m_idx) * p.Cout + col0 + 2 * lane) = acc;
+                }
+              }
+              named_bar_sync(1 + es, 128);
             }
-            named_bar_sync(1, 128);
           }
           return;
         }
@@ -496,19 +534,21 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
 // MMA commit multicasts the "stage free" / "accumulator ready" arrivals to both CTAs; the peer's epilogue warps arrive
 // remotely on the leader's "accumulator drained" barrier.
 // ------------------------------------------------------------------------------------------------
-template <int BN>
+template <int BN, int ES = 1>
 struct Cfg2 {
   static constexpr int B_STAGE_BYTES = (BN / 2) * BK * 2;   // this CTA's half of the weight tile
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (BN >= 256) ? 6 : (BN >= 192 ? 7 : 8);
+  // the second epilogue warp set's staging / bias buffers (another EPI_BYTES) cost one pipeline stage
+  static constexpr int STAGES = ((BN >= 256) ? 6 : (BN >= 192 ? 7 : 8)) - (ES - 1);
   static constexpr int TMEM_COLS = 512;                      // 2 accumulator buffers at columns 0 and 256
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + EPI_BYTES + 1024;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + ES * EPI_BYTES + 1024;
+  static constexpr int THREADS = 128 + 128 * ES;             // 4 control warps + ES sets of 4 epilogue warps
 };
 
-template <int BN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+template <int BN, int ES = 1>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 128 * ES, 1)
 conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p) {
-  using C = Cfg2<BN>;
+  using C = Cfg2<BN, ES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -537,7 +577,7 @@ conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 8);  // 4 epilogue warps x 2 CTAs (only the leader's copy is waited on)
+      mbar_init(&tmem_empty[i], 8 * ES);  // 4 epilogue warps per set x 2 CTAs (only the leader's copy is waited on)
     }
     fence_barrier_init();
   }
@@ -637,7 +677,8 @@ conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p) {
     }
   } else if (warp_idx >= 4) {
     // ===================================== epilogue (both CTAs, own TMEM) ====================
-    const int ew = warp_idx - 4;
+    const int ew = (ES == 1) ? warp_idx - 4 : (warp_idx & 3);  // TMEM lane quarter
+    const int es = (ES == 1) ? 0 : ((warp_idx - 4) >> 2);       // epilogue warp set
     int acc = 0;
     uint32_t acc_phase = 0;
     const uint32_t leader_empty0 = mapa_u32(smem_u32(&tmem_empty[0]), 0);
@@ -650,7 +691,7 @@ conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p) {
       decode_m_tile(p, m_idx, n0, y0, x0);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      epilogue_tile<BN>(p, tmem_base, acc * 256, ew, lane, n0, y0, x0, n_idx, split, m_idx, stat_smem);
+      epilogue_tile<BN, ES>(p, tmem_base, acc * 256, ew, lane, n0, y0, x0, n_idx, split, m_idx, stat_smem, es);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(acc ? leader_empty1 : leader_empty0);
@@ -680,6 +721,23 @@ int launch_bn2(const ConvGemmParams& p, cudaStream_t stream) {
   const int max_pairs = num_sms() / 2;
   const int pairs = total < max_pairs ? total : max_pairs;
   K2_CHECK_CUDA(launch_k(conv_gemm2_kernel<BN>, dim3(2 * pairs), dim3(256), C::SMEM_BYTES, stream, p));
+  return 0;
+}
+
+// CTA-pair kernel with two epilogue warp sets (384 threads, one pipeline stage fewer): NOT YET VALIDATED ON A GPU.
+template <int BN>
+int launch_bn2e(const ConvGemmParams& p, cudaStream_t stream) {
+  using C = Cfg2<BN, 2>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    K2_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm2_kernel<BN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int m_pairs = (p.m_tiles + 1) / 2;
+  const int total = m_pairs * p.n_tiles * p.splits;
+  const int max_pairs = num_sms() / 2;
+  const int pairs = total < max_pairs ? total : max_pairs;
+  K2_CHECK_CUDA(launch_k(conv_gemm2_kernel<BN, 2>, dim3(2 * pairs), dim3(C::THREADS), C::SMEM_BYTES, stream, p));
   return 0;
 }
 
@@ -1015,6 +1073,14 @@ int launch_conv_gemm(const ConvGemmParams& p, int BN, cudaStream_t stream) {
       case 192: return launch_bn3<192>(p, stream);
       case 256: return launch_bn3<256>(p, stream);
       default: return fail("conv_gemm: unsupported BN for the halo kernel");
+    }
+  }
+  if (p.two_cta && conv_epilogue_sets() == 2) {  // round-2 candidate (tuning key 10): two epilogue warp sets
+    switch (BN) {
+      case 128: return launch_bn2e<128>(p, stream);
+      case 192: return launch_bn2e<192>(p, stream);
+      case 256: return launch_bn2e<256>(p, stream);
+      default: return fail("conv_gemm: unsupported BN for the 2-CTA kernel");
     }
   }
   if (p.two_cta) {

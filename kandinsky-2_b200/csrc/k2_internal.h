@@ -96,6 +96,7 @@ struct AttnParams {
   unsigned long long* trace;  // diagnostics: 3 x 16 x 8 clock64 stamps of CTA (0,0,0), or null
   int issue_mode;      // MMA issuer: 0 = fixed program order per key block, 1 = event driven (polls both query tiles)
 };
+int conv_epilogue_sets();  // 1 (validated) or 2 (tuning key 10, round-2 candidate)
 int attention_stagger();
 unsigned long long* attention_trace_buffer();
 int attention_issue_mode();
