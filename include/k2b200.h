@@ -40,8 +40,9 @@ void k2_reset_launch_count(void);
  * 2xx = traced variants); keys 7 / 8 = low / high 32 bits of a device buffer (384 x u64) that the traced attention
  * variants fill with clock64 stamps of CTA (0,0,0) -- diagnostics only, see profiles/attn_trace.py; key 9 = order of the
  * attention MMA issuer (0 fixed per key block, 1 event driven; default from the environment variable K2_ATTN_ISSUE, else 0);
- * key 10 = epilogue warp sets of the CTA-pair conv kernel (1 = validated; 2 = 384-thread variant whose second set drains the
- * other half of the 64-column pairs -- round-2 candidate, NOT yet validated on a GPU). */
+ * key 10 = default number of epilogue warp sets of the CTA-pair conv kernel (1; 2 = 384-thread variant whose second set drains
+ * the other half of the 64-column pairs: bit-identical results, faster where the K loop is short).  Keys 0, 1, 2 and 10 are
+ * process-wide defaults; k2_conv_gemm_cfg overrides them per call. */
 int k2_set_tuning(int key, int value);
 
 /* ---------------------------------------------------------------------------------------------
@@ -70,19 +71,38 @@ int k2_set_tuning(int key, int value);
  * (k2_gn_scratch_floats); info[5] / info[6] tell what was written.
  * info (HOST pointer, may be NULL): int[7] = {N tile, CTA-pair mode, split-K factor, M tiles, images per tile,
  * gn_partial written (0 no / 1 epilogue / 2 split-K pass), row groups written in total}.
+ * taps = 4 (allowed for a single source, fp16 output, no residual, H and W even): the source is [NB, H/2, W/2, C] and the call
+ * computes the 3x3 convolution over its NEAREST-2x UPSAMPLING (unet.py:67-77 + :199-203; movq_modules.py:93-97) without
+ * materialising it: output pixel (2y+a, 2x+b) = a 2x2 convolution of the source around (y, x) with the kernel rows / columns
+ * that fall on the same source pixel pre-summed by the host (2.25x fewer MACs).  Wp = fp16 [Cout][16 * pad64(C)],
+ * k = ((a*2+b)*4 + ty*2+tx) * pad64(C) + c, source offset (ty+a-1, tx+b-1); Ktot = 16 * pad64(C).
  * A plain GEMM [M,K]x[K,N] is the call with NB=1, H=1, W=M, one source with taps=1.
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
   const void* ptr; /* fp16, NHWC; may point at a channel offset inside a wider buffer */
   int C;           /* channels of this source (multiple of 8) */
   int ld;          /* row stride in elements */
-  int taps;        /* 9 or 1 */
+  int taps;        /* 9, 1, or 4 (3x3 over the nearest-2x upsampled source, see above) */
 } K2ConvSrc;
 
 int k2_conv_gemm(const K2ConvSrc* srcs, int nsrc, int NB, int H, int W, const void* w_packed, int w_rows,
                  int Ktot, int ldw, int Cout, const float* bias, const void* residual, int ldr, void* out, int ldo,
                  int out_mode, void* workspace, long long workspace_bytes, float* gn_partial, int* info,
                  k2_stream_t stream);
+
+/* k2_conv_gemm with the launch configuration chosen by the caller instead of the library's cycle model:
+ * cfg (HOST pointer, may be NULL = k2_conv_gemm) = int[4] {N tile (16/64/128/192/256), CTA-pair kernel (1 off, 2 on),
+ * split-K factor (1 = off), epilogue warp sets of the CTA-pair kernel (1 or 2)}; a 0 entry keeps the automatic choice.
+ * N tile, pair mode and epilogue sets never change a result bit (same K order per output element); the split factor does.
+ * The UNet / MoVQ launch plans time the candidates once per distinct layer shape and bake the winner into their CUDA graph.
+ * w_batch_stride (elements, multiple of 8; 0 = one weight matrix): > 0 makes the call a BATCHED GEMM -- image n of the NB
+ * images multiplies Wp + n * w_batch_stride.  This is how the MoVQ AttnBlock (movq_modules.py:201-225) runs without a loop
+ * over images: scores[n] = q[n] k[n]^T with the k rows of image n as "weights" (w_rows = T, ldw = row stride of the qkv
+ * buffer), out[n] = P[n] v[n] with v[n]^T as "weights".  Tiles then never span two images; no split-K. */
+int k2_conv_gemm_cfg(const K2ConvSrc* srcs, int nsrc, int NB, int H, int W, const void* w_packed, int w_rows,
+                     int Ktot, int ldw, int Cout, const float* bias, const void* residual, int ldr, void* out, int ldo,
+                     int out_mode, void* workspace, long long workspace_bytes, float* gn_partial, int* info,
+                     const int* cfg, long long w_batch_stride, k2_stream_t stream);
 
 /* The decisions k2_conv_gemm takes for a geometry -- M tile box, N tile, CTA-pair mode, split-K factor, how the GroupNorm
  * partials come out -- without touching a pointer or the GPU (host arithmetic only; for tests, tooling and the caller's
@@ -121,8 +141,8 @@ int k2_gn_apply(const void* src0, int C0, int ld0, const void* src1, int C1, int
                 int zw, const float* sn_w, k2_stream_t stream);
 /* k2_gn_apply with the statistics pass folded in: instead of `stats` the producers' partial sums (the part0 / rg0 / part1 / rg1
  * / eps arguments of k2_gn_finalize) are given and every block derives mean / rstd of the groups it touches itself -- one
- * launch less per GroupNorm where an image has few row groups.  No SpatialNorm inputs.  NOT YET VALIDATED ON A GPU (added at
- * the end of round 1 for round 2; the kernels k2_gn_apply launches are bit-for-bit the ones that were validated). */
+ * launch less per GroupNorm.  No SpatialNorm inputs.  Statistics equal k2_gn_finalize's up to fp32 summation order
+ * (tests/test_gpu_ops.py::test_gn_apply_fold_matches_finalize_plus_apply). */
 int k2_gn_apply_fold(const void* src0, int C0, int ld0, const void* src1, int C1, int ld1, int NB, int H, int W, int groups,
                      const float* part0, int rg0, const float* part1, int rg1, float eps, const float* gamma,
                      const float* beta, const float* film, int film_ld, int act, int resample, void* y, int ldy, void* xres,
@@ -212,6 +232,15 @@ int k2_softmax_rows(const void* x, int ldx, void* y, int ldy, long long rows, in
 int k2_nchw_to_nhwc_f32(const float* x, float* y, int NB, int C, int H, int W, k2_stream_t stream);
 int k2_images_to_u8(const float* x_nchw, uint8_t* out_nhwc, int NB, int C, int H, int W, int crop_h,
                     int crop_w, k2_stream_t stream);
+/* MoVQ SpatialNorm (movq_modules.py:61-68) + optional swish (:21-23), one read + one write of the feature map:
+ *   y = act( GroupNorm(x) * (Wy.zq + by) + (Wb.zq + bb) ),  zq fp32 NHWC [NB, zh, zw, 4] nearest-resized to (H, W),
+ * stats fp32 [NB, groups, 2] (mean, rstd) from k2_gn_finalize / k2_gn_stats, sn_w fp32 [C, 10] = (Wy[4], by, Wb[4], bb).
+ * The per-channel normalisation and both 4 -> C modulations are folded into 10 register-resident coefficients per channel. */
+int k2_sn_apply(const void* x, int C, int ldx, int NB, int H, int W, int groups, const float* stats, const float* gamma,
+                const float* beta, const float* zq, int zh, int zw, const float* sn_w, int act, void* y, int ldy,
+                k2_stream_t stream);
+/* fp16 rows [B][T][ldx] (C columns) -> [B][C][T] (the attention values as a K-major B operand, movq_modules.py:216-219) */
+int k2_transpose_f16(const void* x, int ldx, void* y, int B, int T, int C, k2_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Diffusion prior (kandinsky2/model/prior.py:46-127), not on the measured denoising path and not

@@ -33,7 +33,6 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 bool pdl_enabled() { return g_pdl != 0; }
 static int g_conv_epi_sets = 1;
-int conv_epilogue_sets() { return g_conv_epi_sets; }
 int attention_stagger() { return g_attn_stagger; }
 int attention_poly_mode() { return g_attn_poly; }
 static int g_attn_issue = -1;  // -1: take K2_ATTN_ISSUE from the environment at first use (default 0)
@@ -109,7 +108,7 @@ int encode_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t
 // box -- e.g. 12x12 latents, 8 images: 8 images x 4 x 4 pixels = 128 rows per tile, 9 tiles with every MMA row used,
 // instead of 1 image x 6 rows x 12 (16 tiles, 56 % used).  Single-image boxes are preferred otherwise because the fused
 // GroupNorm statistics of the epilogue need them.
-static void choose_tile(int NB, int H, int W, int& TN, int& TH, int& TW) {
+static void choose_tile(int NB, int H, int W, int& TN, int& TH, int& TW, bool single_image_only = false) {
   long long best_tiles[2] = {-1, -1};  // [0]: TN == 1 only, [1]: any TN
   int bn[2] = {1, 1}, bw[2] = {1, 1}, bh[2] = {1, 1};
   const int wmax = W < 128 ? W : 128;
@@ -143,7 +142,7 @@ static void choose_tile(int NB, int H, int W, int& TN, int& TH, int& TW) {
       }
     }
   }
-  const int k = (best_tiles[1] * 100 <= best_tiles[0] * 85) ? 1 : 0;
+  const int k = (!single_image_only && best_tiles[1] * 100 <= best_tiles[0] * 85) ? 1 : 0;
   TN = bn[k];
   TW = bw[k];
   TH = bh[k];
@@ -155,12 +154,22 @@ static void choose_tile(int NB, int H, int W, int& TN, int& TH, int& TW) {
 struct ConvPlan {
   int TN, TH, TW, tiles_w, tiles_h, tiles_n, m_tiles;
   int halo_pitch, halo_bo;
+  int m_tiles_phase;  // up2: tile slots per output phase
   int BN, two_cta, splits;
   int fuse_stats, row_groups;
+  int es;  // epilogue warp sets of the CTA-pair kernel (1 or 2)
 };
 
+// cfg (may be null): per-call overrides {N tile, CTA-pair mode (1 off / 2 on), split-K factor, epilogue warp sets}; 0 = the
+// process-wide tuning knob, else automatic.  The caller's launch plan bakes its choice per launch (kandinsky2/model/unet.py).
 static void plan_conv(int NB, int H, int W, bool any9, int kchunks, int Cout, int out_mode, bool has_workspace,
-                      long long workspace_bytes, bool want_gn, ConvPlan& pl) {
+                      long long workspace_bytes, bool want_gn, ConvPlan& pl, const int* cfg = nullptr, bool up2 = false,
+                      bool w_batched = false) {
+  // up2: NB/H/W are the SOURCE geometry; every box is visited once per output phase (4x the tiles, same K loop)
+  const int g_force_bn = (cfg && cfg[0]) ? cfg[0] : k2::g_force_bn;
+  const int g_force_2cta = (cfg && cfg[1]) ? cfg[1] : k2::g_force_2cta;
+  const int g_force_split = (cfg && cfg[2]) ? cfg[2] : k2::g_force_split;
+  pl.es = (cfg && cfg[3]) ? cfg[3] : k2::g_conv_epi_sets;
   // halo kernel (one (8+2)x(16+2) activation box per K chunk instead of nine shifted boxes): 3x3 convolutions whose
   // image tiles exactly into 8 x 16 pixel boxes -- measured slower than nine shifted boxes, tuning knob 3, off by default
   pl.halo_pitch = 0;
@@ -174,12 +183,13 @@ static void plan_conv(int NB, int H, int W, bool any9, int kchunks, int Cout, in
     pl.TH = 16;
     pl.TW = 8;
   } else {
-    choose_tile(NB, H, W, pl.TN, pl.TH, pl.TW);
+    choose_tile(NB, H, W, pl.TN, pl.TH, pl.TW, w_batched);
   }
   pl.tiles_w = (W + pl.TW - 1) / pl.TW;
   pl.tiles_h = (H + pl.TH - 1) / pl.TH;
   pl.tiles_n = (NB + pl.TN - 1) / pl.TN;
   pl.m_tiles = pl.tiles_w * pl.tiles_h * pl.tiles_n;
+  pl.m_tiles_phase = pl.m_tiles;
 
   // Tile width N, CTA-pair mode and split-K factor from a cycle model fitted to the B200 sweeps
   // (profiles/conv_sweep_r1.txt, conv_sweep_small_r1.txt, conv_small_k_r1.txt):
@@ -194,8 +204,10 @@ static void plan_conv(int NB, int H, int W, bool any9, int kchunks, int Cout, in
   int two_cta = (Cout > 64 && g_force_2cta != 1) ? 1 : 0;
   if (g_force_2cta == 2 && Cout > 64) two_cta = 1;
   if (pl.halo_pitch) two_cta = 1;
+  // per-image weights: the two boxes of a CTA pair share one weight tile, so a pair must not straddle two images
+  if (w_batched && (pl.tiles_w * pl.tiles_h) % 2 != 0) two_cta = 0;
   const long long M_total = static_cast<long long>(NB) * H * W;
-  const bool can_split = !pl.halo_pitch && has_workspace && out_mode == 0 && Cout % 8 == 0;
+  const bool can_split = !pl.halo_pitch && !up2 && !w_batched && has_workspace && out_mode == 0 && Cout % 8 == 0;
   auto split_ok = [&](int sp) {
     if (sp == 1) return true;
     const int kps = (kchunks + sp - 1) / sp;
@@ -204,7 +216,7 @@ static void plan_conv(int NB, int H, int W, bool any9, int kchunks, int Cout, in
   };
   auto model = [&](int bn, int sp, bool pair) {
     const long long nt = (Cout + bn - 1) / bn;
-    const long long units = static_cast<long long>(pair ? (pl.m_tiles + 1) / 2 : pl.m_tiles) * nt * sp;
+    const long long units = static_cast<long long>(pair ? (pl.m_tiles + 1) / 2 : pl.m_tiles) * nt * sp * (up2 ? 4 : 1);
     const long long slots = pair ? num_sms() / 2 : num_sms();
     const long long waves = (units + slots - 1) / slots;
     const long long kps = (kchunks + sp - 1) / sp;
@@ -245,6 +257,9 @@ static void plan_conv(int NB, int H, int W, bool any9, int kchunks, int Cout, in
   pl.BN = BN;
   pl.two_cta = two_cta;
   pl.splits = splits;
+  if (up2) {  // tile slots per phase: even in pair mode, so that both boxes of a CTA pair belong to the same phase
+    pl.m_tiles_phase = two_cta ? (pl.m_tiles + 1) / 2 * 2 : pl.m_tiles;
+  }
 
   // fused GroupNorm partial statistics: from the epilogue when a tile never straddles two images (one partial per M
   // tile: the epilogue folds its four warps) or when it holds 16 pixels of each of 8 images (one partial per (image,
@@ -255,7 +270,7 @@ static void plan_conv(int NB, int H, int W, bool any9, int kchunks, int Cout, in
   if (want_gn && out_mode == 0 && Cout % 8 == 0) {
     if (splits == 1 && BN >= 64 && Cout % 64 == 0 && (pl.TN == 1 || pl.TH * pl.TW == 16)) {
       pl.fuse_stats = 1;
-      pl.row_groups = (pl.TN == 1) ? pl.m_tiles : NB * pl.tiles_h * pl.tiles_w;
+      pl.row_groups = ((pl.TN == 1) ? pl.m_tiles : NB * pl.tiles_h * pl.tiles_w) * (up2 ? 4 : 1);
     } else if (splits > 1 && (static_cast<long long>(H) * W) % 16 == 0) {
       pl.fuse_stats = 2;
       pl.row_groups = static_cast<int>(M_total / 16);
@@ -332,6 +347,22 @@ int k2_conv_gemm(const K2ConvSrc* srcs, int nsrc, int NB, int H, int W, const vo
                  int Ktot, int ldw, int Cout, const float* bias, const void* residual, int ldr, void* out, int ldo,
                  int out_mode, void* workspace, long long workspace_bytes, float* gn_partial, int* info,
                  k2_stream_t stream) {
+  return k2_conv_gemm_cfg(srcs, nsrc, NB, H, W, w_packed, w_rows, Ktot, ldw, Cout, bias, residual, ldr, out, ldo, out_mode,
+                          workspace, workspace_bytes, gn_partial, info, nullptr, 0, stream);
+}
+
+int k2_conv_gemm_cfg(const K2ConvSrc* srcs, int nsrc, int NB, int H, int W, const void* w_packed, int w_rows,
+                     int Ktot, int ldw, int Cout, const float* bias, const void* residual, int ldr, void* out, int ldo,
+                     int out_mode, void* workspace, long long workspace_bytes, float* gn_partial, int* info,
+                     const int* cfg, long long w_batch_stride, k2_stream_t stream) {
+  K2_REQUIRE(w_batch_stride >= 0 && w_batch_stride % 8 == 0, "conv_gemm_cfg: w_batch_stride must be a multiple of 8 elements");
+  const bool w_batched = w_batch_stride > 0;
+  if (cfg) {
+    K2_REQUIRE(cfg[0] == 0 || cfg[0] == 16 || cfg[0] == 64 || cfg[0] == 128 || cfg[0] == 192 || cfg[0] == 256,
+               "conv_gemm_cfg: N tile must be 0, 16, 64, 128, 192 or 256");
+    K2_REQUIRE(cfg[1] >= 0 && cfg[1] <= 2 && cfg[2] >= 0 && cfg[2] <= 8 && cfg[3] >= 0 && cfg[3] <= 2,
+               "conv_gemm_cfg: pair mode in 0..2, splits in 0..8, epilogue sets in 0..2");
+  }
   K2_REQUIRE(nsrc >= 1 && nsrc <= 3, "conv_gemm: 1..3 sources");
   K2_REQUIRE(NB > 0 && H > 0 && W > 0 && Cout > 0, "conv_gemm: bad geometry");
   K2_REQUIRE(w_rows >= Cout, "conv_gemm: w_rows < Cout");
@@ -346,9 +377,19 @@ int k2_conv_gemm(const K2ConvSrc* srcs, int nsrc, int NB, int H, int W, const vo
   p.W = W;
   bool any9 = false;
   int kchunks = 0;
+  const bool up2 = srcs[0].taps == 4;
+  if (up2) {
+    K2_REQUIRE(nsrc == 1 && out_mode == 0 && residual == nullptr && H % 2 == 0 && W % 2 == 0,
+               "conv_gemm: a taps == 4 source (3x3 conv over its nearest-2x upsampling) must be the only source, with fp16 "
+               "output, no residual and even output H, W");
+    H /= 2;  // from here on: SOURCE geometry (the tile boxes live there)
+    W /= 2;
+    p.H = H;
+    p.W = W;
+  }
   for (int s = 0; s < nsrc; ++s) {
     const K2ConvSrc& src = srcs[s];
-    K2_REQUIRE(src.taps == 9 || src.taps == 1, "conv_gemm: taps must be 9 or 1");
+    K2_REQUIRE(src.taps == 9 || src.taps == 1 || (s == 0 && src.taps == 4), "conv_gemm: taps must be 9 or 1 (or 4: up2)");
     K2_REQUIRE(src.C > 0 && src.C % 8 == 0 && src.ld % 8 == 0 && src.ld >= src.C, "conv_gemm: bad source C/ld");
     K2_REQUIRE((reinterpret_cast<uintptr_t>(src.ptr) & 15) == 0, "conv_gemm: source not 16B aligned");
     any9 = any9 || src.taps == 9;
@@ -356,11 +397,15 @@ int k2_conv_gemm(const K2ConvSrc* srcs, int nsrc, int NB, int H, int W, const vo
     p.seg_kchunks[s] = (src.C + 63) / 64;
     kchunks += src.taps * p.seg_kchunks[s];
   }
-  K2_REQUIRE(kchunks * 64 == Ktot, "conv_gemm: Ktot does not match the sources (taps * ceil(C/64)*64 summed)");
+  K2_REQUIRE(kchunks * 64 * (up2 ? 4 : 1) == Ktot,
+             "conv_gemm: Ktot does not match the sources (taps * ceil(C/64)*64 summed; x4 phases for a taps == 4 source)");
   p.num_k_chunks = kchunks;
 
   ConvPlan pl;
-  plan_conv(NB, H, W, any9, kchunks, Cout, out_mode, workspace != nullptr, workspace_bytes, gn_partial != nullptr, pl);
+  plan_conv(NB, H, W, any9 || up2, kchunks, Cout, out_mode, workspace != nullptr, workspace_bytes, gn_partial != nullptr, pl,
+            cfg, up2, w_batched);
+  K2_REQUIRE(!w_batched || (!up2 && pl.TN == 1 && !pl.halo_pitch), "conv_gemm_cfg: batched weights need single-image tiles");
+  p.w_batched = w_batched ? 1 : 0;
   plan_to_info(pl, info);
   p.TN = pl.TN;
   p.TH = pl.TH;
@@ -370,7 +415,9 @@ int k2_conv_gemm(const K2ConvSrc* srcs, int nsrc, int NB, int H, int W, const vo
   p.tiles_w = pl.tiles_w;
   p.tiles_h = pl.tiles_h;
   p.tiles_n = pl.tiles_n;
-  p.m_tiles = pl.m_tiles;
+  p.m_tiles = up2 ? 4 * pl.m_tiles_phase : pl.m_tiles;
+  p.m_tiles_phase = pl.m_tiles_phase;
+  p.up2 = up2 ? 1 : 0;
   p.a_box_bytes = static_cast<uint32_t>(p.TN * p.TH * p.TW * 128);
   for (int s = 0; s < nsrc; ++s) {
     const K2ConvSrc& src = srcs[s];
@@ -389,15 +436,16 @@ int k2_conv_gemm(const K2ConvSrc* srcs, int nsrc, int NB, int H, int W, const vo
   p.two_cta = two_cta;
   p.splits = splits;
   p.k_per_split = (kchunks + splits - 1) / splits;
-  p.M_total = static_cast<long long>(NB) * H * W;
+  p.M_total = static_cast<long long>(NB) * H * W * (up2 ? 4 : 1);
   p.ws = reinterpret_cast<float*>(workspace);
   p.n_tiles = (Cout + BN - 1) / BN;
   p.Cout = Cout;
   {
-    uint64_t dims[2] = {static_cast<uint64_t>(Ktot), static_cast<uint64_t>(w_rows)};
-    uint64_t str[1] = {static_cast<uint64_t>(ldw) * 2};
-    uint32_t box[2] = {64, static_cast<uint32_t>(two_cta ? BN / 2 : BN)};
-    if (encode_tmap_f16(&p.tmB, w_packed, 2, dims, str, box)) return -1;
+    uint64_t dims[3] = {static_cast<uint64_t>(Ktot), static_cast<uint64_t>(w_rows), static_cast<uint64_t>(w_batched ? NB : 1)};
+    uint64_t str[2] = {static_cast<uint64_t>(ldw) * 2,
+                       (w_batched ? static_cast<uint64_t>(w_batch_stride) : static_cast<uint64_t>(ldw) * w_rows) * 2};
+    uint32_t box[3] = {64, static_cast<uint32_t>(two_cta ? BN / 2 : BN), 1};
+    if (encode_tmap_f16(&p.tmB, w_packed, 3, dims, str, box)) return -1;
   }
   p.bias = bias;
   p.residual = reinterpret_cast<const __half*>(residual);
@@ -412,7 +460,7 @@ int k2_conv_gemm(const K2ConvSrc* srcs, int nsrc, int NB, int H, int W, const vo
     if (residual)
       K2_REQUIRE(ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0, "conv_gemm: residual alignment");
   }
-  int rc = launch_conv_gemm(p, BN, static_cast<cudaStream_t>(stream));
+  int rc = launch_conv_gemm(p, BN, pl.es, static_cast<cudaStream_t>(stream));
   if (rc == 0) g_launches.fetch_add(1, std::memory_order_relaxed);
   if (rc == 0 && splits > 1) {
     rc = launch_splitk_finalize(p.ws, splits, p.M_total, Cout, bias, p.residual, ldr, reinterpret_cast<__half*>(out), ldo,

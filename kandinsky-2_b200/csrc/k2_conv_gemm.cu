@@ -45,8 +45,15 @@ struct Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + STAT_BYTES + 1024;  // +1024 alignment slack
 };
 
+// up2 (3x3 conv over the nearest-2x upsampled source as four 2x2 phase convolutions): m_idx = phase * m_tiles_phase + box
+// index; the box lives in SOURCE coordinates, `phase` = (a, b) = parity of the output pixel (2y + a, 2x + b).
 __device__ __forceinline__ void decode_m_tile(const ConvGemmParams& p, int m_idx, int& n0, int& y0,
-                                              int& x0) {
+                                              int& x0, int& phase) {
+  phase = 0;
+  if (p.up2) {
+    phase = m_idx / p.m_tiles_phase;
+    m_idx -= phase * p.m_tiles_phase;
+  }
   int tw_i = m_idx % p.tiles_w;
   int t = m_idx / p.tiles_w;
   int th_i = t % p.tiles_h;
@@ -74,7 +81,7 @@ __device__ __forceinline__ void decode_m_tile(const ConvGemmParams& p, int m_idx
 template <int BN, int ES = 1>
 __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t tmem_base, int acc_col, int ew, int lane,
                                               int n0, int y0, int x0, int n_idx, int split, int m_idx, float* stat_smem,
-                                              int es_arg = 0) {
+                                              int es_arg = 0, int phase = 0) {
   const int es = (ES == 1) ? 0 : es_arg;
   const int row = ew * 32 + lane;
   const int thw = p.TH * p.TW;
@@ -85,7 +92,11 @@ __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t 
       const int tw = rem - th * p.TW;
       const int n = n0 + tn, y = y0 + th, x = x0 + tw;
       const bool valid = (tn < p.TN) && (n < p.NB) && (y < p.H) && (x < p.W);
-      const long long out_row = (static_cast<long long>(n) * p.H + y) * p.W + x;
+      const long long out_row = p.up2 ? (static_cast<long long>(n) * (2 * p.H) + (2 * y + (phase >> 1))) * (2 * p.W) + (2 * x + (phase & 1))
+                                      : (static_cast<long long>(n) * p.H + y) * p.W + x;
+      // GroupNorm partial row groups stay image-major under up2: (box index) * 4 + phase
+      const int m_in = p.up2 ? m_idx - phase * p.m_tiles_phase : m_idx;
+      auto part_index = [&](long long base) { return p.up2 ? base * 4 + phase : base; };
       if constexpr (BN % 64 == 0) {
         if ((p.out_mode == 0 && p.Cout % 64 == 0) || (p.out_mode == 2 && p.Cout % 32 == 0)) {
           const uint32_t stage = smem_u32(stat_smem + (es * 4 + ew) * EPI_STAGE_FLOATS);  // [32 rows][8 x 16 B], piece ^= row & 7
@@ -227,12 +238,12 @@ __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t 
                 if (p.gn_mode == 2) {
                   // 16-pixel x 8-image tiles: half warp h of warp ew holds image n0 + 2*ew + h of spatial tile sp
                   const int per = p.tiles_h * p.tiles_w;
-                  const int sp = m_idx % per;
+                  const int sp = m_in % per;
                   const int img = n0 + 2 * ew;
                   if (2 * ew < p.TN && img < p.NB)
-                    *reinterpret_cast<float4*>(p.gn_part + (static_cast<long long>(img) * per + sp) * p.Cout + col0 + 2 * lane) = h0;
+                    *reinterpret_cast<float4*>(p.gn_part + part_index(static_cast<long long>(img) * per + sp) * p.Cout + col0 + 2 * lane) = h0;
                   if (2 * ew + 1 < p.TN && img + 1 < p.NB)
-                    *reinterpret_cast<float4*>(p.gn_part + (static_cast<long long>(img + 1) * per + sp) * p.Cout + col0 + 2 * lane) = h1;
+                    *reinterpret_cast<float4*>(p.gn_part + part_index(static_cast<long long>(img + 1) * per + sp) * p.Cout + col0 + 2 * lane) = h1;
                 } else {
                   st[jp] = make_float4(h0.x + h1.x, h0.y + h1.y, h0.z + h1.z, h0.w + h1.w);
                 }
@@ -257,7 +268,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t 
                     const float4 t = reinterpret_cast<const float4*>(stat_smem + w * EPI_STAGE_FLOATS)[ew * 32 + lane];
                     acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
                   }
-                  *reinterpret_cast<float4*>(p.gn_part + static_cast<long long>(m_idx) * p.Cout + col0 + 2 * lane) = acc;
+                  *reinterpret_cast<float4*>(p.gn_part + part_index(m_in) * p.Cout + col0 + 2 * lane) = acc;
                 }
               }
               named_bar_sync(1, 128);
@@ -278,7 +289,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t 
                         reinterpret_cast<const float4*>(stat_smem + (es * 4 + w) * EPI_STAGE_FLOATS)[jp_f * 32 + lane];
                     acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
                   }
-                  *reinterpret_cast<float4*>(p.gn_part + static_cast<long long>(m_idx) * p.Cout + col0 + 2 * lane) = acc;
+                  *reinterpret_cast<float4*>(p.gn_part + part_index(m_in) * p.Cout + col0 + 2 * lane) = acc;
                 }
               }
               named_bar_sync(1 + es, 128);
@@ -416,14 +427,15 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
     // ===================================== TMA producer =====================================
     if (elect_one()) {  // one lane, and ptxas KNOWS it is one: UTCHMMA / UTMALDG operands need no per-lane waterfall loop
       int stage = 0;
-      uint32_t phase = 0;
+      uint32_t ring_phase = 0;
       const uint32_t tx_bytes = p.a_box_bytes + C::B_STAGE_BYTES;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m_idx = tile % p.m_tiles;
         const int n_idx = (tile / p.m_tiles) % p.n_tiles;
         const int split = tile / (p.m_tiles * p.n_tiles);
-        int n0, y0, x0;
-        decode_m_tile(p, m_idx, n0, y0, x0);
+        int n0, y0, x0, phase;
+        decode_m_tile(p, m_idx, n0, y0, x0, phase);
+        const int kb = phase * p.num_k_chunks;  // up2: each phase has its own 4-tap weight block
         const int k0 = split * p.k_per_split;
         const int k1 = min(p.num_k_chunks, k0 + p.k_per_split);
         // position (segment, tap, channel chunk) of flattened K chunk k0
@@ -436,17 +448,17 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
         int c = rem - tap * p.seg_kchunks[s];
         for (int kc = k0; kc < k1; ++kc) {
           const int taps = p.seg_taps[s];
-          const int dy = (taps == 9) ? (tap / 3 - 1) : 0;
-          const int dx = (taps == 9) ? (tap % 3 - 1) : 0;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          const int dy = (taps == 9) ? (tap / 3 - 1) : (taps == 4 ? (tap >> 1) + (phase >> 1) - 1 : 0);
+          const int dx = (taps == 9) ? (tap % 3 - 1) : (taps == 4 ? (tap & 1) + (phase & 1) - 1 : 0);
+          mbar_wait(&empty_bar[stage], ring_phase ^ 1);
           uint8_t* sA = smem + stage * C::STAGE_BYTES;
           uint8_t* sB = sA + A_STAGE_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
           tma_load_4d(sA, &p.tmA[s], &full_bar[stage], c * BK, x0 + dx, y0 + dy, n0);
-          tma_load_2d(sB, &p.tmB, &full_bar[stage], kc * BK, n_idx * BN);
+          tma_load_3d(sB, &p.tmB, &full_bar[stage], (kb + kc) * BK, n_idx * BN, p.w_batched ? n0 : 0);
           if (++stage == C::STAGES) {
             stage = 0;
-            phase ^= 1;
+            ring_phase ^= 1;
           }
           if (++c == p.seg_kchunks[s]) {
             c = 0;
@@ -504,11 +516,11 @@ __global__ void __launch_bounds__(256, 1) conv_gemm_kernel(const __grid_constant
       const int m_idx = tile % p.m_tiles;
       const int n_idx = (tile / p.m_tiles) % p.n_tiles;
       const int split = tile / (p.m_tiles * p.n_tiles);
-      int n0, y0, x0;
-      decode_m_tile(p, m_idx, n0, y0, x0);
+      int n0, y0, x0, phase;
+      decode_m_tile(p, m_idx, n0, y0, x0, phase);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      epilogue_tile<BN>(p, tmem_base, acc * BN, ew, lane, n0, y0, x0, n_idx, split, m_idx, stat_smem);
+      epilogue_tile<BN>(p, tmem_base, acc * BN, ew, lane, n0, y0, x0, n_idx, split, m_idx, stat_smem, 0, phase);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -599,14 +611,15 @@ conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p) {
     // ===================================== TMA producer (both CTAs) ==========================
     if (elect_one()) {  // one lane, and ptxas KNOWS it is one: UTCHMMA / UTMALDG operands need no per-lane waterfall loop
       int stage = 0;
-      uint32_t phase = 0;
+      uint32_t ring_phase = 0;
       const uint32_t tx_bytes = 2u * (p.a_box_bytes + C::B_STAGE_BYTES);
       for (int tile = pair; tile < total_tiles; tile += num_pairs) {
         const int m_idx = (tile % m_pairs) * 2 + static_cast<int>(rank);
         const int n_idx = (tile / m_pairs) % p.n_tiles;
         const int split = tile / (m_pairs * p.n_tiles);
-        int n0, y0, x0;
-        decode_m_tile(p, m_idx, n0, y0, x0);  // m_idx == m_tiles (odd tail): n0 >= NB -> the box is all zero-fill
+        int n0, y0, x0, phase;
+        decode_m_tile(p, m_idx, n0, y0, x0, phase);  // m_idx == m_tiles (odd tail): n0 >= NB -> the box is all zero-fill
+        const int kb = phase * p.num_k_chunks;  // up2: each phase has its own 4-tap weight block
         const int k0 = split * p.k_per_split;
         const int k1 = min(p.num_k_chunks, k0 + p.k_per_split);
         int s = 0, rem = k0;
@@ -618,17 +631,18 @@ conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p) {
         int c = rem - tap * p.seg_kchunks[s];
         for (int kc = k0; kc < k1; ++kc) {
           const int taps = p.seg_taps[s];
-          const int dy = (taps == 9) ? (tap / 3 - 1) : 0;
-          const int dx = (taps == 9) ? (tap % 3 - 1) : 0;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          const int dy = (taps == 9) ? (tap / 3 - 1) : (taps == 4 ? (tap >> 1) + (phase >> 1) - 1 : 0);
+          const int dx = (taps == 9) ? (tap % 3 - 1) : (taps == 4 ? (tap & 1) + (phase & 1) - 1 : 0);
+          mbar_wait(&empty_bar[stage], ring_phase ^ 1);
           uint8_t* sA = smem + stage * C::STAGE_BYTES;
           uint8_t* sB = sA + A_STAGE_BYTES;
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
           tma2_load_4d(sA, &p.tmA[s], &full_bar[stage], c * BK, x0 + dx, y0 + dy, n0);
-          tma2_load_2d(sB, &p.tmB, &full_bar[stage], kc * BK, n_idx * BN + static_cast<int>(rank) * (BN / 2));
+          tma2_load_3d(sB, &p.tmB, &full_bar[stage], (kb + kc) * BK, n_idx * BN + static_cast<int>(rank) * (BN / 2),
+                       p.w_batched ? n0 : 0);
           if (++stage == C::STAGES) {
             stage = 0;
-            phase ^= 1;
+            ring_phase ^= 1;
           }
           if (++c == p.seg_kchunks[s]) {
             c = 0;
@@ -687,11 +701,11 @@ conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p) {
       const int m_idx = (tile % m_pairs) * 2 + static_cast<int>(rank);
       const int n_idx = (tile / m_pairs) % p.n_tiles;
       const int split = tile / (m_pairs * p.n_tiles);
-      int n0, y0, x0;
-      decode_m_tile(p, m_idx, n0, y0, x0);
+      int n0, y0, x0, phase;
+      decode_m_tile(p, m_idx, n0, y0, x0, phase);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      epilogue_tile<BN, ES>(p, tmem_base, acc * 256, ew, lane, n0, y0, x0, n_idx, split, m_idx, stat_smem, es);
+      epilogue_tile<BN, ES>(p, tmem_base, acc * 256, ew, lane, n0, y0, x0, n_idx, split, m_idx, stat_smem, es, phase);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(acc ? leader_empty1 : leader_empty0);
@@ -724,7 +738,8 @@ int launch_bn2(const ConvGemmParams& p, cudaStream_t stream) {
   return 0;
 }
 
-// CTA-pair kernel with two epilogue warp sets (384 threads, one pipeline stage fewer): NOT YET VALIDATED ON A GPU.
+// CTA-pair kernel with two epilogue warp sets (384 threads, one pipeline stage fewer); bit-identical to the one-set kernel
+// (tests/test_gpu_conv_gemm.py::test_two_epilogue_sets_bit_identical).
 template <int BN>
 int launch_bn2e(const ConvGemmParams& p, cudaStream_t stream) {
   using C = Cfg2<BN, 2>;
@@ -828,8 +843,8 @@ conv_gemm3_kernel(const __grid_constant__ ConvGemmParams p) {
       for (int tile = pair; tile < total_tiles; tile += num_pairs) {
         const int m_idx = (tile % m_pairs) * 2 + static_cast<int>(rank);
         const int n_idx = tile / m_pairs;
-        int n0, y0, x0;
-        decode_m_tile(p, m_idx, n0, y0, x0);
+        int n0, y0, x0, phase_unused;
+        decode_m_tile(p, m_idx, n0, y0, x0, phase_unused);
         int kc_base = 0;
         for (int s = 0; s < 3; ++s) {
           const int taps = p.seg_taps[s];
@@ -852,8 +867,8 @@ conv_gemm3_kernel(const __grid_constant__ ConvGemmParams p) {
             for (int tap = 0; tap < taps; ++tap) {
               mbar_wait(&b_empty[bs], bph ^ 1);
               if (rank == 0) mbar_arrive_expect_tx(&b_full[bs], 2u * C::B_STAGE);
-              tma2_load_2d(smemB + bs * C::B_STAGE, &p.tmB, &b_full[bs], (kc_base + tap * kch + c) * BK,
-                           n_idx * BN + static_cast<int>(rank) * (BN / 2));
+              tma2_load_3d(smemB + bs * C::B_STAGE, &p.tmB, &b_full[bs], (kc_base + tap * kch + c) * BK,
+                           n_idx * BN + static_cast<int>(rank) * (BN / 2), 0);
               if (++bs == C::B_STAGES) {
                 bs = 0;
                 bph ^= 1;
@@ -930,8 +945,8 @@ conv_gemm3_kernel(const __grid_constant__ ConvGemmParams p) {
     for (int tile = pair; tile < total_tiles; tile += num_pairs) {
       const int m_idx = (tile % m_pairs) * 2 + static_cast<int>(rank);
       const int n_idx = tile / m_pairs;
-      int n0, y0, x0;
-      decode_m_tile(p, m_idx, n0, y0, x0);
+      int n0, y0, x0, phase_unused;
+      decode_m_tile(p, m_idx, n0, y0, x0, phase_unused);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       epilogue_tile<BN>(p, tmem_base, acc * 256, ew, lane, n0, y0, x0, n_idx, 0, m_idx, stat_smem);
@@ -1066,7 +1081,7 @@ int launch_splitk_finalize(const float* ws, int splits, long long M, int Cout, c
   return 0;
 }
 
-int launch_conv_gemm(const ConvGemmParams& p, int BN, cudaStream_t stream) {
+int launch_conv_gemm(const ConvGemmParams& p, int BN, int epilogue_sets, cudaStream_t stream) {
   if (p.halo_pitch) {
     switch (BN) {
       case 128: return launch_bn3<128>(p, stream);
@@ -1075,7 +1090,7 @@ int launch_conv_gemm(const ConvGemmParams& p, int BN, cudaStream_t stream) {
       default: return fail("conv_gemm: unsupported BN for the halo kernel");
     }
   }
-  if (p.two_cta && conv_epilogue_sets() == 2) {  // round-2 candidate (tuning key 10): two epilogue warp sets
+  if (p.two_cta && epilogue_sets == 2) {  // two epilogue warp sets (384 threads): short-K GEMMs are epilogue-paced
     switch (BN) {
       case 128: return launch_bn2e<128>(p, stream);
       case 192: return launch_bn2e<192>(p, stream);

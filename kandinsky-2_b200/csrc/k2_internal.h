@@ -52,7 +52,8 @@ int encode_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t
 // ---- implicit-GEMM convolution / GEMM (k2_conv_gemm.cu) -----------------------------------------
 struct ConvGemmParams {
   CUtensorMap tmA[3];  // activation sources, 4-D (C, W, H, N)
-  CUtensorMap tmB;     // packed weights, 2-D (Ktot, Cout_rows), K contiguous
+  CUtensorMap tmB;     // packed weights, 3-D (Ktot, Cout_rows, batch), K contiguous; batch = 1 unless w_batched
+  int w_batched;       // 1: image n of the NB images multiplies its own weight matrix (batched GEMM; tiles never span images)
   int seg_taps[3];     // 9 (3x3, pad 1), 1 (1x1) or 0 (unused)
   int seg_kchunks[3];  // 64-channel chunks per tap
   int num_k_chunks;
@@ -75,10 +76,14 @@ struct ConvGemmParams {
   int two_cta;         // 1: CTA-pair kernel (cta_group::2, 256-row tiles)
   float2* gn_part;     // fused GroupNorm partials (sum, sumsq) of the fp16-rounded output, or null:
   int gn_mode;         //   1: [m_tiles][Cout], one per M tile (TN == 1); 2: [image][spatial tile][Cout] for 16-pixel x 8-image tiles
+  int up2;             // 1: source 0 has taps == 4: 3x3 conv over the nearest-2x upsampled source as four 2x2 phase convs;
+                       //    NB/H/W and the tile box are SOURCE geometry, outputs go to pixel (2y + a, 2x + b) of a 2H x 2W image
+  int m_tiles_phase;   // up2: tile slots per phase (m_tiles = 4 * m_tiles_phase; even in CTA-pair mode so a pair never
+                       //    straddles two phases -- its two boxes share one weight tile)
   int halo_pitch;      // 0: per-tap boxes; 10 / 16: halo kernel, pixels per halo row in shared memory
   int halo_bo;         // halo kernel: 1 = put (start >> 7) & 7 into the descriptor's base-offset field
 };
-int launch_conv_gemm(const ConvGemmParams& p, int BN, cudaStream_t stream);
+int launch_conv_gemm(const ConvGemmParams& p, int BN, int epilogue_sets, cudaStream_t stream);
 int launch_splitk_finalize(const float* ws, int splits, long long M, int Cout, const float* bias, const __half* residual,
                            int ldr, __half* out, int ldo, float2* gn_part, cudaStream_t stream);
 
@@ -96,7 +101,6 @@ struct AttnParams {
   unsigned long long* trace;  // diagnostics: 3 x 16 x 8 clock64 stamps of CTA (0,0,0), or null
   int issue_mode;      // MMA issuer: 0 = fixed program order per key block, 1 = event driven (polls both query tiles)
 };
-int conv_epilogue_sets();  // 1 (validated) or 2 (tuning key 10, round-2 candidate)
 int attention_stagger();
 unsigned long long* attention_trace_buffer();
 int attention_issue_mode();

@@ -1,0 +1,197 @@
+// k2_movq.cu -- MoVQ decoder elementwise kernels: SpatialNorm apply and the fp16 transpose of the attention values.
+//
+// Replaces (reference file:line):
+//   SpatialNorm.forward   kandinsky2/vqgan/movq_modules.py:61-68
+//       zq = interpolate(zq, size=f.shape[-2:], mode="nearest"); y = GroupNorm(f) * conv_y(zq) + conv_b(zq)   (+ swish, :21-23)
+//   AttnBlock's  v.reshape / permute before torch.bmm   movq_modules.py:216-219
+//
+// SpatialNorm is HBM-bound: one read and one write of the feature map (up to 604 MB per tensor at 768x768).  Round 1 ran it
+// through the generic gn_apply kernel, which re-derived the 2 x (4 -> C) modulation with 80 read-only loads per thread every
+// time the latent pixel under a thread changed: 1.16 TB/s, 38 % of the decode.  Here everything that does not depend on the
+// pixel is folded ONCE per thread into 10 coefficients per channel that live in registers:
+//       y = x * a(z) + b(z),   a(z) = A (wy.z + by),   b(z) = B (wy.z + by) + (wb.z + bb),   A = gamma rstd,  B = beta - mean A
+//   ->  a = a5[0..3].z + a5[4],  b = b5[0..3].z + b5[4]:   9 FMA per element, the 4-float latent pixel z comes from L1.
+#include "../../include/k2b200.h"
+#include "k2_common.cuh"
+#include "k2_internal.h"
+
+namespace k2 {
+namespace {
+
+constexpr int VX = 16;   // channel vectors (8 fp16 = 16 B) per block: a half warp covers 256 contiguous bytes of a pixel
+constexpr int PY = 16;   // pixel lanes per block
+constexpr int UN = 8;    // vectors per thread per iteration, two iterations in flight: the 80 coefficient registers cap the
+                         // kernel at one 256-thread block per SM, so each thread keeps 16 loads (256 B) in flight instead
+
+struct SnParams {
+  const __half* x;
+  int C, ldx;
+  int NB, H, W, groups;
+  const float* stats;   // [NB, groups, 2] (mean, rstd)
+  const float* gamma;
+  const float* beta;
+  const float* zq;      // fp32 [NB, zh, zw, 4]
+  int zh, zw;
+  const float* sn_w;    // fp32 [C, 10] = (wy[4], by, wb[4], bb)
+  int act;
+  __half* y;
+  int ldy;
+  int chunk;            // pixels per block
+};
+
+__global__ void __launch_bounds__(256) sn_apply_kernel(const SnParams p) {
+  const int vx = threadIdx.x % VX;
+  const int py = threadIdx.x / VX;
+  const int v = blockIdx.y * VX + vx;
+  const int n = blockIdx.z;
+  pdl_wait();
+  pdl_launch();
+  if (v >= p.C / 8) return;
+  const int c0 = v * 8;
+  const int HW = p.H * p.W;
+  const int p0 = blockIdx.x * p.chunk;
+  const int p1 = min(HW, p0 + p.chunk);
+
+  float a5[8][5], b5[8][5];
+  {
+    const int cpg = p.C / p.groups;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = c0 + e;
+      const float2 st = __ldg(reinterpret_cast<const float2*>(p.stats + (static_cast<long long>(n) * p.groups + c / cpg) * 2));
+      const float A = __ldg(p.gamma + c) * st.y;
+      const float B = __ldg(p.beta + c) - st.x * A;
+      const float* w = p.sn_w + static_cast<long long>(c) * 10;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const float wy = __ldg(w + k), wb = __ldg(w + 5 + k);
+        a5[e][k] = A * wy;
+        b5[e][k] = fmaf(B, wy, wb);
+      }
+    }
+  }
+  const __half* xb = p.x + c0;
+  __half* yb = p.y + c0;
+  const long long img = static_cast<long long>(n) * HW;
+  const float4* zb = reinterpret_cast<const float4*>(p.zq) + static_cast<long long>(n) * p.zh * p.zw;
+
+  uint4 raw[UN], nxt[UN];
+  auto load_set = [&](int pp, uint4 (&dst)[UN]) {
+#pragma unroll
+    for (int u = 0; u < UN; ++u)
+      if (pp + u < p1) dst[u] = __ldg(reinterpret_cast<const uint4*>(xb + (img + pp + u) * p.ldx));
+  };
+  int last_z = -1;
+  float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  int pp = p0 + py * UN;
+  if (pp < p1) load_set(pp, raw);
+  for (; pp < p1; pp += UN * PY) {
+    const int npp = pp + UN * PY;
+    if (npp < p1) load_set(npp, nxt);
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int q = pp + u;
+      if (q >= p1) break;
+      const int yi = q / p.W, xi = q - yi * p.W;
+      const int zi = ((yi * p.zh) / p.H) * p.zw + (xi * p.zw) / p.W;   // nearest: floor(dst * in / out)
+      if (zi != last_z) {
+        last_z = zi;
+        z = __ldg(zb + zi);
+      }
+      const __half2* h2 = reinterpret_cast<const __half2*>(&raw[u]);
+      uint4 ov;
+      __half2* oh = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+      for (int e2 = 0; e2 < 4; ++e2) {
+        const float2 f = __half22float2(h2[e2]);
+        float o[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int e = 2 * e2 + k;
+          const float a = fmaf(a5[e][3], z.w, fmaf(a5[e][2], z.z, fmaf(a5[e][1], z.y, fmaf(a5[e][0], z.x, a5[e][4]))));
+          const float b = fmaf(b5[e][3], z.w, fmaf(b5[e][2], z.z, fmaf(b5[e][1], z.y, fmaf(b5[e][0], z.x, b5[e][4]))));
+          const float t = fmaf(k ? f.y : f.x, a, b);
+          o[k] = p.act ? silu_f(t) : t;
+        }
+        oh[e2] = __floats2half2_rn(o[0], o[1]);
+      }
+      *reinterpret_cast<uint4*>(yb + (img + q) * p.ldy) = ov;
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) raw[u] = nxt[u];
+  }
+}
+
+// fp16 [B][T][ldx] (C columns) -> [B][C][T]: 64 x 64 tiles through shared memory, 16-byte accesses on both sides.
+__global__ void __launch_bounds__(256) transpose_f16_kernel(const __half* __restrict__ x, int ldx, __half* __restrict__ y,
+                                                            int T, int C) {
+  __shared__ __half tile[64][64 + 8];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  pdl_wait();
+  pdl_launch();
+  const __half* xb = x + static_cast<long long>(b) * T * ldx;
+  __half* yb = y + static_cast<long long>(b) * C * T;
+  for (int i = threadIdx.x; i < 64 * 8; i += 256) {  // 64 rows (t) x 8 vectors of 8 channels
+    const int r = i >> 3, vv = i & 7;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (t0 + r < T && c0 + vv * 8 < C) val = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<long long>(t0 + r) * ldx + c0 + vv * 8));
+    *reinterpret_cast<uint4*>(&tile[r][vv * 8]) = val;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64 * 8; i += 256) {  // 64 rows (c) x 8 vectors of 8 tokens
+    const int r = i >> 3, vv = i & 7;
+    if (c0 + r >= C || t0 + vv * 8 >= T) continue;
+    __half o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = tile[vv * 8 + e][r];
+    *reinterpret_cast<uint4*>(yb + static_cast<long long>(c0 + r) * T + t0 + vv * 8) = *reinterpret_cast<const uint4*>(o);
+  }
+}
+
+}  // namespace
+}  // namespace k2
+
+using namespace k2;
+
+extern "C" {
+
+int k2_sn_apply(const void* x, int C, int ldx, int NB, int H, int W, int groups, const float* stats, const float* gamma,
+                const float* beta, const float* zq, int zh, int zw, const float* sn_w, int act, void* y, int ldy,
+                k2_stream_t stream) {
+  K2_REQUIRE(x && y && stats && gamma && beta && zq && sn_w, "sn_apply: null pointer");
+  K2_REQUIRE(C % 8 == 0 && C % groups == 0 && ldx % 8 == 0 && ldy % 8 == 0, "sn_apply: bad channel counts / strides");
+  K2_REQUIRE(NB > 0 && H > 0 && W > 0 && zh > 0 && zw > 0 && NB <= 65535, "sn_apply: bad geometry");
+  SnParams p;
+  p.x = reinterpret_cast<const __half*>(x);
+  p.C = C; p.ldx = ldx; p.NB = NB; p.H = H; p.W = W; p.groups = groups;
+  p.stats = stats; p.gamma = gamma; p.beta = beta; p.zq = zq; p.zh = zh; p.zw = zw; p.sn_w = sn_w; p.act = act;
+  p.y = reinterpret_cast<__half*>(y); p.ldy = ldy;
+  const int ctiles = (C / 8 + VX - 1) / VX;
+  const int HW = H * W;
+  // ~6 blocks per SM in total, each thread at least one full double-buffered iteration
+  int chunks = (6 * num_sms() + ctiles * NB - 1) / (ctiles * NB);
+  const int max_chunks = (HW + UN * PY - 1) / (UN * PY);
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  int chunk = (HW + chunks - 1) / chunks;
+  chunk = (chunk + UN * PY - 1) / (UN * PY) * (UN * PY);
+  p.chunk = chunk;
+  dim3 grid((HW + chunk - 1) / chunk, ctiles, NB);
+  K2_CHECK_CUDA(launch_k(sn_apply_kernel, grid, dim3(256), 0, static_cast<cudaStream_t>(stream), p));
+  count_launch();
+  return 0;
+}
+
+int k2_transpose_f16(const void* x, int ldx, void* y, int B, int T, int C, k2_stream_t stream) {
+  K2_REQUIRE(x && y && B > 0 && T > 0 && C > 0, "transpose_f16: bad arguments");
+  K2_REQUIRE(ldx % 8 == 0 && C % 8 == 0 && T % 8 == 0, "transpose_f16: T, C and the row stride must be multiples of 8");
+  K2_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0, "transpose_f16: alignment");
+  dim3 grid((T + 63) / 64, (C + 63) / 64, B);
+  K2_CHECK_CUDA(launch_k(transpose_f16_kernel, grid, dim3(256), 0, static_cast<cudaStream_t>(stream),
+                         reinterpret_cast<const __half*>(x), ldx, reinterpret_cast<__half*>(y), T, C));
+  count_launch();
+  return 0;
+}
+
+}  // extern "C"

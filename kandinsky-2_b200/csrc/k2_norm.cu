@@ -284,7 +284,7 @@ struct ApplyParams {
 // FOLD: the block derives mean / rstd of the groups it touches from the producers' partial sums itself (the work of
 // k2_gn_finalize, redone per block: worthwhile where an image has few row groups -- levels 1-3 of the U with one partial per
 // conv M tile -- because it removes a launch per GroupNorm).  Same fold as gn_finalize_kernel, warp-wide instead of block-wide.
-constexpr int FOLD_MAXG = 34;  // groups one block of 128 channels can touch: 128 / 4 + 2
+constexpr int FOLD_MAXG = 66;  // groups one block of 128 channels can touch: 128 / 2 + 2 (at least 2 channels per group)
 template <int RESAMPLE, bool SPATIAL, bool FOLD = false>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const ApplyParams p) {
   const int C = p.C0 + p.C1;
@@ -311,9 +311,24 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const ApplyParams p) {
         const int w = hi - lo;
         if (w <= 0) return;
         const float2* p0 = part + static_cast<long long>(n) * rgs * Cs + (lo - base);
-        for (int i = lane; i < rgs * w; i += 32) {
+        auto load = [&](int i) {
           const int rg = i / w;
-          const float2 t = __ldg(p0 + static_cast<long long>(rg) * Cs + (i - rg * w));
+          return __ldg(p0 + static_cast<long long>(rg) * Cs + (i - rg * w));
+        };
+        const int items = rgs * w;
+        int i = lane;
+        for (; i + 7 * 32 < items; i += 8 * 32) {  // 8 loads in flight per lane: the fold is pure L2 latency
+          float2 t[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) t[u] = load(i + u * 32);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            fs += t[u].x;
+            fq += t[u].y;
+          }
+        }
+        for (; i < items; i += 32) {
+          const float2 t = load(i);
           fs += t.x;
           fq += t.y;
         }
@@ -587,15 +602,14 @@ int k2_gn_apply(const void* src0, int C0, int ld0, const void* src1, int C1, int
   return 0;
 }
 
-// Round-2 candidate (not yet run on a GPU): same launch as k2_gn_apply, statistics folded from the producers' partials inside
-// the kernel.  Kept as a separate entry point so that the validated k2_gn_apply path above is textually what was tested.
+// Same launch as k2_gn_apply, statistics folded from the producers' partials inside the kernel (no k2_gn_finalize launch).
 int k2_gn_apply_fold(const void* src0, int C0, int ld0, const void* src1, int C1, int ld1, int NB, int H, int W, int groups,
                      const float* part0, int rg0, const float* part1, int rg1, float eps, const float* gamma,
                      const float* beta, const float* film, int film_ld, int act, int resample, void* y, int ldy, void* xres,
                      int ldx, k2_stream_t stream) {
   const int C = C0 + C1;
   K2_REQUIRE(src0 && y && gamma && beta, "gn_apply_fold: null pointer");
-  K2_REQUIRE(C0 % 8 == 0 && C1 % 8 == 0 && C % groups == 0 && C / groups >= 4, "gn_apply_fold: bad channel counts");
+  K2_REQUIRE(C0 % 8 == 0 && C1 % 8 == 0 && C % groups == 0 && C / groups >= 2, "gn_apply_fold: bad channel counts");
   K2_REQUIRE(resample >= 0 && resample <= 2, "gn_apply_fold: resample in {0,1,2}");
   K2_REQUIRE(resample != 1 || (H % 2 == 0 && W % 2 == 0), "gn_apply_fold: avg-pool needs even H, W");
   K2_REQUIRE(part0 && rg0 > 0 && (C1 == 0 || (src1 && part1 && rg1 > 0)), "gn_apply_fold: partial buffers");

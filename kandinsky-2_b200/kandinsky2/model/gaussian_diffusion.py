@@ -140,7 +140,7 @@ def _sampling_loop(schedule, model, shape, noise, model_kwargs, device, progress
     full, C, H, W = shape
     B = full // 2
     x_full = noise.float().to(device) if noise is not None else torch.randn(*shape, device=device)
-    x = x_full[:B].contiguous()
+    x = x_full[:B].clone()  # the caller's noise tensor is left untouched, like the reference
     coef, ts = schedule._tables(device)
     indices = list(range(schedule.num_timesteps))
     if init_step is not None:
@@ -253,7 +253,7 @@ class PLMSSampler(DDIMSampler):
         model = self.model
         device = next(model.parameters()).device
         x_full = x_T.float().to(device) if x_T is not None else torch.randn(batch_size, C, H, W, device=device)
-        x = x_full[:B].contiguous()
+        x = x_full[:B].clone()  # the caller's noise tensor is left untouched, like the reference
         step = FusedStep(model, B, H, W, dict(conditioning or {}), guidance_scale, cond_first, 1e30, 0)
         plan = step.plan
         a_t, a_p = self.ddim_alphas, self.ddim_alphas_prev
@@ -299,7 +299,7 @@ class FusedStep:
         if model._packed is None:
             model.finalize()
         cond = model.get_text_emb(**{k: model_kwargs.get(k) for k in ("full_emb", "pooled_emb", "image_emb")})
-        self.plan = model._plan(2 * B, H, W)
+        self.plan = model._plan(2 * B, H, W, cond["xf_out"].shape[1])
         self.plan.bind(cond)
         dev = self.plan.dev
         self.B = B

@@ -7,19 +7,27 @@ Nothing here computes with torch: forward() replays a pre-built launch list of C
 (include/k2b200.h) over pre-allocated NHWC fp16 buffers, captured in a CUDA graph per input geometry.
 
 Layer program per block (reference file:line in parentheses):
-  ResBlock (unet.py:193-220)       gn_stats -> gn_apply[GN32+SiLU (+2x up / avg-pool of h and x)] -> conv3x3
-                                   -> gn_stats -> gn_apply[GN32 * (1+scale) + shift, SiLU] -> conv3x3 with the
+  ResBlock (unet.py:193-220)       norm[GN32+SiLU (+2x up / avg-pool of h and x)] -> conv3x3
+                                   -> norm[GN32 * (1+scale) + shift, SiLU] -> conv3x3 with the
                                    skip folded in (identity: epilogue residual; 1x1: extra K segments, and
                                    the torch.cat of the up path is read as two sources)
-  AttentionBlock (unet.py:260-269) gn_stats -> gn_apply -> qkv GEMM -> attention_d64 (encoder K/V cached per
+  AttentionBlock (unet.py:260-269) norm -> qkv GEMM -> attention_d64 (encoder K/V cached per
                                    generation) -> proj GEMM + residual
+  norm = ONE k2_gn_apply_fold launch: the statistics come from partial sums the producing conv's epilogue wrote
   time/cond head                   timestep_embedding, time_embed MLP, one batched GEMM for all 36 emb_layers
 """
+import os
+
 import torch
 import torch.nn as nn
 
 from .. import ops
 from .._native import K2Error
+from ..launch_plan import LaunchPlan
+
+
+# the up ResBlocks' first conv (3x3 over the nearest-2x upsampled activations) as four 2x2 phase convolutions (ops.py)
+_UP2 = os.environ.get("K2_UP2", "1") != "0"
 
 
 def _topology(in_ch, mc, mult, nrb, attention_ds):
@@ -219,12 +227,14 @@ class Text2ImUNet(nn.Module):
                         pk["stem_w"] = ops.pack_stem_weight(self._param(p + "weight"))
                         pk["stem_b"] = f32(p + "bias")
                     elif layer[0] == "res":
-                        _, cin, cout, _ = layer
+                        _, cin, cout, updown = layer
                         d = dict(g1=f32(p + "in_layers.0.weight"), b1=f32(p + "in_layers.0.bias"),
                                  w1=ops.pack_conv_weight(self._param(p + "in_layers.2.weight")),
                                  c1=f32(p + "in_layers.2.bias"),
                                  g2=f32(p + "out_layers.0.weight"), b2=f32(p + "out_layers.0.bias"),
                                  c2=f32(p + "out_layers.3.bias"), film_off=off)
+                        if updown == "up":  # conv over the nearest-2x upsampled h as four 2x2 phase convs (ops.py)
+                            d["w1u"] = ops.pack_conv_weight_up2(self._param(p + "in_layers.2.weight"))
                         w2 = ops.pack_conv_weight(self._param(p + "out_layers.3.weight"))
                         if cin != cout:
                             d["wskip_raw"] = self._param(p + "skip_connection.weight").detach()
@@ -319,7 +329,7 @@ class Text2ImUNet(nn.Module):
             self.finalize()
         cond = self.get_text_emb(full_emb=full_emb, pooled_emb=pooled_emb, image_emb=image_emb)
         N, _, H, W = x.shape
-        plan = self._plan(N, H, W)
+        plan = self._plan(N, H, W, cond["xf_out"].shape[1])
         plan.bind(cond)
         plan.x_in.copy_(x)
         plan.t_in.copy_(timesteps)
@@ -331,10 +341,10 @@ class Text2ImUNet(nn.Module):
 
     _inpainting = False
 
-    def _plan(self, N, H, W):
-        key = (N, H, W)
+    def _plan(self, N, H, W, ctx):
+        key = (N, H, W, ctx)
         if key not in self._plans:
-            self._plans[key] = _Plan(self, N, H, W)
+            self._plans[key] = _Plan(self, N, H, W, ctx)
         return self._plans[key]
 
 
@@ -349,15 +359,15 @@ class InpaintText2ImUNet(Text2ImUNet):
         super().__init__(*args, **kwargs)
 
 
-class _Plan:
+class _Plan(LaunchPlan):
     """Static launch list + buffers of one forward at a fixed (N, H, W); replayed eagerly or as a CUDA graph."""
 
-    def __init__(self, model, N, H, W):
-        self.m = model
-        self.N, self.H, self.W = N, H, W
+    def __init__(self, model, N, H, W, ctx):
         pk = model._packed
         dev = pk["te0_w"].device
-        self.dev = dev
+        super().__init__(dev, N)
+        self.m = model
+        self.N, self.H, self.W, self.ctx = N, H, W, ctx
         f32 = dict(device=dev, dtype=torch.float32)
         lat = model._latent_channels if model._inpainting else model.in_channels
         self.x_in = torch.zeros(N, lat, H, W, **f32)
@@ -368,24 +378,8 @@ class _Plan:
         self.out = torch.empty(N, model.out_channels, H, W, **f32)
         self.xf_proj = torch.zeros(N, 4 * model.model_channels, **f32)
         self.enc_kv = {}
-        self._parts = {}
-        self._scratch = {}
-        self.steps = []
-        self.graph = None
         self._bound = None
         self._build()
-
-    # buffers -----------------------------------------------------------------------------------
-    def _tmp(self, slot, *shape, dtype=torch.float16):
-        """Scratch reused by every block that asks for the same (slot, shape): all launches are stream-ordered
-        and a block's temporaries are dead when the next block starts."""
-        key = (slot, dtype) + tuple(shape)
-        if key not in self._scratch:
-            self._scratch[key] = torch.empty(*shape, device=self.dev, dtype=dtype)
-        return self._scratch[key]
-
-    def _new(self, *shape, dtype=torch.float16):
-        return torch.empty(*shape, device=self.dev, dtype=dtype)
 
     def bind(self, cond):
         """Point the plan at this generation's conditioning (copied into the plan's static buffers)."""
@@ -440,10 +434,8 @@ class _Plan:
             for li, layer in enumerate(blk):
                 h = self._layer(f"output_blocks.{bi}.{li}.", layer, h, skip if li == 0 else None)
         # head: GN32 + SiLU + conv3x3 -> fp32 NCHW (unet.py:559-563; text2im_model2_1.py:101-102)
-        st = self._new(N, 32, 2, dtype=torch.float32)
         hn = self._tmp("h1", *h.shape)
-        self._stats(h, None, st)
-        S(lambda h=h: ops.gn_apply(h, None, st, pk["out_g"], pk["out_b"], act=1, y=hn), "gn_apply")
+        self._norm(h, None, pk["out_g"], pk["out_b"], hn)
         S(lambda: ops.conv_gemm([(hn, 9)], pk["out_w"], m.out_channels, bias=pk["out_c"], out=self.out, out_mode=1),
           "conv_gemm", 2 * N * H * W * m.out_channels * 9 * h.shape[-1])
 
@@ -454,24 +446,29 @@ class _Plan:
             d = pk["res"][p]
             Hi, Wi = a.shape[1], a.shape[2]
             Ho, Wo = (Hi, Wi) if updown is None else ((Hi // 2, Wi // 2) if updown == "down" else (Hi * 2, Wi * 2))
-            st1 = self._new(N, 32, 2, dtype=torch.float32)
-            st2 = self._new(N, 32, 2, dtype=torch.float32)
             h1 = self._tmp("h1", N, Ho, Wo, cin)
             h2 = self._tmp("h2", N, Ho, Wo, cout)
             h3 = self._tmp("h3", N, Ho, Wo, cout)
             o = self._new(N, Ho, Wo, cout)
             film = self.film[:, d["film_off"]:d["film_off"] + 2 * cout]
-            self._stats(a, b, st1)
+            flops1 = 2 * N * Ho * Wo * cout * 9 * cin  # of the reference graph (the up2 path executes 4/9 of them)
             if updown is None:
                 xres = None
-                S(lambda: ops.gn_apply(a, b, st1, d["g1"], d["b1"], act=1, y=h1), "gn_apply")
+                self._norm(a, b, d["g1"], d["b1"], h1)
+                self._conv([(h1, 9)], d["w1"], cout, h2, flops1, bias=d["c1"], part_slot="part_h2")
+            elif updown == "up" and _UP2:
+                # unet.py:198-203: h = conv(upsample(silu(norm(x)))), x = upsample(x).  The upsampled h is never written: the
+                # conv runs over the low-resolution h as four 2x2 phase convolutions (k2b200.h, taps = 4)
+                xres = self._tmp("xres", N, Ho, Wo, cin)
+                h1s = self._tmp("h1s", N, Hi, Wi, cin)
+                self._norm(a, b, d["g1"], d["b1"], h1s)
+                S(lambda: ops.upsample2x(a, out=xres), "upsample")
+                self._conv([(h1s, 4)], d["w1u"], cout, h2, flops1, bias=d["c1"], part_slot="part_h2")
             else:
                 xres = self._tmp("xres", N, Ho, Wo, cin)
-                S(lambda: ops.gn_apply(a, b, st1, d["g1"], d["b1"], act=1, resample=1 if updown == "down" else 2,
-                                       y=h1, xres=xres), "gn_apply")
-            self._conv([(h1, 9)], d["w1"], cout, h2, 2 * N * Ho * Wo * cout * 9 * cin, bias=d["c1"], part_slot="part_h2")
-            self._stats(h2, None, st2)
-            S(lambda: ops.gn_apply(h2, None, st2, d["g2"], d["b2"], film=film, act=1, y=h3), "gn_apply")
+                self._norm(a, b, d["g1"], d["b1"], h1, resample=1 if updown == "down" else 2, xres=xres)
+                self._conv([(h1, 9)], d["w1"], cout, h2, flops1, bias=d["c1"], part_slot="part_h2")
+            self._norm(h2, None, d["g2"], d["b2"], h3, film=film)
             if cin == cout:
                 if b is not None:
                     raise NotImplementedError("identity skip over a concatenated input")
@@ -492,112 +489,14 @@ class _Plan:
         heads = ch // 64
         _, Hh, Ww, _ = a.shape
         T = Hh * Ww
-        st = self._new(N, 32, 2, dtype=torch.float32)
         xn = self._tmp("h1", N, Hh, Ww, ch)
         qkv = self._tmp("qkv", N, T, 3 * ch)
         att = self._tmp("att", N, T, ch)
         o = self._new(N, Hh, Ww, ch)
-        ctx = self.m.cache["xf_out"].shape[1]
-        enc = self._new(N, ctx, 2 * ch)
+        enc = self._new(N, self.ctx, 2 * ch)
         self.enc_kv[p] = enc
-        self._stats(a, None, st)
-        S(lambda: ops.gn_apply(a, None, st, d["g"], d["b"], act=0, y=xn), "gn_apply")
-        S(lambda: ops.gemm_rows(xn.view(N, T, ch), d["wqkv"], 3 * ch, bias=d["bqkv"], out=qkv), "conv_gemm", 2 * N * T * 3 * ch * ch)
-        S(lambda: ops.attention_d64(qkv, heads, enc, out=att), "attention", 4 * N * T * (T + ctx) * ch)
+        self._norm(a, None, d["g"], d["b"], xn, act=0)
+        self._gemm(xn.view(N, T, ch), d["wqkv"], 3 * ch, qkv, 2 * N * T * 3 * ch * ch, bias=d["bqkv"])
+        S(lambda: ops.attention_d64(qkv, heads, enc, out=att), "attention", 4 * N * T * (T + self.ctx) * ch)
         self._conv([(att.view(N, Hh, Ww, ch), 1)], d["wproj"], ch, o, 2 * N * T * ch * ch, bias=d["bproj"], residual=a)
         return o
-
-    def _add(self, fn, kind="misc", flops=0):
-        """Record a launch AND run it once now (build = eager trace), so that data-dependent plan decisions -- did the
-        conv epilogue emit GroupNorm partials for this geometry? -- are known when the next step is recorded."""
-        fn()
-        self.steps.append((fn, kind, flops))
-
-    def _conv(self, srcs, w, cout, out, flops, bias=None, residual=None, want_stats=True, part_slot=None):
-        """conv_gemm step; with want_stats the epilogue also writes GroupNorm partial statistics of `out` (when the
-        launch geometry allows it: k2b200.h), remembered in self._parts for the consumer's _stats()."""
-        N = self.N
-        part = None
-        if want_stats:
-            n = ops.gn_part_floats(N, out.shape[1], out.shape[2], cout)
-            part = self._tmp(part_slot, n, dtype=torch.float32) if part_slot else self._new(n, dtype=torch.float32)
-        info = [0] * 7
-        self._add(lambda: ops.conv_gemm(srcs, w, cout, bias=bias, residual=residual, out=out, gn_part=part, info=info),
-                  "conv_gemm", flops)
-        if want_stats and info[5]:
-            self._parts[out.data_ptr()] = (part, info[6] // N)
-        else:
-            self._parts.pop(out.data_ptr(), None)
-
-    def _stats(self, a, b, st):
-        """GroupNorm statistics of [a | b]: from the producers' fused partials when both have them, else a read pass."""
-        pa = self._parts.get(a.data_ptr())
-        pb = self._parts.get(b.data_ptr()) if b is not None else None
-        HW = a.shape[1] * a.shape[2]
-        if pa is not None and (b is None or pb is not None):
-            c1 = b.shape[-1] if b is not None else 0
-            self._add(lambda: ops.gn_finalize(pa[0], a.shape[-1], pb[0] if pb else None, c1, self.N, pa[1], HW, st,
-                                              rg1=pb[1] if pb else None), "gn_finalize")
-        else:
-            self._add(lambda: ops.gn_stats(a, b, stats=st), "gn_stats")
-
-    # execution ---------------------------------------------------------------------------------
-    def launch(self):
-        for fn, _, _ in self.steps:
-            fn()
-
-    def profile_detail(self, reps=3):
-        """[(kind, flops, ms)] per launch, averaged over `reps` eager passes (same method as profile())."""
-        acc = [0.0] * len(self.steps)
-        for _ in range(reps):
-            evs = []
-            torch.cuda.synchronize()
-            torch.cuda._sleep(int(4e7))
-            for fn, kind, flops in self.steps:
-                s = torch.cuda.Event(enable_timing=True)
-                e = torch.cuda.Event(enable_timing=True)
-                s.record()
-                fn()
-                e.record()
-                evs.append((s, e))
-            torch.cuda.synchronize()
-            for i, (s, e) in enumerate(evs):
-                acc[i] += s.elapsed_time(e) / reps
-        return [(k, f, ms) for (_, k, f), ms in zip(self.steps, acc)]
-
-    def profile(self, reps=3):
-        """Per-kernel-family device time of one eager pass (CUDA events around every launch; a long sleep kernel
-        is queued first so the host runs ahead and the events are not skewed by launch latency).
-        -> {kind: dict(ms=..., launches=..., flops=...)} averaged over `reps` passes."""
-        agg = {}
-        for _ in range(reps):
-            evs = []
-            torch.cuda.synchronize()
-            torch.cuda._sleep(int(4e7))
-            for fn, kind, flops in self.steps:
-                s = torch.cuda.Event(enable_timing=True)
-                e = torch.cuda.Event(enable_timing=True)
-                s.record()
-                fn()
-                e.record()
-                evs.append((s, e, kind, flops))
-            torch.cuda.synchronize()
-            for s, e, kind, flops in evs:
-                a = agg.setdefault(kind, dict(ms=0.0, launches=0, flops=0))
-                a["ms"] += s.elapsed_time(e) / reps
-                a["launches"] += 1.0 / reps
-                a["flops"] += flops / reps
-        return agg
-
-    def run(self, use_graph):
-        if not use_graph:
-            self.launch()
-            return
-        if self.graph is None:
-            self.launch()  # warm-up: one-time cudaFuncSetAttribute calls are not capturable
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self.launch()
-            self.graph = g
-        self.graph.replay()

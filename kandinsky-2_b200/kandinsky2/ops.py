@@ -55,6 +55,33 @@ def pack_conv_weight(w, split=None):
     return torch.cat(segs, dim=1).to(torch.float16).contiguous()
 
 
+_UP2_TAPS = {0: ((0,), (1, 2)), 1: ((0, 1), (2,))}  # output parity a -> 3x3 kernel rows feeding source offsets (a - 1, a)
+
+
+def pack_conv_weight_up2(w):
+    """[Cout, Cin, 3, 3] -> fp16 [Cout, 16 * pad64(Cin)] for a `taps = 4` source of k2_conv_gemm: the 3x3 convolution over the
+    nearest-2x upsampled input, as four 2x2 convolutions over the input itself, one per output parity (a, b).  Output pixel
+    (2y + a, 2x + b) sees upsampled rows 2y + a + ky - 1, i.e. source rows y + floor((a + ky - 1) / 2): the kernel rows that
+    land on the same source row are summed (fp32) before the fp16 rounding.  k = ((a * 2 + b) * 4 + ty * 2 + tx) * pad64(Cin) + c,
+    source offset (dy, dx) = (ty + a - 1, tx + b - 1).  2.25x fewer MACs than convolving the upsampled tensor, which is never
+    materialised (unet.py:67-77 Upsample + :199-203 h_upd; movq_modules.py:93-97)."""
+    w = w.detach().float()
+    cout, cin = w.shape[:2]
+    blocks = []
+    for a in (0, 1):
+        for b in (0, 1):
+            for ty in (0, 1):
+                for tx in (0, 1):
+                    acc = torch.zeros(cout, cin, dtype=torch.float32, device=w.device)
+                    for ky in _UP2_TAPS[a][ty]:
+                        for kx in _UP2_TAPS[b][tx]:
+                            acc += w[:, :, ky, kx]
+                    if _pad64(cin) != cin:
+                        acc = torch.nn.functional.pad(acc, (0, _pad64(cin) - cin))
+                    blocks.append(acc)
+    return torch.cat(blocks, dim=1).to(torch.float16).contiguous()
+
+
 def pad_rows(wp, rows):
     if wp.shape[0] >= rows:
         return wp
@@ -76,12 +103,19 @@ def _workspace(dev):
     return buf
 
 
-def conv_gemm(srcs, w_packed, cout, bias=None, residual=None, out=None, out_mode=0, geom=None, gn_part=None, info=None):
-    """srcs: list of (tensor NHWC fp16 [NB,H,W,C], taps).  Returns fp16 [NB,H,W,cout] (out_mode 0) or
-    fp32 NCHW [NB,cout,H,W] (out_mode 1).  geom=(NB,H,W) overrides the geometry (GEMM on flat rows)."""
+def conv_gemm(srcs, w_packed, cout, bias=None, residual=None, out=None, out_mode=0, geom=None, gn_part=None, info=None,
+              cfg=None, w_batch_stride=0):
+    """srcs: list of (tensor NHWC fp16 [NB,H,W,C], taps); taps = 9 (3x3), 1 (1x1) or 4 (single source: 3x3 over its nearest-2x
+    upsampling, weights from pack_conv_weight_up2, output [NB,2H,2W,cout]).  Returns fp16 [NB,H,W,cout] (out_mode 0) or
+    fp32 NCHW [NB,cout,H,W] (out_mode 1).  geom=(NB,H,W) overrides the geometry (GEMM on flat rows).
+    cfg = (N tile, pair mode, splits, epilogue sets) overrides the library's choice (k2_conv_gemm_cfg; 0 = auto).
+    w_batch_stride > 0: batched GEMM, image n uses the weight matrix at w_packed + n * w_batch_stride elements (w_packed is then
+    any fp16 tensor whose data_ptr() is matrix 0, shape[0] / shape[1] / stride(0) = rows / K / row stride of ONE matrix)."""
     lib = nat.load()
     t0 = srcs[0][0]
     NB, H, W = geom if geom is not None else t0.shape[:3]
+    if srcs[0][1] == 4:  # 3x3 conv over the nearest-2x upsampling of the source: geometry = the OUTPUT's
+        H, W = 2 * H, 2 * W
     arr = (K2ConvSrc * len(srcs))()
     for i, (t, taps) in enumerate(srcs):
         assert t.dtype == torch.float16 and t.is_cuda
@@ -99,10 +133,11 @@ def conv_gemm(srcs, w_packed, cout, bias=None, residual=None, out=None, out_mode
     assert w_packed.dtype == torch.float16 and w_packed.stride(1) == 1
     ws = _workspace(t0.device)
     _info = (ctypes.c_int * 7)()
-    check(lib.k2_conv_gemm(arr, len(srcs), NB, H, W, ptr(w_packed), w_packed.shape[0], w_packed.shape[1],
-                           w_packed.stride(0), cout,
-                           ptr(bias), ptr(residual), ldr, ptr(out), ldo, out_mode, ptr(ws), ws.numel(), ptr(gn_part),
-                           _info, stream_ptr()))
+    _cfg = (ctypes.c_int * 4)(*cfg) if cfg is not None else None
+    check(lib.k2_conv_gemm_cfg(arr, len(srcs), NB, H, W, ptr(w_packed), w_packed.shape[0], w_packed.shape[1],
+                               w_packed.stride(0), cout,
+                               ptr(bias), ptr(residual), ldr, ptr(out), ldo, out_mode, ptr(ws), ws.numel(), ptr(gn_part),
+                               _info, _cfg, int(w_batch_stride), stream_ptr()))
     if info is not None:
         info[:] = list(_info)
     return out
@@ -117,7 +152,7 @@ def conv_plan(NB, H, W, taps, ktot, cout, out_mode=0, workspace_bytes=1 << 28, w
     return dict(zip(keys, list(info)))
 
 
-def gemm_rows(x, w_packed, cout, bias=None, residual=None, out=None):
+def gemm_rows(x, w_packed, cout, bias=None, residual=None, out=None, cfg=None, info=None):
     """x: fp16 [..., K] rows -> fp16 [..., cout]; one 1x1 'conv' over M = prod(leading dims) rows."""
     lead = x.shape[:-1]
     M = 1
@@ -133,7 +168,7 @@ def gemm_rows(x, w_packed, cout, bias=None, residual=None, out=None):
     r3 = None
     if residual is not None:
         r3 = residual.as_strided((1, 1, M, cout), (0, 0, residual.stride(-2), 1))
-    conv_gemm([(x3, 1)], w_packed, cout, bias=bias, residual=r3, out=o3, geom=(1, 1, M))
+    conv_gemm([(x3, 1)], w_packed, cout, bias=bias, residual=r3, out=o3, geom=(1, 1, M), cfg=cfg, info=info)
     return out
 
 
@@ -347,11 +382,11 @@ def vq_argmin(z, codebook):
     return idx
 
 
-def pointwise_nchw_f32(x, w, b):
+def pointwise_nchw_f32(x, w, b, out=None):
     lib = nat.load()
     NB, Ci, H, W = x.shape
     Co = w.shape[0]
-    y = torch.empty((NB, Co, H, W), dtype=torch.float32, device=x.device)
+    y = out if out is not None else torch.empty((NB, Co, H, W), dtype=torch.float32, device=x.device)
     check(lib.k2_pointwise_nchw_f32(ptr(x), ptr(w), ptr(b), ptr(y), NB, Ci, Co, H * W, stream_ptr()))
     return y
 
@@ -366,11 +401,12 @@ def upsample2x(x, out=None):
     return out
 
 
-def subsample2(x, oy=1, ox=1):
+def subsample2(x, oy=1, ox=1, out=None):
     """fp16 NHWC [NB,H,W,C] -> [NB,H/2,W/2,C] taking pixels (2y+oy, 2x+ox)."""
     lib = nat.load()
     NB, H, W, C = x.shape
-    out = torch.empty((NB, H // 2, W // 2, C), dtype=torch.float16, device=x.device)
+    if out is None:
+        out = torch.empty((NB, H // 2, W // 2, C), dtype=torch.float16, device=x.device)
     check(lib.k2_subsample2_nhwc(ptr(x), _row_stride(x), ptr(out), _row_stride(out), NB, H, W, C, oy, ox, stream_ptr()))
     return out
 
@@ -385,18 +421,41 @@ def softmax_rows(x, scale, out=None):
     return out
 
 
-def nchw_to_nhwc_f32(x):
+def sn_apply(x, stats, gamma, beta, zq, sn_w, act=1, groups=32, y=None):
+    """MoVQ SpatialNorm (+ swish): x fp16 NHWC [NB,H,W,C], zq fp32 [NB,zh,zw,4], sn_w fp32 [C,10] -> fp16 NHWC (k2_sn_apply)."""
+    lib = nat.load()
+    NB, H, W, C = x.shape
+    if y is None:
+        y = torch.empty((NB, H, W, C), dtype=torch.float16, device=x.device)
+    check(lib.k2_sn_apply(ptr(x), C, _row_stride(x), NB, H, W, groups, ptr(stats), ptr(gamma), ptr(beta), ptr(zq),
+                          zq.shape[1], zq.shape[2], ptr(sn_w), act, ptr(y), _row_stride(y), stream_ptr()))
+    return y
+
+
+def transpose_f16(x, out=None):
+    """fp16 [B, T, C] (row-strided) -> contiguous [B, C, T]."""
+    lib = nat.load()
+    B, T, C = x.shape
+    assert x.stride(-1) == 1 and x.stride(0) == T * x.stride(1)
+    if out is None:
+        out = torch.empty((B, C, T), dtype=torch.float16, device=x.device)
+    check(lib.k2_transpose_f16(ptr(x), x.stride(1), ptr(out), B, T, C, stream_ptr()))
+    return out
+
+
+def nchw_to_nhwc_f32(x, out=None):
     lib = nat.load()
     NB, C, H, W = x.shape
-    y = torch.empty((NB, H, W, C), dtype=torch.float32, device=x.device)
+    y = out if out is not None else torch.empty((NB, H, W, C), dtype=torch.float32, device=x.device)
     check(lib.k2_nchw_to_nhwc_f32(ptr(x), ptr(y), NB, C, H, W, stream_ptr()))
     return y
 
 
-def images_to_u8(x, crop_h, crop_w):
+def images_to_u8(x, crop_h, crop_w, out=None):
     lib = nat.load()
     NB, C, H, W = x.shape
-    out = torch.empty((NB, crop_h, crop_w, C), dtype=torch.uint8, device=x.device)
+    if out is None:
+        out = torch.empty((NB, crop_h, crop_w, C), dtype=torch.uint8, device=x.device)
     check(lib.k2_images_to_u8(ptr(x), ptr(out), NB, C, H, W, crop_h, crop_w, stream_ptr()))
     return out
 

@@ -5,20 +5,24 @@ with the decoder of kandinsky2/vqgan/movq_modules.py:228-357.  state_dict keys/s
 `decoder.*`, `post_quant_conv.*` and `quantize.embedding.weight` (the encoder / quant_conv halves of a reference
 checkpoint are accepted and ignored: the image->latent direction is SURVEY.md 8f rank 1, not on this path).
 
-Kernel program (activations NHWC fp16, fp32 accumulate):
-  SpatialNorm + swish      gn_stats + gn_apply with the 4-channel latent modulation computed on the fly
-                           (movq_modules.py:61-68: no [B,C,H,W] conv_y/conv_b tensors, no interpolate)
+decode / encode at a fixed geometry are static launch plans (kandinsky2/launch_plan.py) over pre-allocated buffers, replayed as
+ONE CUDA graph; nothing loops over images on the host.  Kernel program (activations NHWC fp16, fp32 accumulate):
+  SpatialNorm + swish      statistics from partial sums the producing conv's epilogue wrote (k2_gn_finalize, no read of the
+                           tensor) + k2_sn_apply: GroupNorm and the two 4 -> C latent modulations folded into 10 coefficients
+                           per channel held in registers (movq_modules.py:61-68: no conv_y / conv_b tensors, no interpolate)
   conv3x3 / nin_shortcut   k2_conv_gemm (shortcut folded in as extra K segment / epilogue residual)
-  AttnBlock (1 head, d=C)  q,k in one GEMM; scores = q k^T with the k rows as a strided B operand; row softmax;
-                           P V with V^T produced directly by a GEMM (W_v as the A operand); v bias added after PV
-                           (softmax rows sum to 1); proj GEMM + residual   (movq_modules.py:201-225)
-  Upsample                 nearest 2x copy kernel + conv3x3 (movq_modules.py:93-97)
+  AttnBlock (1 head, d=C)  q,k,v in one GEMM; scores = q k^T as ONE batched GEMM (image n's k rows are its B operand);
+                           row softmax in place; P V as one batched GEMM against the transposed values; proj GEMM + residual
+                           (movq_modules.py:201-225)
+  Upsample                 no upsampled tensor: conv3x3(nearest_2x(h)) = four 2x2 phase convolutions over h itself
+                           (k2_conv_gemm taps = 4, 2.25x fewer MACs; movq_modules.py:93-97)
 """
 import torch
 import torch.nn as nn
 
 from .. import ops
 from .._native import K2Error
+from ..launch_plan import LaunchPlan
 
 
 class _Node(nn.Module):
@@ -66,6 +70,8 @@ class MOVQ(nn.Module):
         self.ddconfig = dict(ddconfig)
         self.n_embed, self.embed_dim = n_embed, embed_dim
         self._packed = None
+        self._plans = {}
+        self.use_cuda_graph = True
         dd = self.ddconfig
         kw = dict(device=device, dtype=param_dtype)
         zc = embed_dim
@@ -155,11 +161,11 @@ class MOVQ(nn.Module):
     def load_state_dict(self, state_dict, strict=True, assign=False):
         """Same keys as the reference's MOVQ (autoencoder.py:167-174); training-only `loss.*` entries are dropped."""
         sd = {k: v for k, v in state_dict.items() if not k.startswith("loss.")}
-        self._packed = None
+        self._packed, self._plans = None, {}
         return super().load_state_dict(sd, strict=strict, assign=assign)
 
     def _apply(self, fn, recurse=True):
-        self._packed = None
+        self._packed, self._plans = None, {}
         return super()._apply(fn, recurse)
 
     @torch.no_grad()
@@ -175,7 +181,7 @@ class MOVQ(nn.Module):
                 prm.normal_(0.0, 1.0, generator=g)
             else:
                 prm.normal_(0.0, prm[0].numel() ** -0.5, generator=g)
-        self._packed = None
+        self._packed, self._plans = None, {}
         return self
 
     def _get(self, key):
@@ -209,9 +215,8 @@ class MOVQ(nn.Module):
 
         def att_common(p):
             pc = ops.pack_conv_weight
-            return dict(wqk=torch.cat([pc(self._get(p + "q.weight")), pc(self._get(p + "k.weight"))], 0).contiguous(),
-                        bqk=torch.cat([f32(p + "q.bias"), f32(p + "k.bias")]).contiguous(),
-                        wv=pc(self._get(p + "v.weight")), bv=f32(p + "v.bias"),
+            return dict(wqkv=torch.cat([pc(self._get(p + n + ".weight")) for n in ("q", "k", "v")], 0).contiguous(),
+                        bqkv=torch.cat([f32(p + n + ".bias") for n in ("q", "k", "v")]).contiguous(),
                         wp=pc(self._get(p + "proj_out.weight")), bp=f32(p + "proj_out.bias"))
 
         def att(p):
@@ -233,7 +238,7 @@ class MOVQ(nn.Module):
                 if lv["attn"]:
                     pk[p + f"attn.{bi}"] = att(p + f"attn.{bi}.")
             if lv["up"]:
-                pk[p + "up_w"] = ops.pack_conv_weight(self._get(p + "upsample.conv.weight"))
+                pk[p + "up_w"] = ops.pack_conv_weight_up2(self._get(p + "upsample.conv.weight"))
                 pk[p + "up_b"] = f32(p + "upsample.conv.bias")
         # ---- encoder
         def gn(p):
@@ -279,40 +284,17 @@ class MOVQ(nn.Module):
         pk["out_b"] = f32("decoder.conv_out.bias")
         pk["codebook"] = f32("quantize.embedding.weight")
         self._packed = pk
+        self._plans = {}
         return self
 
     # ------------------------------------------------------------------------------------------
-    def _sn_act(self, x, zq, n, act):
-        """SpatialNorm (decoder: zq given) or plain GroupNorm(32, eps 1e-6) (encoder: zq None), optional swish."""
-        st = ops.gn_stats(x, None, groups=32, eps=1e-6)
-        if zq is None:
-            return ops.gn_apply(x, None, st, n["g"], n["b"], act=act)
-        return ops.gn_apply(x, None, st, n["g"], n["b"], act=act, zq=zq, sn_w=n["w"])
-
-    def _res(self, x, zq, d):
-        cout = d["c1"].shape[0]
-        h = ops.conv_gemm([(self._sn_act(x, zq, d["n1"], 1), 9)], d["w1"], cout, bias=d["c1"])
-        h = self._sn_act(h, zq, d["n2"], 1)
-        if x.shape[-1] == cout:
-            return ops.conv_gemm([(h, 9)], d["w2"], cout, bias=d["c2"], residual=x)
-        return ops.conv_gemm([(h, 9), (x, 1)], d["w2"], cout, bias=d["c2"])
-
-    def _attn(self, x, zq, d):
-        B, H, W, C = x.shape
-        T = H * W
-        if T % 64:
-            raise K2Error("MoVQ attention needs h*w to be a multiple of 64 (latents are multiples of 8 px)")
-        hn = self._sn_act(x, zq, d["n"], 0).view(B, T, C)
-        qk = ops.gemm_rows(hn, d["wqk"], 2 * C, bias=d["bqk"])
-        o = torch.empty((B, T, C), dtype=torch.float16, device=x.device)
-        scores = torch.empty((T, T), dtype=torch.float16, device=x.device)
-        vT = torch.empty((C, T), dtype=torch.float16, device=x.device)
-        for b in range(B):
-            ops.gemm_rows(d["wv"], hn[b], T, out=vT)                      # V^T = W_v hn^T   [C, T]
-            ops.gemm_rows(qk[b, :, :C], qk[b, :, C:], T, out=scores)      # q k^T            [T, T]
-            ops.softmax_rows(scores, C ** -0.5, out=scores)
-            ops.gemm_rows(scores, vT, C, bias=d["bv"], out=o[b])          # P V (+ b_v)      [T, C]
-        return ops.gemm_rows(o, d["wp"], C, bias=d["bp"], residual=x.view(B, T, C)).view(B, H, W, C)
+    def _plan(self, mode, B, H, W):
+        if self._packed is None:
+            self.finalize()
+        key = (mode, B, H, W)
+        if key not in self._plans:
+            self._plans[key] = _MovqPlan(self, mode, B, H, W)
+        return self._plans[key]
 
     @torch.no_grad()
     def decode(self, quant, out_dtype=None):
@@ -320,28 +302,11 @@ class MOVQ(nn.Module):
         the input (the reference decodes in fp16 when the pipeline is fp16) unless out_dtype is given."""
         if not quant.is_cuda:
             raise K2Error("k2b200 MOVQ.decode: input must be a CUDA tensor (no CPU fallback)")
-        if self._packed is None:
-            self.finalize()
-        pk = self._packed
-        q32 = quant.float().contiguous()
-        zq = ops.nchw_to_nhwc_f32(q32)
-        z2 = ops.pointwise_nchw_f32(q32, pk["pq_w"], pk["pq_b"])
-        h = ops.gemm_rows(ops.stem_im2col(z2), pk["in_w"], self.block_in, bias=pk["in_b"])
-        h = self._res(h, zq, pk["mid1"])
-        h = self._attn(h, zq, pk["mida"])
-        h = self._res(h, zq, pk["mid2"])
-        for lv in self.levels:
-            p = f"decoder.up.{lv['level']}."
-            for bi in range(len(lv["blocks"])):
-                h = self._res(h, zq, pk[p + f"block.{bi}"])
-                if lv["attn"]:
-                    h = self._attn(h, zq, pk[p + f"attn.{bi}"])
-            if lv["up"]:
-                h = ops.conv_gemm([(ops.upsample2x(h), 9)], pk[p + "up_w"], lv["ch"], bias=pk[p + "up_b"])
-        h = self._sn_act(h, zq, pk["out_n"], 1)
-        img = ops.conv_gemm([(h, 9)], pk["out_w"], self.ddconfig["out_ch"], bias=pk["out_b"], out_mode=1)
+        plan = self._plan("decode", quant.shape[0], quant.shape[2], quant.shape[3])
+        plan.x_in.copy_(quant)
+        plan.run(self.use_cuda_graph)
         dt = out_dtype or (quant.dtype if quant.is_floating_point() else torch.float32)
-        return img if dt == torch.float32 else img.to(dt)
+        return plan.out.clone() if dt == torch.float32 else plan.out.to(dt)
 
     @torch.no_grad()
     def encode(self, x):
@@ -350,32 +315,20 @@ class MOVQ(nn.Module):
         the stride-1 'same' conv on tensor cores followed by taking the odd pixels."""
         if not x.is_cuda:
             raise K2Error("k2b200 MOVQ.encode: input must be a CUDA tensor (no CPU fallback)")
-        if self._packed is None:
-            self.finalize()
-        pk = self._packed
-        h = ops.gemm_rows(ops.stem_im2col(x.float().contiguous()), pk["e_in_w"], self.ddconfig["ch"], bias=pk["e_in_b"])
-        for lv in self.enc_levels:
-            p = f"encoder.down.{lv['level']}."
-            for bi in range(len(lv["blocks"])):
-                h = self._res(h, None, pk[p + f"block.{bi}"])
-                if lv["attn"]:
-                    h = self._attn(h, None, pk[p + f"attn.{bi}"])
-            if lv["down"]:
-                full = ops.conv_gemm([(h, 9)], pk[p + "down_w"], lv["ch"], bias=pk[p + "down_b"])
-                h = ops.subsample2(full, 1, 1)
-        h = self._res(h, None, pk["e_mid1"])
-        h = self._attn(h, None, pk["e_mida"])
-        h = self._res(h, None, pk["e_mid2"])
-        h = self._sn_act(h, None, pk["e_out_n"], 1)
-        zc_out = pk["e_out_b"].shape[0]
-        z = ops.conv_gemm([(h, 9)], pk["e_out_w"], zc_out, bias=pk["e_out_b"], out_mode=1)
-        return ops.pointwise_nchw_f32(z, pk["qc_w"], pk["qc_b"])
+        plan = self._plan("encode", x.shape[0], x.shape[2], x.shape[3])
+        plan.x_in.copy_(x)
+        plan.run(self.use_cuda_graph)
+        return plan.out.clone()
 
     @torch.no_grad()
     def decode_to_uint8(self, quant, crop_h=None, crop_w=None):
         """decode + process_images (kandinsky2/utils.py:57-70) fused on the device -> uint8 NHWC (cropped)."""
-        img = self.decode(quant, out_dtype=torch.float32)
-        return ops.images_to_u8(img, crop_h or img.shape[2], crop_w or img.shape[3])
+        if not quant.is_cuda:
+            raise K2Error("k2b200 MOVQ.decode: input must be a CUDA tensor (no CPU fallback)")
+        plan = self._plan("decode", quant.shape[0], quant.shape[2], quant.shape[3])
+        plan.x_in.copy_(quant)
+        plan.run(self.use_cuda_graph)
+        return ops.images_to_u8(plan.out, crop_h or plan.out.shape[2], crop_w or plan.out.shape[3])
 
     @torch.no_grad()
     def quantize_indices(self, z):
@@ -384,3 +337,152 @@ class MOVQ(nn.Module):
             self.finalize()
         zf = ops.nchw_to_nhwc_f32(z.float().contiguous()).reshape(-1, self.embed_dim)
         return ops.vq_argmin(zf, self._packed["codebook"])
+
+
+class _MovqPlan(LaunchPlan):
+    """Launch plan of MOVQ.decode (mode "decode": H, W = latent size) or MOVQ.encode ("encode": H, W = image size) for B
+    images.  x_in (fp32 NCHW) is the static input, out (fp32 NCHW) the static output."""
+    EPS = 1e-6  # GroupNorm eps of the VQGAN blocks (movq_modules.py:48, vqgan_blocks.py:34)
+
+    def __init__(self, model, mode, B, H, W):
+        pk = model._packed
+        super().__init__(pk["pq_w"].device, B)
+        self.m, self.mode, self.B = model, mode, B
+        self._flip = 0
+        f32 = dict(device=self.dev, dtype=torch.float32)
+        dd = model.ddconfig
+        if mode == "decode":
+            self.x_in = torch.zeros(B, dd["z_channels"], H, W, **f32)
+            s = 2 ** (len(model.levels) - 1)
+            self.out = torch.empty(B, dd["out_ch"], H * s, W * s, **f32)
+            self._build_decode(H, W)
+        else:
+            self.x_in = torch.zeros(B, dd["in_channels"], H, W, **f32)
+            self._build_encode(H, W)
+
+    # blocks ------------------------------------------------------------------------------------
+    def _x(self, *shape):
+        """Block outputs alternate between two buffers per shape (a block's input is dead once the next block has run)."""
+        self._flip ^= 1
+        return self._tmp(f"x{self._flip}", *shape)
+
+    def _sn(self, x, zq, n, act, y):
+        """SpatialNorm (decoder: zq given) or plain GroupNorm(32, eps 1e-6) (encoder: zq None), optional swish."""
+        st = self._stats(x, None, self.EPS)
+        if zq is None:
+            self._add(lambda: ops.gn_apply(x, None, st, n["g"], n["b"], act=act, y=y), "gn_apply")
+        else:
+            self._add(lambda: ops.sn_apply(x, st, n["g"], n["b"], zq, n["w"], act=act, y=y), "sn_apply")
+
+    def _res(self, x, zq, d):
+        B, H, W, cin = x.shape
+        cout = d["c1"].shape[0]
+        hn = self._tmp("hn", B, H, W, cin)
+        self._sn(x, zq, d["n1"], 1, hn)
+        h = self._tmp("h", B, H, W, cout)
+        self._conv([(hn, 9)], d["w1"], cout, h, 2 * B * H * W * cout * 9 * cin, bias=d["c1"], part_slot="part_h")
+        hn2 = self._tmp("hn", B, H, W, cout)
+        self._sn(h, zq, d["n2"], 1, hn2)
+        o = self._x(B, H, W, cout)
+        if cin == cout:
+            self._conv([(hn2, 9)], d["w2"], cout, o, 2 * B * H * W * cout * 9 * cout, bias=d["c2"], residual=x)
+        else:
+            self._conv([(hn2, 9), (x, 1)], d["w2"], cout, o, 2 * B * H * W * cout * (9 * cout + cin), bias=d["c2"])
+        return o
+
+    def _attn(self, x, zq, d):
+        """AttnBlock (movq_modules.py:201-225 / vqgan_blocks.py:186-240): one head of width C over T = H*W tokens."""
+        B, H, W, C = x.shape
+        T = H * W
+        if T % 64:
+            raise K2Error("MoVQ attention needs h*w to be a multiple of 64 (latents are multiples of 8 px)")
+        hn = self._tmp("hn", B, H, W, C)
+        self._sn(x, zq, d["n"], 0, hn)
+        qkv = self._tmp("qkv", B, T, 3 * C)
+        self._gemm(hn.view(B, T, C), d["wqkv"], 3 * C, qkv, 2 * B * T * 3 * C * C, bias=d["bqkv"])
+        vT = self._tmp("vT", B, C, T)
+        self._add(lambda: ops.transpose_f16(qkv[:, :, 2 * C:], out=vT), "transpose")
+        scores = self._tmp("scores", B, T, T)
+        q, k = qkv[:, :, :C], qkv[0, :, C:2 * C]
+        # scores[n] = q[n] k[n]^T: A rows = q (row stride 3C), B operand of image n = its k rows (batch stride T * 3C)
+        self._conv([(q.unsqueeze(1), 1)], k, T, scores.view(B, 1, T, T), 2 * B * T * T * C, want_stats=False,
+                   w_batch_stride=T * 3 * C, kind="attn_gemm")
+        self._add(lambda: ops.softmax_rows(scores.view(B * T, T), C ** -0.5, out=scores.view(B * T, T)), "softmax")
+        o = self._tmp("att", B, T, C)
+        self._conv([(scores.view(B, 1, T, T), 1)], vT[0], C, o.view(B, 1, T, C), 2 * B * T * T * C, want_stats=False,
+                   w_batch_stride=C * T, kind="attn_gemm")
+        out = self._x(B, H, W, C)
+        self._conv([(o.view(B, H, W, C), 1)], d["wp"], C, out, 2 * B * T * C * C, bias=d["bp"], residual=x)
+        return out
+
+    # programs ----------------------------------------------------------------------------------
+    def _build_decode(self, h, w):
+        m, pk, B, S = self.m, self.m._packed, self.B, self._add
+        f32 = dict(device=self.dev, dtype=torch.float32)
+        zc = m.ddconfig["z_channels"]
+        zq = torch.empty(B, h, w, m.embed_dim, **f32)
+        z2 = torch.empty(B, zc, h, w, **f32)
+        S(lambda: ops.nchw_to_nhwc_f32(self.x_in, out=zq), "misc")
+        S(lambda: ops.pointwise_nchw_f32(self.x_in, pk["pq_w"], pk["pq_b"], out=z2), "misc")
+        kpad = (9 * zc + 63) // 64 * 64
+        patches = self._new(B, h, w, kpad)
+        S(lambda: ops.stem_im2col(z2, kpad=kpad, out=patches), "stem_im2col")
+        x = self._x(B, h, w, m.block_in)
+        self._conv([(patches, 1)], pk["in_w"], m.block_in, x, 2 * B * h * w * m.block_in * 9 * zc, bias=pk["in_b"])
+        x = self._res(x, zq, pk["mid1"])
+        x = self._attn(x, zq, pk["mida"])
+        x = self._res(x, zq, pk["mid2"])
+        for lv in m.levels:
+            p = f"decoder.up.{lv['level']}."
+            for bi in range(len(lv["blocks"])):
+                x = self._res(x, zq, pk[p + f"block.{bi}"])
+                if lv["attn"]:
+                    x = self._attn(x, zq, pk[p + f"attn.{bi}"])
+            if lv["up"]:
+                _, H, W, C = x.shape
+                o = self._x(B, 2 * H, 2 * W, C)
+                self._conv([(x, 4)], pk[p + "up_w"], C, o, 2 * B * 4 * H * W * C * C * 9, bias=pk[p + "up_b"])
+                x = o
+        _, H, W, C = x.shape
+        hn = self._tmp("hn", B, H, W, C)
+        self._sn(x, zq, pk["out_n"], 1, hn)
+        oc = m.ddconfig["out_ch"]
+        self._conv([(hn, 9)], pk["out_w"], oc, self.out, 2 * B * H * W * oc * 9 * C, bias=pk["out_b"], out_mode=1,
+                   want_stats=False)
+
+    def _build_encode(self, H, W):
+        m, pk, B, S = self.m, self.m._packed, self.B, self._add
+        dd = m.ddconfig
+        cin = dd["in_channels"]
+        kpad = (9 * cin + 63) // 64 * 64
+        patches = self._new(B, H, W, kpad)
+        S(lambda: ops.stem_im2col(self.x_in, kpad=kpad, out=patches), "stem_im2col")
+        x = self._x(B, H, W, dd["ch"])
+        self._conv([(patches, 1)], pk["e_in_w"], dd["ch"], x, 2 * B * H * W * dd["ch"] * 9 * cin, bias=pk["e_in_b"])
+        for lv in m.enc_levels:
+            p = f"encoder.down.{lv['level']}."
+            for bi in range(len(lv["blocks"])):
+                x = self._res(x, None, pk[p + f"block.{bi}"])
+                if lv["attn"]:
+                    x = self._attn(x, None, pk[p + f"attn.{bi}"])
+            if lv["down"]:
+                _, h, w, C = x.shape
+                full = self._tmp("h", B, h, w, C)
+                self._conv([(x, 9)], pk[p + "down_w"], C, full, 2 * B * h * w * C * C * 9, bias=pk[p + "down_b"],
+                           want_stats=False)
+                o = self._x(B, h // 2, w // 2, C)
+                S(lambda full=full, o=o: ops.subsample2(full, 1, 1, out=o), "misc")
+                self._parts.pop(o.data_ptr(), None)
+                x = o
+        x = self._res(x, None, pk["e_mid1"])
+        x = self._attn(x, None, pk["e_mida"])
+        x = self._res(x, None, pk["e_mid2"])
+        _, h, w, C = x.shape
+        hn = self._tmp("hn", B, h, w, C)
+        self._sn(x, None, pk["e_out_n"], 1, hn)
+        zc_out = pk["e_out_b"].shape[0]
+        z = torch.empty(B, zc_out, h, w, device=self.dev, dtype=torch.float32)
+        self._conv([(hn, 9)], pk["e_out_w"], zc_out, z, 2 * B * h * w * zc_out * 9 * C, bias=pk["e_out_b"], out_mode=1,
+                   want_stats=False)
+        self.out = torch.empty(B, m.embed_dim, h, w, device=self.dev, dtype=torch.float32)
+        S(lambda: ops.pointwise_nchw_f32(z, pk["qc_w"], pk["qc_b"], out=self.out), "misc")

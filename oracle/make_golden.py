@@ -62,7 +62,18 @@ def golden_unet(name, cfg, B, H, W, ntext, wseed, iseed):
         y_orc = uo.unet_forward(sd, cfg, inp["x"], inp["t"], **kw)
     err = (y_ref - y_orc).abs().max().item()
     assert err <= 1e-5, f"{name}: oracle deviates from the reference by {err}"
-    torch.save(dict(cfg=cfg, weight_seed=wseed, inputs=inp, out=y_ref, shape=(B, H, W), ntext=ntext,
+    # the reference in ITS OWN fp16 mode (Text2ImUNet.convert_to_fp16, text2im_model2_1.py:49-55; the pipelines feed fp16
+    # embeddings): pins the oracle's fp16 mode, which calibrates the product's deviation on the GPU (tests/test_gpu_unet.py)
+    model.del_cache()
+    model.dtype = torch.float16
+    model.convert_to_fp16()
+    with torch.no_grad():
+        y_ref16 = model(inp["x"], inp["t"], **{k: (v.half() if k.endswith("_emb") else v) for k, v in kw.items()})
+        y_orc16 = uo.unet_forward(uo.to_reference_fp16(sd), cfg, inp["x"], inp["t"], fp16=True, **kw)
+    err16 = (y_ref16 - y_orc16).abs().max().item()
+    assert err16 <= 1e-5, f"{name}: oracle fp16 mode deviates from the reference's fp16 mode by {err16}"
+    print(f"{name}: reference fp16 mode vs fp32 mode max abs {(y_ref16 - y_ref).abs().max():.2e}; oracle fp16 vs it {err16:.2e}")
+    torch.save(dict(cfg=cfg, weight_seed=wseed, inputs=inp, out=y_ref, out_ref_fp16=y_ref16, shape=(B, H, W), ntext=ntext,
                     weight_checksum=float(sum(v.double().sum() for v in sd.values()))),
                os.path.join(GOLD, name + ".pt"))
     print(f"{name}: reference out std {y_ref.std():.4f}, oracle-vs-reference max abs {err:.2e}")

@@ -208,9 +208,26 @@ def conditioning(sd, cfg, full_emb=None, pooled_emb=None, image_emb=None):
     return add, tok.permute(0, 2, 1)
 
 
+def to_reference_fp16(sd):
+    """State dict as the reference holds it after convert_to_fp16() (unet.py:566-571 + fp16_util.py:9-16): the Conv1d / Conv2d
+    weights and biases of input_blocks / middle_block / output_blocks in fp16, everything else (GroupNorm gains, emb_layers
+    and time_embed Linears, the `out` head) fp32; Text2ImUNet.convert_to_fp16 (text2im_model2_1.py:49-55) also halves the
+    2.1 conditioning head, whose inputs the pipeline passes in fp16."""
+    out = {}
+    head = ("clip_to_seq.", "proj_n.", "to_model_dim_n.", "ln_model_n.", "img_layer.")
+    for k, v in sd.items():
+        torso = k.startswith(("input_blocks.", "middle_block.", "output_blocks."))
+        is_conv = torso and (v.dim() >= 3 or (k.endswith(".bias") and sd[k[:-4] + "weight"].dim() >= 3))
+        out[k] = v.half() if is_conv or k.startswith(head) else v.float()
+    return out
+
+
 def unet_forward(sd, cfg, x, timesteps, full_emb=None, pooled_emb=None, image_emb=None, inpaint_image=None,
-                 inpaint_mask=None, taps=None):
-    """fp32 forward. `taps` (optional dict) receives intermediate activations keyed by block name."""
+                 inpaint_mask=None, taps=None, fp16=False):
+    """fp32 forward. `taps` (optional dict) receives intermediate activations keyed by block name.
+    fp16=True: the reference's own fp16 mode (use_fp16, text2im_model2_1.py:94,100): sd from to_reference_fp16, the torso
+    runs on h = x.half() (fp16 storage between all ops; GroupNorm32 and softmax upcast internally, nn.py:31-37,
+    unet.py:338), time_embed / emb_layers / the `out` head stay fp32.  Used to CALIBRATE the product's deviation."""
     if cfg.get("inpainting"):
         if inpaint_image is None:
             inpaint_image = torch.zeros_like(x)
@@ -221,6 +238,8 @@ def unet_forward(sd, cfg, x, timesteps, full_emb=None, pooled_emb=None, image_em
     emb = timestep_embedding(timesteps, mc)
     emb = F.linear(F.silu(F.linear(emb, sd["time_embed.0.weight"], sd["time_embed.0.bias"])),
                    sd["time_embed.2.weight"], sd["time_embed.2.bias"])
+    if fp16 and cfg.get("cond", "2.1") == "2.1":  # the pipeline feeds the (halved) head fp16 embeddings
+        full_emb, pooled_emb, image_emb = full_emb.half(), pooled_emb.half(), image_emb.half()
     xf_proj, xf_out = conditioning(sd, cfg, full_emb, pooled_emb, image_emb)
     emb = emb + xf_proj.to(emb)
     inp, mid, out = unet_topology(cfg)
@@ -241,6 +260,9 @@ def unet_forward(sd, cfg, x, timesteps, full_emb=None, pooled_emb=None, image_em
 
     hs = []
     h = x
+    if fp16:
+        h = x.half()
+        xf_out = xf_out.half()
     for bi, blk in enumerate(inp):
         h = run(f"input_blocks.{bi}", blk, h)
         hs.append(h)
@@ -248,6 +270,7 @@ def unet_forward(sd, cfg, x, timesteps, full_emb=None, pooled_emb=None, image_em
     for bi, blk in enumerate(out):
         h = torch.cat([h, hs.pop()], dim=1)
         h = run(f"output_blocks.{bi}", blk, h)
+    h = h.to(x.dtype)
     h = _gn(h, sd, "out.0.", True)
     return F.conv2d(h, sd["out.2.weight"], sd["out.2.bias"], padding=1)
 

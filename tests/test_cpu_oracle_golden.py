@@ -28,6 +28,26 @@ def test_unet_oracle_matches_reference_golden(name):
     assert (y - fx["out"]).abs().max().item() <= 1e-5
 
 
+@pytest.mark.parametrize("name", ["unet_tiny", "unet_tiny_inpaint"])
+def test_unet_oracle_fp16_mode_matches_reference_fp16_mode(name):
+    """The oracle's fp16 mode (to_reference_fp16 + fp16=True) against the output of the reference's own fp16 mode
+    (Text2ImUNet.convert_to_fp16(), run by oracle/make_golden.py).  It is the comparator of the GPU calibration test
+    (tests/test_gpu_unet.py::test_unet_full_size_fp16_calibration).  Bit-equal where the fixture was written; a tolerance of
+    one fp16 ulp of the O(1) activations absorbs CPU-dependent fp16 conv kernels."""
+    from oracle import synth, unet_oracle as uo
+    fx = _load(name)
+    sd = synth.synth_state_dict(uo.unet_param_spec(fx["cfg"]), seed=fx["weight_seed"])
+    inp = fx["inputs"]
+    kw = {k: v for k, v in inp.items() if k not in ("x", "t")}
+    with torch.no_grad():
+        y = uo.unet_forward(uo.to_reference_fp16(sd), fx["cfg"], inp["x"], inp["t"], fp16=True, **kw)
+    assert y.dtype == torch.float32
+    assert (y - fx["out_ref_fp16"]).abs().max().item() <= 1e-3
+    # the reference's fp16 mode itself is ~5e-3 away from its fp32 mode at this size: the north_star's 1e-3 is not a property
+    # of the reference
+    assert (fx["out_ref_fp16"] - fx["out"]).abs().max().item() > 1e-3
+
+
 def test_movq_oracle_matches_reference_golden():
     from oracle import movq_oracle as mo, synth
     fx = _load("movq_tiny")

@@ -205,3 +205,85 @@ def test_multi_image_tile_fused_groupnorm_partials(NB):
         ref = ops.gn_stats(y, None)
         torch.cuda.synchronize()
         assert torch.allclose(st[..., 0], ref[..., 0], atol=2e-5) and torch.allclose(st[..., 1], ref[..., 1], rtol=2e-5)
+
+
+@pytest.mark.parametrize("NB,H,W,Cin,Cout,taps,res,split", [
+    (8, 48, 48, 768, 768, 9, True, 0), (8, 96, 96, 384, 384, 9, False, 0), (1, 1, 18432, 768, 2304, 1, False, 0),
+    (8, 24, 24, 1152, 1152, 9, True, 0), (8, 12, 12, 1536, 1536, 9, True, 0), (8, 12, 12, 1536, 1536, 9, False, 2),
+    (2, 24, 24, 128, 192, 9, True, 0)])
+def test_two_epilogue_sets_bit_identical(NB, H, W, Cin, Cout, taps, res, split):
+    """The 384-thread CTA-pair kernel (two epilogue warp sets, k2_conv_gemm_cfg cfg[3] = 2) against the one-set kernel:
+    outputs and GroupNorm partials must be bit-identical (same arithmetic, different warps)."""
+    from kandinsky2 import ops
+    g = torch.Generator(device="cuda").manual_seed(12)
+    x = torch.randn(NB, H, W, Cin, device="cuda", generator=g).half()
+    w = torch.randn(Cout, Cin, 3 if taps == 9 else 1, 3 if taps == 9 else 1, device="cuda", generator=g) / (Cin * taps) ** 0.5
+    b = torch.randn(Cout, device="cuda", generator=g)
+    r = torch.randn(NB, H, W, Cout, device="cuda", generator=g).half() if res else None
+    wp = ops.pack_conv_weight(w)
+    outs = []
+    for sets in (1, 2):
+        part = torch.zeros(ops.gn_part_floats(NB, H, W, Cout), device="cuda")
+        info = [0] * 7
+        y = ops.conv_gemm([(x, taps)], wp, Cout, bias=b, residual=r, gn_part=part, info=info, cfg=(0, 0, split, sets))
+        torch.cuda.synchronize()
+        outs.append((y.clone(), part.clone(), list(info)))
+    assert outs[0][2] == outs[1][2]
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.parametrize("bn", [128, 192, 256])
+def test_n_tile_choice_is_bit_identical(bn):
+    """k2_conv_gemm_cfg: the N tile never changes a result bit (the launch plans' autotuner relies on it)."""
+    from kandinsky2 import ops
+    g = torch.Generator(device="cuda").manual_seed(13)
+    x = torch.randn(4, 24, 24, 320, device="cuda", generator=g).half()
+    w = torch.randn(384, 320, 3, 3, device="cuda", generator=g) / 54
+    b = torch.randn(384, device="cuda", generator=g)
+    wp = ops.pack_conv_weight(w)
+    outs = []
+    for cfg in (None, (bn, 0, 1, 1), (bn, 0, 1, 2)):
+        part = torch.zeros(ops.gn_part_floats(4, 24, 24, 384), device="cuda")
+        y = ops.conv_gemm([(x, 9)], wp, 384, bias=b, gn_part=part, cfg=cfg)
+        torch.cuda.synchronize()
+        outs.append((y.clone(), part.clone()))
+    for y, part in outs[1:]:
+        assert torch.equal(y, outs[0][0]) and torch.equal(part, outs[0][1])
+
+
+@pytest.mark.parametrize("NB,H,W,Cin,Cout", [
+    (2, 24, 24, 128, 192),     # CTA pair, odd number of boxes per phase
+    (8, 12, 12, 1536, 1536),   # UNet level 3 -> 2: (8 image x 4 x 4) boxes, partials per (image, spatial tile)
+    (8, 48, 48, 768, 768),     # UNet level 1 -> 0
+    (1, 6, 10, 64, 64),        # 1-CTA kernel, ragged box
+    (2, 16, 16, 96, 128),      # Cin not a multiple of 64
+    (1, 96, 96, 256, 256),     # MoVQ Upsample geometry
+])
+def test_conv3x3_over_nearest_upsample(NB, H, W, Cin, Cout):
+    """taps = 4: conv3x3(nearest_2x(x)) evaluated as four 2x2 phase convolutions over x (unet.py:67-77, movq_modules.py:93-97);
+    the 4x larger tensor never exists.  Reference: torch fp32 on the same fp16 data with the ORIGINAL 3x3 weights rounded to
+    fp16 -- the pre-summed phase weights are rounded once more, hence the slightly wider tolerance than test_conv3x3.  Also
+    checks the fused GroupNorm partials (4 phases per box) through k2_gn_apply_fold against a direct statistics pass."""
+    from kandinsky2 import ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(NB, H, W, Cin, device="cuda", generator=g).half()
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) / (3 * Cin ** 0.5)
+    b = torch.randn(Cout, device="cuda", generator=g)
+    part = torch.zeros(ops.gn_part_floats(NB, 2 * H, 2 * W, Cout), device="cuda")
+    info = [0] * 7
+    y = ops.conv_gemm([(x, 4)], ops.pack_conv_weight_up2(w), Cout, bias=b, gn_part=part, info=info)
+    torch.cuda.synchronize()
+    assert tuple(y.shape) == (NB, 2 * H, 2 * W, Cout)
+    up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+    ref = F.conv2d(up, w.half().float(), b, padding=1).permute(0, 2, 3, 1)
+    rel = ((y.float() - ref).norm() / ref.norm()).item()
+    err = (y.float() - ref).abs().max().item()
+    assert rel < 1.5e-3 and err < 1e-2 * max(1.0, ref.abs().max().item()), (rel, err)
+    if Cout % 64 == 0 and info[5]:
+        gamma = torch.randn(Cout, device="cuda", generator=g)
+        beta = torch.randn(Cout, device="cuda", generator=g)
+        got = ops.gn_apply_fold(y, None, part, info[6] // NB, None, 0, gamma, beta, act=1)
+        want = ops.gn_apply(y, None, ops.gn_stats(y), gamma, beta, act=1)
+        torch.cuda.synchronize()
+        assert (got.float() - want.float()).abs().max().item() <= 2e-3 * max(1.0, want.float().abs().max().item())

@@ -59,6 +59,41 @@ def test_movq_decode_mid_vs_oracle():
     assert y.shape == (2, 3, 128, 128) and rel < 8e-3, rel
 
 
+def test_movq_decode_full_size_vs_oracle():
+    """The real decoder (DDCONFIG_2_1: ch 128, mult (1,2,2,4), 4 attention blocks of ONE head of width 512) on a 96x96 latent
+    -> 768x768 image, T = 9216 attention tokens (BASELINE configs[1..3] decode geometry), against the fp32 oracle on the GPU;
+    also graph replay == eager, a batch of 2 == the two images decoded alone (no cross-image coupling in the batched
+    attention GEMMs), and decode_to_uint8 == the reference's process_images arithmetic on our fp32 image."""
+    from kandinsky2.vqgan import MOVQ
+    from oracle import movq_oracle as mo, synth
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    dd = dict(mo.DDCONFIG_2_1)
+    sd = synth.synth_state_dict(mo.movq_param_spec(dd, 4, 16384), seed=10)
+    m = MOVQ(dd, 16384, 4)
+    m.load_state_dict(sd)
+    m.to("cuda")
+    z = torch.randn(2, 4, 96, 96, generator=torch.Generator().manual_seed(2)).cuda()
+    m.use_cuda_graph = False
+    y_eager = m.decode(z)
+    m.use_cuda_graph = True
+    y = m.decode(z)
+    assert torch.equal(y, y_eager) and torch.equal(y, m.decode(z)), "graph replay must be bit-identical to the eager plan"
+    assert y.shape == (2, 3, 768, 768)
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    with torch.no_grad():
+        ref = mo.movq_decode(sdc, dd, z[:1])
+    rel = ((y[:1] - ref).norm() / ref.norm()).item()
+    err = (y[:1] - ref).abs().max().item()
+    print(f"MoVQ decode 96x96 -> 768x768: rel L2 {rel:.3e} max abs {err:.3e} (image rms {ref.pow(2).mean().sqrt().item():.3f})")
+    assert rel < 8e-3, rel
+    y1 = m.decode(z[1:])
+    rel1 = ((y1 - y[1:]).norm() / y[1:].norm()).item()
+    assert rel1 < 1e-3, rel1   # different tile shapes at batch 1 may change fp32 summation order, nothing more
+    u8 = m.decode_to_uint8(z, crop_h=760, crop_w=768)
+    assert torch.equal(u8, mo.process_images(y)[:, :760, :768])
+
+
 def test_sampler_trajectory_golden():
     """5 reference p_sampler steps (CFG 4, clamp +-2, dynamic threshold, injected noise) on the tiny UNet."""
     from kandinsky2.model.gaussian_diffusion import create_gaussian_diffusion

@@ -203,3 +203,78 @@ def test_images_to_u8():
     out = ops.images_to_u8(x, 6, 7)
     ref = ((x + 1) * 127.5).round().clamp(0, 255).to(torch.uint8)[:, :, :6, :7].permute(0, 2, 3, 1)
     assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("NB,H,W,C0,C1,resample", [(8, 24, 24, 1152, 0, 0), (2, 48, 48, 768, 384, 0), (8, 12, 12, 1536, 0, 2),
+                                                   (2, 24, 24, 256, 0, 1)])
+def test_gn_apply_fold_matches_finalize_plus_apply(NB, H, W, C0, C1, resample):
+    """k2_gn_apply_fold (statistics folded from the producers' partial sums inside the apply kernel) against the
+    k2_gn_finalize + k2_gn_apply pair."""
+    from kandinsky2 import ops
+    g = torch.Generator(device="cuda").manual_seed(11)
+    outs, parts, rgs = [], [], []
+    for cout in [C0] + ([C1] if C1 else []):
+        x = torch.randn(NB, H, W, 64, device="cuda", generator=g).half()
+        w = torch.randn(cout, 64, 3, 3, device="cuda", generator=g) / 24
+        part = torch.zeros(ops.gn_part_floats(NB, H, W, cout), device="cuda")
+        info = [0] * 7
+        outs.append(ops.conv_gemm([(x, 9)], ops.pack_conv_weight(w), cout, gn_part=part, info=info))
+        assert info[5] in (1, 2), info
+        parts.append(part)
+        rgs.append(info[6] // NB)
+    C = C0 + C1
+    gamma, beta = torch.randn(C, device="cuda", generator=g), torch.randn(C, device="cuda", generator=g)
+    film = torch.randn(NB, 2 * C, device="cuda", generator=g)
+    st = torch.empty(NB, 32, 2, device="cuda")
+    ops.gn_finalize(parts[0], C0, parts[1] if C1 else None, C1, NB, rgs[0], H * W, st, rg1=rgs[1] if C1 else None)
+    ref = ops.gn_apply(outs[0], outs[1] if C1 else None, st, gamma, beta, film=film, act=1, resample=resample)
+    got = ops.gn_apply_fold(outs[0], outs[1] if C1 else None, parts[0], rgs[0], parts[1] if C1 else None,
+                            rgs[1] if C1 else 0, gamma, beta, film=film, act=1, resample=resample)
+    torch.cuda.synchronize()
+    assert (got.float() - ref.float()).abs().max().item() <= 2e-3 * max(1.0, ref.float().abs().max().item())
+
+
+@pytest.mark.parametrize("NB,H,W,C,zs,act", [(2, 16, 16, 512, 1, 0), (2, 32, 48, 256, 2, 1), (1, 64, 64, 128, 8, 1), (3, 24, 40, 128, 4, 1)])
+def test_sn_apply(NB, H, W, C, zs, act):
+    """k2_sn_apply (MoVQ SpatialNorm + swish, movq_modules.py:61-68,21-23) against torch fp32 on the same fp16 activations."""
+    from kandinsky2 import ops
+    g = torch.Generator(device="cuda").manual_seed(31)
+    x = (torch.randn(NB, H, W, C, device="cuda", generator=g) * 1.5 + 0.3).half()
+    zq = torch.randn(NB, H // zs, W // zs, 4, device="cuda", generator=g)
+    gamma = 1 + 0.1 * torch.randn(C, device="cuda", generator=g)
+    beta = 0.1 * torch.randn(C, device="cuda", generator=g)
+    wy, by = torch.randn(C, 4, device="cuda", generator=g) / 2, torch.randn(C, device="cuda", generator=g) / 4 + 1
+    wb, bb = torch.randn(C, 4, device="cuda", generator=g) / 2, torch.randn(C, device="cuda", generator=g) / 4
+    sn_w = torch.cat([wy, by[:, None], wb, bb[:, None]], 1).contiguous()
+    st = ops.gn_stats(x, None, eps=1e-6)
+    y = ops.sn_apply(x, st, gamma, beta, zq, sn_w, act=act)
+    torch.cuda.synchronize()
+    xn = F.group_norm(x.float().permute(0, 3, 1, 2), 32, gamma, beta, eps=1e-6)
+    zu = F.interpolate(zq.permute(0, 3, 1, 2), size=(H, W), mode="nearest")
+    ref = xn * (F.conv2d(zu, wy[:, :, None, None], by)) + F.conv2d(zu, wb[:, :, None, None], bb)
+    if act:
+        ref = ref * torch.sigmoid(ref)
+    ref = ref.permute(0, 2, 3, 1)
+    err = (y.float() - ref).abs().max().item()
+    assert err <= 3e-3 * max(1.0, ref.abs().max().item()), err
+
+
+def test_transpose_and_batched_gemm():
+    """k2_transpose_f16 and the batched k2_conv_gemm_cfg (w_batch_stride): the MoVQ AttnBlock's scores = q k^T and out = P v
+    for all images in one launch each (movq_modules.py:209-219)."""
+    from kandinsky2 import ops
+    g = torch.Generator(device="cuda").manual_seed(32)
+    B, T, C = 3, 320, 128   # T / 128 = 2.5 boxes per image: odd box count, the pair kernel must not straddle images
+    qkv = torch.randn(B, T, 3 * C, device="cuda", generator=g).half()
+    vT = ops.transpose_f16(qkv[:, :, 2 * C:])
+    assert torch.equal(vT, qkv[:, :, 2 * C:].transpose(1, 2).contiguous())
+    scores = torch.empty(B, T, T, device="cuda", dtype=torch.float16)
+    ops.conv_gemm([(qkv[:, :, :C].unsqueeze(1), 1)], qkv[0, :, C:2 * C], T, out=scores.view(B, 1, T, T), w_batch_stride=T * 3 * C)
+    ref = torch.einsum("btc,bsc->bts", qkv[:, :, :C].float(), qkv[:, :, C:2 * C].float())
+    assert ((scores.float() - ref).norm() / ref.norm()).item() < 1e-3
+    p = torch.softmax(ref * C ** -0.5, -1).half()
+    o = torch.empty(B, T, C, device="cuda", dtype=torch.float16)
+    ops.conv_gemm([(p.view(B, 1, T, T), 1)], vT[0], C, out=o.view(B, 1, T, C), w_batch_stride=C * T)
+    torch.cuda.synchronize()
+    ref_o = torch.einsum("bts,bsc->btc", p.float(), qkv[:, :, 2 * C:].float())
+    assert ((o.float() - ref_o).norm() / ref_o.norm()).item() < 1e-3
