@@ -170,6 +170,60 @@ def run_reference(args):
         "gpu_launches": 0, "steps_timed": len(times)}))
 
 
+def run_torch_gpu(args):
+    """Side baseline (SURVEY.md 8d last row): the reference ALGORITHM on this GPU in the reference's own fp16 mode through
+    plain PyTorch -- the oracle restatement of the reference modules (oracle/unet_oracle.py, fp16=True: cuDNN convolutions,
+    torch.einsum attention with an fp32 softmax, GroupNorm32 in fp32) + the CFG combine and DDPM update in torch.  Same step,
+    same geometry, weights of the same architecture; NOT the product and not part of any parity claim."""
+    from oracle import unet_oracle as uo
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    dev = torch.device("cuda", 0)
+    B, H, W = args.batch, args.height // 8, args.width // 8
+    cfg = uo.CONFIG_2_2
+    g = torch.Generator(device=dev).manual_seed(0)
+    sd = {}
+    for k, shape in uo.unet_param_spec(cfg):
+        if len(shape) == 1:
+            sd[k] = torch.full(shape, 1.0 if k.endswith("weight") else 0.0, device=dev)
+        else:
+            fan = 1
+            for d in shape[1:]:
+                fan *= d
+            sd[k] = torch.randn(shape, device=dev, generator=g) / fan ** 0.5
+    sd = uo.to_reference_fp16(sd)
+    x = torch.randn(B, 4, H, W, device=dev, generator=g)
+    img = torch.randn(2 * B, 1280, device=dev, generator=g)
+
+    def one_step(n):
+        nonlocal x
+        t = torch.full((2 * B,), 980.0 - 20 * (n % 49), device=dev)
+        out = uo.unet_forward(sd, cfg, torch.cat([x, x]), t, image_emb=img, fp16=True)
+        eps, _ = out.split(4, dim=1)
+        eu, ec = eps.chunk(2)
+        e = eu + 4.0 * (ec - eu)
+        x0 = (1.02 * x - 0.2 * e).clamp(-2, 2)
+        x = 0.5 * x0 + 0.5 * x + 0.01 * torch.randn_like(x)
+
+    with torch.no_grad():
+        for n in range(max(args.warmup, 3)):
+            one_step(n)
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for n in range(args.steps):
+            one_step(n)
+        e.record()
+        torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / args.steps
+    print(json.dumps({
+        "impl": "torch_gpu", "metric": METRIC, "value": 1e3 / ms, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16", "data": "synthetic", "config": workload_config(args, 1),
+        "note": "PyTorch-eager fp16 side baseline (cuDNN conv + einsum attention), oracle restatement of the reference modules"}))
+
+
 def _init_pipe_with_model(pipe, config, dev, model):
     """Kandinsky2_2 around an already-built UNet (the 1.22B synthetic model of the step benchmark)."""
     from kandinsky2.pipelines import SyntheticEmbedder
@@ -195,19 +249,60 @@ def workload_config(args, world):
             "l2": "per-step working set (2.5 GB weights + activations) exceeds the 126 MB L2; no explicit flush"}
 
 
+# BASELINE.json configs other than the metric config, as per-GPU step geometries (name, images per GPU, latent H, W, inpaint)
+OTHER_CONFIGS = [
+    ("cfg-2p text2img 512x768 (north_star's 4x64x96 latents), batch 4", 4, 64, 96, False),
+    ("cfg-3 text2img 1024x1024, batch 16 over 8 GPUs = 2 images per GPU (BASELINE configs[2])", 2, 128, 128, False),
+    ("cfg-4 inpainting 768x768, batch 4, 9-channel masked-latent stem (BASELINE configs[3])", 4, 96, 96, True),
+]
+
+
+def build_unet(dev, inpaint=False):
+    from kandinsky2.model.unet import InpaintText2ImUNet, Text2ImUNet
+    model = (InpaintText2ImUNet if inpaint else Text2ImUNet)(**UNET_CFG, device=dev, param_dtype=torch.float16)
+    model.init_synthetic_(seed=0)
+    model.finalize(release_params=True)
+    return model
+
+
+def step_roofline(plan, ms_per_step, n_unet, H, W, peaks, reps=2):
+    """Per-kernel-family CUDA-event times of one eager pass of the step's launch plan -> the `roofline` object."""
+    from oracle import unet_oracle as uo  # FLOP accounting of the reference graph only (checker-side helper)
+    prof = plan.profile(reps=reps)
+    total_ms = sum(v["ms"] for v in prof.values())
+    conv = prof["conv_gemm"]
+    achieved = conv["flops"] / (conv["ms"] * 1e-3) / 1e12
+    peak = peaks["tflops_sustained"] or peaks["tflops_burst"]
+    step_flops = uo.algorithmic_flops(uo.CONFIG_2_2, n_unet, H, W, 32)
+    return {
+        "bound": "tensor", "kernel": "conv_gemm_kernel (3x3 / 1x1 / Conv1d implicit GEMM, tcgen05)",
+        "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+        "frac_of_burst": achieved / peaks["tflops_burst"] if peaks["tflops_burst"] else None, "traffic": None,
+        "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step); burst "
+                       f"{peaks['tflops_burst']}",
+        "flops_note": "algorithmic FLOPs of the REFERENCE graph; the three up-ResBlock convs execute 4/9 of theirs (3x3 over a "
+                      "nearest-2x upsampling = four 2x2 phase convolutions, DESIGN.md section 3)",
+        "launches_per_step": conv["launches"], "kernel_ms_per_step": conv["ms"],
+        "share_of_step": conv["ms"] / total_ms,
+        "step_algorithmic_tflop": step_flops / 1e12,
+        "step_tflops_achieved": step_flops / (ms_per_step * 1e-3) / 1e12,
+        "step_frac_of_peak": step_flops / (ms_per_step * 1e-3) / 1e12 / peak,
+        "step_frac_of_burst": step_flops / (ms_per_step * 1e-3) / 1e12 / peaks["tflops_burst"] if peaks["tflops_burst"] else None,
+        "per_kind_ms": {k: round(v["ms"], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
+        "attention_tflops": prof["attention"]["flops"] / (prof["attention"]["ms"] * 1e-3) / 1e12,
+    }
+
+
 def run_k2(args):
     from kandinsky2 import ops
     from kandinsky2.model.gaussian_diffusion import FusedStep, create_ddpm_v22
-    from kandinsky2.model.unet import Text2ImUNet
     world, rank, local = dist_setup(args.gpus)
     ops.set_tuning(4, 0 if os.environ.get("K2_PDL", "1") == "0" else 1)  # programmatic dependent launch of the step's kernels
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     B, H, W = args.batch, args.height // 8, args.width // 8
 
-    model = Text2ImUNet(**UNET_CFG, device=dev, param_dtype=torch.float16)
-    model.init_synthetic_(seed=0)
-    model.finalize(release_params=True)
+    model = build_unet(dev, inpaint=args.inpaint)
 
     # conditioning: rank 0 draws the image embeddings for the whole job, ONE broadcast, each rank keeps its rows
     emb = torch.empty(world, 2 * B, 1280, device=dev)
@@ -220,16 +315,34 @@ def run_k2(args):
 
     diffusion = create_ddpm_v22(50)
     coef, ts = diffusion._tables(dev)
-    step = FusedStep(model, B, H, W, dict(image_emb=image_emb), guidance_scale=4.0, cond_first=False,
-                     clip_range=2.0, threshold_mode=0)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    x = torch.randn(B, 4, H, W, device=dev, generator=g)
+
+    def make_step(mdl, b, h, w, emb_rows, inpaint):
+        kw, extra = dict(image_emb=emb_rows), {}
+        if inpaint:  # masked-latent path: the stem sees [x, image*mask, mask]; x0 is blended with the clean latent in the step
+            init = torch.randn(1, 4, h, w, device=dev, generator=g)
+            mask = (torch.rand(1, 1, h, w, device=dev, generator=g) > 0.5).float()
+            kw["inpaint_image"] = (init * mask).repeat(2 * b, 1, 1, 1)
+            kw["inpaint_mask"] = mask.repeat(2 * b, 1, 1, 1)
+            extra = dict(inpaint_init=init.repeat(b, 1, 1, 1), inpaint_mask=mask.repeat(b, 1, 1, 1))
+        return FusedStep(mdl, b, h, w, kw, guidance_scale=4.0, cond_first=False, clip_range=2.0, threshold_mode=0, **extra)
+
     order = list(range(diffusion.num_timesteps))[::-1]
+    oidx = torch.tensor(order, device=dev, dtype=torch.long)
+
+    def schedule(st, b, h, w):
+        """The 50-step DDPM schedule + the run's per-step noise staged on the device (what the pipeline's loop does): a step
+        is then ONE graph launch (k2_step_begin + UNet + k2_sampler_step + k2_step_end), nothing else."""
+        st.set_schedule(ts[oidx], coef[oidx], torch.randn(len(order), b, 4, h, w, device=dev, generator=g))
+        xs = st.latent()
+        xs.copy_(torch.randn(b, 4, h, w, device=dev, generator=g))
+        return xs
+
+    step = make_step(model, B, H, W, image_emb, args.inpaint)
+    x = schedule(step, B, H, W)
 
     def one_step(n):
-        i = order[n % len(order)]
-        step.noise.normal_(generator=g)
-        step.run(x, ts[i], coef[i])
+        step.advance(x)
 
     def barrier():
         if world > 1:
@@ -294,39 +407,50 @@ def run_k2(args):
         "clocks": clocks,
     }
 
+    peaks = measured_peaks()
     if rank == 0 and not args.no_profile:
-        peaks = measured_peaks()
         if args.detail:
             det = step.plan.profile_detail(reps=3)
             with open(args.detail, "w") as f:
                 json.dump([dict(i=i, kind=k, gflop=fl / 1e9, us=ms * 1e3, tflops=(fl / (ms * 1e-3) / 1e12 if ms > 0 else 0))
                            for i, (k, fl, ms) in enumerate(det)], f)
-        prof = step.plan.profile(reps=2)
-        total_ms = sum(v["ms"] for v in prof.values())
-        conv = prof["conv_gemm"]
-        achieved = conv["flops"] / (conv["ms"] * 1e-3) / 1e12
-        peak = peaks["tflops_sustained"] or peaks["tflops_burst"]
-        from oracle import unet_oracle as uo  # FLOP accounting of the reference graph only (checker-side helper)
-        step_flops = uo.algorithmic_flops(uo.CONFIG_2_2, 2 * B, H, W, 32)
-        line["roofline"] = {
-            "bound": "tensor", "kernel": "conv_gemm_kernel (3x3 / 1x1 / Conv1d implicit GEMM, tcgen05)",
-            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-            "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step); burst "
-                           f"{peaks['tflops_burst']}",
-            "launches_per_step": conv["launches"], "kernel_ms_per_step": conv["ms"],
-            "share_of_step": conv["ms"] / total_ms,
-            "step_algorithmic_tflop": step_flops / 1e12,
-            "step_tflops_achieved": step_flops / (ms_per_step * 1e-3) / 1e12,
-            "step_frac_of_peak": step_flops / (ms_per_step * 1e-3) / 1e12 / peak,
-            "per_kind_ms": {k: round(v["ms"], 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
-            "attention_tflops": prof["attention"]["flops"] / (prof["attention"]["ms"] * 1e-3) / 1e12,
-        }
-    traffic_file = os.path.join(ROOT, "profiles", "conv_traffic_r1.json")
-    if "roofline" in line and os.path.exists(traffic_file):
-        with open(traffic_file) as f:
-            tf = json.load(f)
-        line["roofline"]["traffic"] = tf["dram_bytes_per_launch"]
-        line["roofline"]["traffic_note"] = tf["note"]
+        line["roofline"] = step_roofline(step.plan, ms_per_step, 2 * B, H, W, peaks)
+        # DRAM traffic of the dominant kernel comes from an ncu launch list of this same step (it cannot be measured inside
+        # an un-profiled run): profiles/conv_traffic_r2.json carries the commit it was measured at
+        traffic_file = os.path.join(ROOT, "profiles", "conv_traffic_r2.json")
+        if os.path.exists(traffic_file):
+            with open(traffic_file) as f:
+                tf = json.load(f)
+            line["roofline"]["traffic"] = tf["dram_bytes_per_launch"]
+            line["roofline"]["traffic_note"] = tf["note"]
+            line["roofline"]["traffic_measured_at_commit"] = tf.get("commit")
+    if rank == 0 and world == 1 and not args.no_configs:
+        # the other BASELINE configs' per-GPU step geometry: steps/s (graph replay, latents resident) + the same roofline object
+        cfgs = {}
+        for name, b, h, w, inp in OTHER_CONFIGS:
+            mdl = model if inp == args.inpaint else build_unet(dev, inpaint=inp)
+            emb_c = torch.randn(2 * b, 1280, device=dev, generator=g)
+            mdl.del_cache()  # new conditioning (the UNet caches it per generation, like the reference)
+            st = make_step(mdl, b, h, w, emb_c, inp)
+            xc = schedule(st, b, h, w)
+
+            def stepc(n, st=st, xc=xc):
+                st.advance(xc)
+            for n in range(3):
+                stepc(n)
+            ms_c = timed(stepc, 10) / 10
+            cfgs[name] = {"steps_per_s": 1e3 / ms_c, "ms_per_step": ms_c, "images_per_gpu": b, "latent": [h, w],
+                          "unet_batch": 2 * b}
+            if not args.no_profile:
+                r = step_roofline(st.plan, ms_c, 2 * b, h, w, peaks, reps=1)
+                cfgs[name].update(step_algorithmic_tflop=r["step_algorithmic_tflop"], step_tflops_achieved=r["step_tflops_achieved"],
+                                  step_frac_of_peak=r["step_frac_of_peak"], conv_gemm_tflops=r["achieved"],
+                                  conv_gemm_frac=r["frac"], per_kind_ms=r["per_kind_ms"])
+            del st, xc
+            if mdl is not model:
+                del mdl
+            torch.cuda.empty_cache()
+        line["configs"] = cfgs
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = int(os.environ.get('K2_CPU_THREADS', 0)) or min(os.cpu_count() or 1, 32)
         t = cpu_oracle_sample(1, H, W, threads, reps=1, warm=0)[0]
@@ -343,20 +467,30 @@ def run_k2(args):
         model.del_cache()
         pipe = Kandinsky2_2.__new__(Kandinsky2_2)
         _init_pipe_with_model(pipe, CONFIG_2_2, dev, model)
-        for _ in range(2):  # second call is steady state (plans, graphs and MoVQ packing exist)
+        calls = []
+        for it in range(4):  # call 0 builds the plans / graphs / MoVQ packing; 1..3 are steady state
             barrier()
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
             s.record()
             imgs = pipe.generate_text2img("bench", batch_size=B * world, decoder_steps=50, decoder_guidance_scale=4,
                                           h=args.height, w=args.width)
             e.record()
             barrier()
-            ms_img = torch.tensor([s.elapsed_time(e)], device=dev)
+            wall_ms = (time.perf_counter() - t0) * 1e3
+            ms_img = torch.tensor([s.elapsed_time(e), wall_ms], device=dev)
             if world > 1:
                 import torch.distributed as dist
                 dist.all_reduce(ms_img, op=dist.ReduceOp.MAX)
-        line["images"] = {"value": B * world / (ms_img.item() * 1e-3), "unit": "images/s", "decoder_steps": 50,
-                          "ms_per_call": ms_img.item(), "images_per_rank": len(imgs),
+            if it > 0:
+                calls.append(ms_img.tolist())
+        dev_ms = sorted(c[0] for c in calls)
+        med = dev_ms[len(dev_ms) // 2]
+        line["images"] = {"value": B * world / (med * 1e-3), "unit": "images/s", "decoder_steps": 50,
+                          "ms_per_call": med, "ms_per_call_min": dev_ms[0], "ms_per_call_all": [round(c[0], 1) for c in calls],
+                          "host_wall_ms_all": [round(c[1], 1) for c in calls], "images_per_rank": len(imgs),
+                          "statistic": "median of 3 steady-state calls (CUDA events, max over ranks); call 0 (plan / graph "
+                                       "build) excluded",
                           "includes": "latent init, 50 x (UNet + scheduler), MoVQ decode, uint8 + D2H + PIL"}
     if rank == 0:
         print(json.dumps(line))
@@ -370,7 +504,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="k2", choices=["k2", "reference"])
+    ap.add_argument("--impl", default="k2", choices=["k2", "reference", "torch_gpu"])
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--height", type=int, default=768)
     ap.add_argument("--width", type=int, default=768)
@@ -378,9 +512,13 @@ def main():
     ap.add_argument("--detail", default=None, help="write per-launch timings of one eager step to this JSON file")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-images", action="store_true", help="skip the whole-call images/s measurement")
+    ap.add_argument("--no-configs", action="store_true", help="skip the other BASELINE configs' step geometries (N=1 only)")
+    ap.add_argument("--inpaint", action="store_true", help="main workload = the inpainting UNet (9-channel stem)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "torch_gpu":
+        run_torch_gpu(args)
     else:
         run_k2(args)
 

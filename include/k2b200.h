@@ -42,7 +42,8 @@ void k2_reset_launch_count(void);
  * attention MMA issuer (0 fixed per key block, 1 event driven; default from the environment variable K2_ATTN_ISSUE, else 0);
  * key 10 = default number of epilogue warp sets of the CTA-pair conv kernel (1; 2 = 384-thread variant whose second set drains
  * the other half of the 64-column pairs: bit-identical results, faster where the K loop is short).  Keys 0, 1, 2 and 10 are
- * process-wide defaults; k2_conv_gemm_cfg overrides them per call. */
+ * process-wide defaults; k2_conv_gemm_cfg overrides them per call.  key 11 = blocks per SM the GroupNorm apply grids are sized
+ * for (0 = each kernel's real occupancy, i.e. one full wave; 4 = the round-1 sizing). */
 int k2_set_tuning(int key, int value);
 
 /* ---------------------------------------------------------------------------------------------
@@ -192,15 +193,32 @@ int k2_stem_im2col(const float* x, int Cx, const float* x2, int C2, const float*
  * (gaussian_diffusion.py:223-322,352-382) and denoised_fun (kandinsky2_1_model.py:237-243).
  *   model_out fp32 NCHW [2B, 8, H, W]; x fp32 [B, 4, H, W] (in place -> x_{t-1}); noise fp32 [B,4,H,W].
  *   coef (device, fp32[8]): sqrt_recip_ac, sqrt_recipm1_ac, post_coef1, post_coef2, min_log, max_log,
- *   nonzero, unused.  cond_first: 1 = rows [0,B) conditional (2.1), 0 = unconditional first (2.2).
+ *   nonzero, sqrt(alphas_cumprod[next timestep]) (2.2 inpainting only).  cond_first: 1 = rows [0,B) conditional (2.1), 0 = unconditional first (2.2).
  *   threshold_mode 0: x0 = clamp(x0, -clip, clip); 1: additionally the reference's dynamic threshold
  *   s = max(percentile_99.5(|x0[sample 0]|), 1); x0 = clip(x0, -s, s)/s   (gaussian_diffusion.py:284-294).
- *   Inpainting: x0 = x0*(1-mask) + init*mask after the clamp (mask fp32 [B,1,H,W], init fp32 [B,4,H,W]).
+ *   Inpainting (mask fp32 [B,1,H,W], 1 = keep; init fp32 [B,4,H,W] = the clean latent):
+ *     inpaint_noise == NULL (Kandinsky 2.1, kandinsky2_1_model.py:237-243): x0 = x0*(1-mask) + init*mask after the clamp;
+ *     inpaint_noise != NULL (Kandinsky 2.2 = diffusers KandinskyV22InpaintPipeline, restated: not in /root/reference): x0 is
+ *     left alone and  x_{t-1} = mask * (c*init + sqrt(1-c^2)*inpaint_noise) + (1-mask) * x_{t-1}  with c = coef[7] =
+ *     sqrt(alphas_cumprod[next timestep]) (1 at the last step = the final blend with the clean latent); inpaint_noise fp32
+ *     [B,4,H,W] is the run's initial latent noise.
  *   work: fp32 scratch of at least B*4*H*W + 4096 floats.
  * ------------------------------------------------------------------------------------------- */
 int k2_sampler_step(const float* model_out, float* x, const float* noise, const float* coef, int B, int H,
                     int W, float guidance, int cond_first, float clip, int threshold_mode,
-                    const float* inpaint_init, const float* inpaint_mask, float* work, k2_stream_t stream);
+                    const float* inpaint_init, const float* inpaint_mask, const float* inpaint_noise, float* work,
+                    k2_stream_t stream);
+
+/* Device-side schedule of the sampling loop, so that a whole denoising step (latent duplication for CFG + UNet + guidance +
+ * scheduler update) is one CUDA graph replayed once per step with nothing copied from the host (gaussian_diffusion.py:
+ * 426-475 p_sample_loop_progressive runs the loop on the host).  `counter` is a device int[2] = (step, number of steps in the
+ * schedule), written by the caller before step 0; with k = counter[0] % counter[1]:
+ *   k2_step_begin: x_in[0:n) = x_in[n:2n) = x[0:n) (n = B*4*H*W);  t_in[0:nt) = ts_seq[k];  coef_out[0:8) = coef_seq[k][0:8);
+ *                  noise[0:n) = noise_seq[k][0:n) if noise_seq != NULL (per-step noise drawn up front, one stream per image).
+ *   k2_step_end:   counter[0] += 1. */
+int k2_step_begin(const float* x, float* x_in, long long n, float* t_in, int nt, float* coef_out, const float* ts_seq,
+                  const float* coef_seq, const float* noise_seq, float* noise, const int* counter, k2_stream_t stream);
+int k2_step_end(int* counter, k2_stream_t stream);
 
 /* PLMS / DDIM update with an explicit epsilon history (replaces PLMSSampler.p_sample_plms, samplers.py:571-637, and the
  * CFG closure): e_t = uncond + g (cond - uncond) from model_out's first 4 channels (C2 channels per sample);

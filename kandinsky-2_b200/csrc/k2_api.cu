@@ -33,6 +33,8 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 bool pdl_enabled() { return g_pdl != 0; }
 static int g_conv_epi_sets = 1;
+static int g_gn_bps = 0;
+int gn_apply_blocks_per_sm() { return g_gn_bps; }
 int attention_stagger() { return g_attn_stagger; }
 int attention_poly_mode() { return g_attn_poly; }
 static int g_attn_issue = -1;  // -1: take K2_ATTN_ISSUE from the environment at first use (default 0)
@@ -325,6 +327,10 @@ int k2_set_tuning(int key, int value) {
   }
   if (key == 10) {  // epilogue warp sets of the CTA-pair conv kernel: 1 (validated) or 2 (round-2 candidate)
     g_conv_epi_sets = (value == 2) ? 2 : 1;
+    return 0;
+  }
+  if (key == 11) {  // GroupNorm apply: blocks per SM the grid is sized for (0 = the kernel's occupancy; round 1 used 4)
+    g_gn_bps = value;
     return 0;
   }
   if (key == 9) {  // attention MMA issue order: 0 fixed, 1 event driven

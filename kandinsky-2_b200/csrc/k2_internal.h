@@ -101,6 +101,7 @@ struct AttnParams {
   unsigned long long* trace;  // diagnostics: 3 x 16 x 8 clock64 stamps of CTA (0,0,0), or null
   int issue_mode;      // MMA issuer: 0 = fixed program order per key block, 1 = event driven (polls both query tiles)
 };
+int gn_apply_blocks_per_sm();  // tuning key 11: blocks per SM the GroupNorm apply kernels are sized for (0 = their occupancy)
 int attention_stagger();
 unsigned long long* attention_trace_buffer();
 int attention_issue_mode();

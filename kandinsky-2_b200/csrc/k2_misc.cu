@@ -248,6 +248,7 @@ struct SamplerParams {
   int threshold_mode;
   const float* init;       // [B,4,H,W] or null
   const float* mask;       // [B,1,H,W] or null
+  const float* rnoise;     // [B,4,H,W] or null: inpainting blends x_{t-1} with the re-noised init (diffusers) instead of x0
   float* x0;               // work [B*4*HW]
   float* sval;             // work scalar (dynamic threshold s)
 };
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(256) sampler_x0_kernel(const SamplerParams p) 
   const float eps = eu + p.guidance * (ec - eu);
   float x0 = p.coef[0] * p.x[i] - p.coef[1] * eps;
   x0 = fminf(fmaxf(x0, -p.clip), p.clip);
-  if (p.mask) {
+  if (p.mask && !p.rnoise) {  // Kandinsky 2.1: the known region replaces x0 (denoised_fun, kandinsky2_1_model.py:237-243)
     const float m = p.mask[static_cast<long long>(b) * p.HW + sp];
     x0 = x0 * (1.f - m) + p.init[i] * m;
   }
@@ -348,7 +349,17 @@ __global__ void __launch_bounds__(256) sampler_post_kernel(const SamplerParams p
   const float v = p.model_out[(static_cast<long long>(bc) * 8 + 4 + c) * p.HW + sp];
   const float frac = (v + 1.f) * 0.5f;
   const float logvar = frac * p.coef[5] + (1.f - frac) * p.coef[4];
-  p.x[i] = mean + p.coef[6] * expf(0.5f * logvar) * p.noise[i];
+  float xp = mean + p.coef[6] * expf(0.5f * logvar) * p.noise[i];
+  if (p.mask && p.rnoise) {
+    // Kandinsky 2.2 (diffusers KandinskyV22InpaintPipeline): after the scheduler step the known region is replaced by the
+    // clean latent noised to the NEXT timestep with the run's initial noise; coef[7] = sqrt(alphas_cumprod[t_next]), 1 at
+    // the last step (which is also the pipeline's final blend with the clean latent)
+    const float m = p.mask[static_cast<long long>(b) * p.HW + sp];
+    const float c = p.coef[7];
+    const float sgm = sqrtf(fmaxf(0.f, 1.f - c * c));
+    xp = m * (c * p.init[i] + sgm * p.rnoise[i]) + (1.f - m) * xp;
+  }
+  p.x[i] = xp;
 }
 
 // PLMS / DDIM update with an explicit epsilon history (samplers.py:571-637):
@@ -644,13 +655,14 @@ int k2_stem_im2col(const float* x, int Cx, const float* x2, int C2, const float*
 
 int k2_sampler_step(const float* model_out, float* x, const float* noise, const float* coef, int B, int H, int W,
                     float guidance, int cond_first, float clip, int threshold_mode, const float* inpaint_init,
-                    const float* inpaint_mask, float* work, k2_stream_t stream) {
+                    const float* inpaint_mask, const float* inpaint_noise, float* work, k2_stream_t stream) {
   K2_REQUIRE(model_out && x && noise && coef && work && B > 0, "sampler_step: bad arguments");
   K2_REQUIRE((inpaint_init == nullptr) == (inpaint_mask == nullptr), "sampler_step: init and mask go together");
+  K2_REQUIRE(inpaint_noise == nullptr || inpaint_init, "sampler_step: inpaint_noise without init / mask");
   SamplerParams p;
   p.model_out = model_out; p.x = x; p.noise = noise; p.coef = coef;
   p.B = B; p.HW = H * W; p.guidance = guidance; p.cond_first = cond_first; p.clip = clip;
-  p.threshold_mode = threshold_mode; p.init = inpaint_init; p.mask = inpaint_mask;
+  p.threshold_mode = threshold_mode; p.init = inpaint_init; p.mask = inpaint_mask; p.rnoise = inpaint_noise;
   p.x0 = work; p.sval = work + static_cast<long long>(B) * 4 * H * W;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long total = static_cast<long long>(B) * 4 * H * W;
@@ -663,6 +675,52 @@ int k2_sampler_step(const float* model_out, float* x, const float* noise, const 
   K2_CHECK_CUDA(launch_k(sampler_post_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, st, p));
   K2_CHECK_CUDA(cudaGetLastError());
   count_launch(2);
+  return 0;
+}
+
+// Device-side schedule of the sampling loop (the whole denoising step is ONE CUDA graph, replayed once per step):
+// step_begin reads the step counter k, duplicates the latent for classifier-free guidance, and stages this step's timestep,
+// coefficient row and noise; step_end advances k.  Nothing comes from the host inside the loop.
+__global__ void __launch_bounds__(256) step_begin_kernel(const float* __restrict__ x, float* __restrict__ x_in, long long n,
+                                                         float* __restrict__ t_in, int nt, float* __restrict__ coef_out,
+                                                         const float* __restrict__ ts_seq, const float* __restrict__ coef_seq,
+                                                         const float* __restrict__ noise_seq, float* __restrict__ noise,
+                                                         const int* __restrict__ counter) {
+  pdl_wait();
+  pdl_launch();
+  const int k = counter[0] % max(counter[1], 1);  // counter = (step, steps in the schedule)
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const float v = x[i];
+    x_in[i] = v;
+    x_in[n + i] = v;
+    if (noise_seq) noise[i] = noise_seq[static_cast<long long>(k) * n + i];
+  }
+  if (blockIdx.x == 0) {
+    for (int j = threadIdx.x; j < nt; j += blockDim.x) t_in[j] = ts_seq[k];
+    if (threadIdx.x < 8) coef_out[threadIdx.x] = coef_seq[k * 8 + threadIdx.x];
+  }
+}
+__global__ void step_end_kernel(int* counter) {
+  pdl_wait();
+  pdl_launch();
+  *counter += 1;
+}
+
+int k2_step_begin(const float* x, float* x_in, long long n, float* t_in, int nt, float* coef_out, const float* ts_seq,
+                  const float* coef_seq, const float* noise_seq, float* noise, const int* counter, k2_stream_t stream) {
+  K2_REQUIRE(x && x_in && t_in && coef_out && ts_seq && coef_seq && counter && n > 0 && nt > 0, "step_begin: bad arguments");
+  K2_REQUIRE((noise_seq == nullptr) || noise, "step_begin: noise_seq without a noise buffer");
+  K2_CHECK_CUDA(launch_k(step_begin_kernel, dim3(blocks_for(n, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), x, x_in, n,
+                         t_in, nt, coef_out, ts_seq, coef_seq, noise_seq, noise, counter));
+  count_launch();
+  return 0;
+}
+
+int k2_step_end(int* counter, k2_stream_t stream) {
+  K2_REQUIRE(counter, "step_end: null counter");
+  K2_CHECK_CUDA(launch_k(step_end_kernel, dim3(1), dim3(1), 0, static_cast<cudaStream_t>(stream), counter));
+  count_launch();
   return 0;
 }
 

@@ -293,6 +293,20 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const ApplyParams p) {
   const int py = threadIdx.x / VX;
   const int v = blockIdx.y * VX + vx;
   const int n = blockIdx.z;
+  // Everything that the PREVIOUS kernel of the stream does not produce is fetched before griddepcontrol.wait, i.e. while that
+  // kernel is still draining: gamma / beta are weights, the FiLM rows come from the step's first launches (every kernel waits
+  // for its predecessor before it lets its successor start, so launches <= N-2 are complete when launch N begins).
+  float ga8[8], be8[8], sc8[8], sh8[8];
+  {
+    const int cc = min(v, CV - 1) * 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      ga8[e] = __ldg(p.gamma + cc + e);
+      be8[e] = __ldg(p.beta + cc + e);
+      sc8[e] = p.film ? 1.f + __ldg(p.film + static_cast<long long>(n) * p.film_ld + cc + e) : 1.f;
+      sh8[e] = p.film ? __ldg(p.film + static_cast<long long>(n) * p.film_ld + C + cc + e) : 0.f;
+    }
+  }
   pdl_wait();
   pdl_launch();
   __shared__ float2 s_fold[FOLD ? FOLD_MAXG : 1];
@@ -373,16 +387,10 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const ApplyParams p) {
       } else {
         st = __ldg(reinterpret_cast<const float2*>(p.stats + (static_cast<long long>(n) * p.groups + g) * 2));
       }
-      float ga = __ldg(p.gamma + c) * st.y;
-      float be = __ldg(p.beta + c) - st.x * ga;
-      if (p.film) {
-        const float sc = 1.f + __ldg(p.film + static_cast<long long>(n) * p.film_ld + c);
-        const float sh = __ldg(p.film + static_cast<long long>(n) * p.film_ld + C + c);
-        ga *= sc;
-        be = be * sc + sh;
-      }
-      A[e] = ga;
-      Bc[e] = be;
+      const float ga = ga8[e] * st.y;
+      const float be = be8[e] - st.x * ga;
+      A[e] = ga * sc8[e];
+      Bc[e] = fmaf(be, sc8[e], sh8[e]);
     }
   }
   const __half* base = (c0 < p.C0) ? (p.s0 + c0) : (p.s1 + (c0 - p.C0));
@@ -499,9 +507,11 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const ApplyParams p) {
   }
 }
 
-// work pixels per block: enough blocks to fill the machine ~8x, at least one pixel per lane
-static int pick_chunk(int HW, int ctiles, int NB) {
-  const int target_blocks = 4 * num_sms();
+// work pixels per block: `blocks_per_sm` blocks per SM in total, at least one pixel per lane.  For the apply kernels the
+// caller passes the kernel's real occupancy (3 blocks of 256 threads at 80 registers): ONE full wave.  Round 1 asked for 4 per
+// SM regardless, i.e. 592 blocks on 444 slots = a second wave with one block per SM (profiles/README.md, round 2).
+static int pick_chunk(int HW, int ctiles, int NB, int blocks_per_sm = 4) {
+  const int target_blocks = blocks_per_sm * num_sms();
   int chunks = (target_blocks + ctiles * NB - 1) / (ctiles * NB);
   int max_chunks = (HW + PY - 1) / PY;
   if (chunks > max_chunks) chunks = max_chunks;
@@ -509,6 +519,15 @@ static int pick_chunk(int HW, int ctiles, int NB) {
   int chunk = (HW + chunks - 1) / chunks;
   chunk = (chunk + PY - 1) / PY * PY;
   return chunk;
+}
+
+template <typename K>
+static int apply_blocks_per_sm(K kernel) {
+  const int forced = gn_apply_blocks_per_sm();  // tuning key 11 (0 = the kernel's occupancy)
+  if (forced > 0) return forced;
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, 0) != cudaSuccess || occ < 1) occ = 3;
+  return occ;
 }
 
 }  // namespace
@@ -583,19 +602,22 @@ int k2_gn_apply(const void* src0, int C0, int ld0, const void* src1, int C1, int
   const int Hw = (resample == 1) ? H / 2 : H;
   const int Ww = (resample == 1) ? W / 2 : W;
   const int ctiles = (C / 8 + VX - 1) / VX;
-  p.chunk = pick_chunk(Hw * Ww, ctiles, NB);
-  dim3 grid((Hw * Ww + p.chunk - 1) / p.chunk, ctiles, NB);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const bool sp = zq != nullptr;
+  auto go = [&](auto kernel) -> cudaError_t {
+    p.chunk = pick_chunk(Hw * Ww, ctiles, NB, apply_blocks_per_sm(kernel));
+    dim3 grid((Hw * Ww + p.chunk - 1) / p.chunk, ctiles, NB);
+    return launch_k(kernel, grid, dim3(256), 0, st, p);
+  };
   if (resample == 0) {
-    if (sp) K2_CHECK_CUDA(launch_k(gn_apply_kernel<0, true>, grid, dim3(256), 0, st, p));
-    else K2_CHECK_CUDA(launch_k(gn_apply_kernel<0, false>, grid, dim3(256), 0, st, p));
+    if (sp) K2_CHECK_CUDA(go(gn_apply_kernel<0, true>));
+    else K2_CHECK_CUDA(go(gn_apply_kernel<0, false>));
   } else if (resample == 1) {
-    if (sp) K2_CHECK_CUDA(launch_k(gn_apply_kernel<1, true>, grid, dim3(256), 0, st, p));
-    else K2_CHECK_CUDA(launch_k(gn_apply_kernel<1, false>, grid, dim3(256), 0, st, p));
+    if (sp) K2_CHECK_CUDA(go(gn_apply_kernel<1, true>));
+    else K2_CHECK_CUDA(go(gn_apply_kernel<1, false>));
   } else {
-    if (sp) K2_CHECK_CUDA(launch_k(gn_apply_kernel<2, true>, grid, dim3(256), 0, st, p));
-    else K2_CHECK_CUDA(launch_k(gn_apply_kernel<2, false>, grid, dim3(256), 0, st, p));
+    if (sp) K2_CHECK_CUDA(go(gn_apply_kernel<2, true>));
+    else K2_CHECK_CUDA(go(gn_apply_kernel<2, false>));
   }
   K2_CHECK_CUDA(cudaGetLastError());
   count_launch();
@@ -629,12 +651,15 @@ int k2_gn_apply_fold(const void* src0, int C0, int ld0, const void* src1, int C1
   const int Hw = (resample == 1) ? H / 2 : H;
   const int Ww = (resample == 1) ? W / 2 : W;
   const int ctiles = (C / 8 + VX - 1) / VX;
-  p.chunk = pick_chunk(Hw * Ww, ctiles, NB);
-  dim3 grid((Hw * Ww + p.chunk - 1) / p.chunk, ctiles, NB);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (resample == 0) K2_CHECK_CUDA(launch_k(gn_apply_kernel<0, false, true>, grid, dim3(256), 0, st, p));
-  else if (resample == 1) K2_CHECK_CUDA(launch_k(gn_apply_kernel<1, false, true>, grid, dim3(256), 0, st, p));
-  else K2_CHECK_CUDA(launch_k(gn_apply_kernel<2, false, true>, grid, dim3(256), 0, st, p));
+  auto go = [&](auto kernel) -> cudaError_t {
+    p.chunk = pick_chunk(Hw * Ww, ctiles, NB, apply_blocks_per_sm(kernel));
+    dim3 grid((Hw * Ww + p.chunk - 1) / p.chunk, ctiles, NB);
+    return launch_k(kernel, grid, dim3(256), 0, st, p);
+  };
+  if (resample == 0) K2_CHECK_CUDA(go(gn_apply_kernel<0, false, true>));
+  else if (resample == 1) K2_CHECK_CUDA(go(gn_apply_kernel<1, false, true>));
+  else K2_CHECK_CUDA(go(gn_apply_kernel<2, false, true>));
   K2_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return 0;

@@ -146,29 +146,39 @@ def _sampling_loop(schedule, model, shape, noise, model_kwargs, device, progress
     if init_step is not None:
         indices = schedule.truncate(indices, init_step)
     indices = indices[::-1]
+    tqdm = None
     if progress:
         try:
             from tqdm.auto import tqdm
-            indices = tqdm(indices)
         except ImportError:
             pass
     step = FusedStep(model, B, H, W, model_kwargs, guidance_scale, cond_first, clip_range, threshold_mode, inpaint_init,
                      inpaint_mask)
+    order = [int(i) for i in indices]
+    n = len(order)
+    # the whole run's per-step noise is drawn up front (one stream per image when sample_generators are given, so an image's
+    # noise does not depend on which rank / batch position it runs at) and indexed by the device-side step counter
     if not needs_noise:
         step.noise.zero_()
-    for n, i in enumerate(indices):
-        if not needs_noise:
-            pass
-        elif step_noise is not None:
-            step.noise.copy_(step_noise[n])
-        elif sample_generators is not None:
-            for b, gen in enumerate(sample_generators):
-                step.noise[b].normal_(generator=gen)
-        else:
-            step.noise.normal_()
-        step.run(x, ts[i], coef[i])
+        noise_seq = None
+    elif step_noise is not None:
+        noise_seq = step_noise[:n].float().to(device)
+    elif sample_generators is not None:
+        noise_seq = torch.empty(n, B, C, H, W, device=device, dtype=torch.float32)
+        for b, gen in enumerate(sample_generators):
+            noise_seq[:, b].copy_(torch.randn(n, C, H, W, device=device, generator=gen))
+    else:
+        noise_seq = torch.randn(n, B, C, H, W, device=device)
+    idx = torch.tensor(order, device=device, dtype=torch.long)
+    step.set_schedule(ts[idx], coef[idx], noise_seq)
+    xs = step.latent()
+    xs.copy_(x)
+    it = tqdm(order) if progress and tqdm is not None else order
+    for i in it:
+        step.advance(xs)
         if callback is not None:
-            callback(i, x)
+            callback(i, xs)
+    x = xs.clone()
     return torch.cat([x, x], 0)
 
 
@@ -291,7 +301,14 @@ class PLMSSampler(DDIMSampler):
 
 
 class FusedStep:
-    """One denoising step = CFG-doubled UNet forward + k2_sampler_step, on static buffers (graph-replayable)."""
+    """One denoising step = CFG-doubled UNet forward + k2_sampler_step on static buffers.
+
+    Scheduled mode (the sampling loops, bench.py): set_schedule() stages the whole run's timesteps, coefficient rows and
+    (optionally) per-step noise on the device; advance(x) then replays ONE CUDA graph per step that holds
+    k2_step_begin (latent duplication for CFG, this step's t / coefficients / noise picked by a device-side counter), every
+    launch of the UNet plan, k2_sampler_step and k2_step_end.  A 50-step call is 50 graph launches and nothing else (the
+    reference syncs the device every step for np.percentile, gaussian_diffusion.py:288).
+    run(x, t, coef_row) is the step-at-a-time form (explicit timestep / coefficients; profiling scripts, PLMS)."""
 
     def __init__(self, model, B, H, W, model_kwargs, guidance_scale, cond_first, clip_range, threshold_mode,
                  inpaint_init=None, inpaint_mask=None):
@@ -303,18 +320,89 @@ class FusedStep:
         self.plan.bind(cond)
         dev = self.plan.dev
         self.B = B
-        self.noise = torch.empty(B, 4, H, W, device=dev, dtype=torch.float32)
-        self.coef = torch.zeros(8, device=dev, dtype=torch.float32)
-        self.work = torch.empty(B * 4 * H * W + 4096, device=dev, dtype=torch.float32)
         self.guidance, self.cond_first, self.clip, self.mode = guidance_scale, int(cond_first), clip_range, threshold_mode
-        self.init = inpaint_init.float().contiguous()[:B] if inpaint_init is not None else None
-        self.mask = inpaint_mask.float().contiguous()[:B] if inpaint_mask is not None else None
+        has_inpaint = inpaint_init is not None
+        # buffers and the captured step graph live on the plan, keyed by everything the graph bakes in as a kernel argument
+        key = (float(guidance_scale), int(cond_first), float(clip_range), int(threshold_mode), has_inpaint)
+        states = self.plan.__dict__.setdefault("_step_states", {})
+        st = states.get(key)
+        if st is None:
+            f32 = dict(device=dev, dtype=torch.float32)
+            st = dict(noise=torch.zeros(B, 4, H, W, **f32), coef=torch.zeros(8, **f32),
+                      work=torch.empty(B * 4 * H * W + 4096, **f32), counter=torch.zeros(2, device=dev, dtype=torch.int32),
+                      ts_seq=torch.zeros(4096, **f32), coef_seq=torch.zeros(4096, 8, **f32), noise_seq=None, graph=None,
+                      init=torch.zeros(B, 4, H, W, **f32) if has_inpaint else None,
+                      mask=torch.zeros(B, 1, H, W, **f32) if has_inpaint else None, x=torch.zeros(B, 4, H, W, **f32))
+            states[key] = st
+        self.st = st
+        self.noise, self.coef, self.work = st["noise"], st["coef"], st["work"]
+        self.init, self.mask = st["init"], st["mask"]
+        if has_inpaint:
+            self.init.copy_(inpaint_init.float()[:B])
+            self.mask.copy_(inpaint_mask.float()[:B])
         if model._inpainting:
             img = model_kwargs.get("inpaint_image")
             msk = model_kwargs.get("inpaint_mask")
             self.plan.img_in.copy_(img) if img is not None else self.plan.img_in.zero_()
             self.plan.mask_in.copy_(msk) if msk is not None else self.plan.mask_in.zero_()
 
+    # -- scheduled mode ---------------------------------------------------------------------------
+    def set_schedule(self, ts_seq, coef_seq, noise_seq=None):
+        """ts_seq fp32 [n], coef_seq fp32 [n, 8] in LOOP order; noise_seq fp32 [n, B, 4, H, W] or None (then the caller
+        fills self.noise before every advance()).  Resets the device-side step counter."""
+        st = self.st
+        n = ts_seq.shape[0]
+        if n > st["ts_seq"].shape[0]:
+            raise K2Error("FusedStep: more than 4096 sampling steps")
+        st["ts_seq"][:n].copy_(ts_seq)
+        st["coef_seq"][:n].copy_(coef_seq)
+        if noise_seq is not None:
+            if st["noise_seq"] is None or st["noise_seq"].shape[0] < n:
+                st["noise_seq"] = torch.empty((n,) + tuple(self.noise.shape), device=self.noise.device, dtype=torch.float32)
+                st["graph"] = None  # its address is baked into the captured graph
+            st["noise_seq"][:n].copy_(noise_seq)
+        self._use_noise_seq = noise_seq is not None
+        st["counter"].copy_(torch.tensor([0, n], dtype=torch.int32))
+
+    def _launch_step(self, x, noise_seq):
+        st, p = self.st, self.plan
+        ops.step_begin(x, p.x_in, p.t_in, self.coef, st["ts_seq"], st["coef_seq"], noise_seq, self.noise, st["counter"])
+        p.launch()
+        ops.sampler_step(p.out, x, self.noise, self.coef, self.guidance, self.cond_first, self.clip, self.mode,
+                         self.init, self.mask, self.work)
+        ops.step_end(st["counter"])
+
+    def advance(self, x):
+        """Next step of the schedule: x fp32 [B,4,H,W] -> x_{t-1} in place."""
+        st = self.st
+        nseq = st["noise_seq"] if self._use_noise_seq else None
+        if not self.model.use_cuda_graph:
+            self._launch_step(x, nseq)
+            return x
+        xs = st["x"]
+        if x.data_ptr() != xs.data_ptr():
+            xs.copy_(x)
+        gkey = "graph" if self._use_noise_seq else "graph_nonoise"
+        if st.get(gkey) is None:
+            k0, x0 = st["counter"].clone(), xs.clone()
+            self._launch_step(xs, nseq)  # warm-up: one-time cudaFuncSetAttribute calls are not capturable
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._launch_step(xs, nseq)
+            st[gkey] = g
+            st["counter"].copy_(k0)  # the warm-up advanced the schedule and the latent: put both back
+            xs.copy_(x0)
+        st[gkey].replay()
+        if x.data_ptr() != xs.data_ptr():
+            x.copy_(xs)
+        return x
+
+    def latent(self):
+        """The static latent buffer of the step graph: run the loop on it to avoid the copy in / out of advance()."""
+        return self.st["x"]
+
+    # -- step-at-a-time mode ----------------------------------------------------------------------
     def run(self, x, t_scalar, coef_row):
         """x fp32 [B,4,H,W] is updated in place to x_{t-1}."""
         p = self.plan

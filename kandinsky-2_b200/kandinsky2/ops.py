@@ -363,6 +363,19 @@ def sampler_step(model_out, x, noise, coef, guidance, cond_first, clip=2.0, thre
     return x
 
 
+def step_begin(x, x_in, t_in, coef_out, ts_seq, coef_seq, noise_seq, noise, counter):
+    """k2_step_begin: counter = device int32 [2] = (k, nsteps); see k2b200.h."""
+    lib = nat.load()
+    n = x.numel()
+    assert x_in.numel() == 2 * n and x.is_contiguous() and x_in.is_contiguous()
+    check(lib.k2_step_begin(ptr(x), ptr(x_in), n, ptr(t_in), t_in.numel(), ptr(coef_out), ptr(ts_seq), ptr(coef_seq),
+                            ptr(noise_seq), ptr(noise), ptr(counter), stream_ptr()))
+
+
+def step_end(counter):
+    check(nat.load().k2_step_end(ptr(counter), stream_ptr()))
+
+
 def plms_step(model_out, x, out, hist, store, coef, guidance, cond_first):
     """hist: list of up to 3 fp32 [B,4,H,W] tensors, newest first (None entries allowed)."""
     lib = nat.load()

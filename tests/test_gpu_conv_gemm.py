@@ -276,7 +276,10 @@ def test_conv3x3_over_nearest_upsample(NB, H, W, Cin, Cout):
     torch.cuda.synchronize()
     assert tuple(y.shape) == (NB, 2 * H, 2 * W, Cout)
     up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
-    ref = F.conv2d(up, w.half().float(), b, padding=1).permute(0, 2, 3, 1)
+    # one image per cuDNN call: at batch 8, 768 -> 768 channels, 96 x 96, this image's cuDNN fp32 convolution returns wrong
+    # values in output channels >= 683 (35 % relative error against a float64 evaluation; the per-image calls agree with
+    # float64 to 3e-7 and with this kernel to 3e-4 -- profiles/README.md, round 2)
+    ref = torch.cat([F.conv2d(up[i:i + 1], w.half().float(), b, padding=1) for i in range(NB)]).permute(0, 2, 3, 1)
     rel = ((y.float() - ref).norm() / ref.norm()).item()
     err = (y.float() - ref).abs().max().item()
     assert rel < 1.5e-3 and err < 1e-2 * max(1.0, ref.abs().max().item()), (rel, err)
