@@ -263,8 +263,13 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
   return r;
 }
+// Remote arrive on the pair leader's "accumulator drained" barrier.  What the arrival publishes is TMEM state, ordered by
+// tcgen05.wait::ld + tcgen05.fence::before_thread_sync on this side and tcgen05.fence::after_thread_sync on the waiter's; no
+// generic-proxy memory needs to become visible, so the arrive is RELAXED.  Round 1 used .release.cluster, which ptxas lowers to
+// MEMBAR.ALL.CTA + MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR: every epilogue warp waited, once per tile, until the tile's global
+// stores were visible GPU-wide before it released the accumulator (ncu source page of the proj GEMM, profiles/README.md).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit: the barrier of the pair's leader
 __device__ __forceinline__ void tma2_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {

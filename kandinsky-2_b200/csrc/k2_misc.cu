@@ -662,19 +662,32 @@ int k2_sampler_step(const float* model_out, float* x, const float* noise, const 
   SamplerParams p;
   p.model_out = model_out; p.x = x; p.noise = noise; p.coef = coef;
   p.B = B; p.HW = H * W; p.guidance = guidance; p.cond_first = cond_first; p.clip = clip;
-  p.threshold_mode = threshold_mode; p.init = inpaint_init; p.mask = inpaint_mask; p.rnoise = inpaint_noise;
+  // threshold_mode: 0 clamp only; 1 dynamic threshold of LOCAL sample 0; 2 / 4 = first half of a split step (x0, and for 2 the
+  // percentile of local sample 0) without the update; 3 = second half (update with the threshold found in `work`): lets a
+  // sharded run broadcast the threshold of GLOBAL sample 0 between the halves (kandinsky2/model/gaussian_diffusion.py)
+  K2_REQUIRE(threshold_mode >= 0 && threshold_mode <= 4, "sampler_step: threshold_mode in 0..4");
+  const bool do_front = threshold_mode != 3;
+  const bool do_pct = threshold_mode == 1 || threshold_mode == 2;
+  const bool do_post = threshold_mode == 0 || threshold_mode == 1 || threshold_mode == 3;
+  p.threshold_mode = (threshold_mode == 1 || threshold_mode == 3) ? 1 : 0;
+  p.init = inpaint_init; p.mask = inpaint_mask; p.rnoise = inpaint_noise;
   p.x0 = work; p.sval = work + static_cast<long long>(B) * 4 * H * W;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long total = static_cast<long long>(B) * 4 * H * W;
-  K2_CHECK_CUDA(launch_k(sampler_x0_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, st, p));
-  if (threshold_mode == 1) {
+  if (do_front) {
+    K2_CHECK_CUDA(launch_k(sampler_x0_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, st, p));
+    count_launch();
+  }
+  if (do_pct) {
     K2_CHECK_CUDA(launch_k(sampler_percentile_kernel, dim3(1), dim3(1024), 0, st, static_cast<const float*>(p.x0), 4 * H * W,
                            p.sval));
     count_launch();
   }
-  K2_CHECK_CUDA(launch_k(sampler_post_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, st, p));
+  if (do_post) {
+    K2_CHECK_CUDA(launch_k(sampler_post_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, st, p));
+    count_launch();
+  }
   K2_CHECK_CUDA(cudaGetLastError());
-  count_launch(2);
   return 0;
 }
 

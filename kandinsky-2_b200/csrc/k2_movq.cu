@@ -10,7 +10,8 @@
 // time the latent pixel under a thread changed: 1.16 TB/s, 38 % of the decode.  Here everything that does not depend on the
 // pixel is folded ONCE per thread into 10 coefficients per channel that live in registers:
 //       y = x * a(z) + b(z),   a(z) = A (wy.z + by),   b(z) = B (wy.z + by) + (wb.z + bb),   A = gamma rstd,  B = beta - mean A
-//   ->  a = a5[0..3].z + a5[4],  b = b5[0..3].z + b5[4]:   9 FMA per element, the 4-float latent pixel z comes from L1.
+//   ->  a = a5[0..3].z + a5[4],  b = b5[0..3].z + b5[4], evaluated once per (latent pixel, channel) and reused for the run of
+//       pixels under it: ~2 FMA per element at the fine levels, the 4-float latent pixel z comes from L1.
 #include "../../include/k2b200.h"
 #include "k2_common.cuh"
 #include "k2_internal.h"
@@ -81,8 +82,13 @@ __global__ void __launch_bounds__(256) sn_apply_kernel(const SnParams p) {
     for (int u = 0; u < UN; ++u)
       if (pp + u < p1) dst[u] = __ldg(reinterpret_cast<const uint4*>(xb + (img + pp + u) * p.ldx));
   };
+  // the per-channel (a, b) of the current latent pixel: a thread's UN consecutive pixels lie under the same latent pixel
+  // wherever the feature map is >= UN times finer than the latent (the 384^2 and 768^2 levels, i.e. most of the bytes), so
+  // the 2 x 8 x 4 modulation FMAs are paid once per run instead of once per pixel
   int last_z = -1;
-  float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  float a8[8], b8[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) a8[e] = b8[e] = 0.f;
   int pp = p0 + py * UN;
   if (pp < p1) load_set(pp, raw);
   for (; pp < p1; pp += UN * PY) {
@@ -96,7 +102,12 @@ __global__ void __launch_bounds__(256) sn_apply_kernel(const SnParams p) {
       const int zi = ((yi * p.zh) / p.H) * p.zw + (xi * p.zw) / p.W;   // nearest: floor(dst * in / out)
       if (zi != last_z) {
         last_z = zi;
-        z = __ldg(zb + zi);
+        const float4 z = __ldg(zb + zi);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          a8[e] = fmaf(a5[e][3], z.w, fmaf(a5[e][2], z.z, fmaf(a5[e][1], z.y, fmaf(a5[e][0], z.x, a5[e][4]))));
+          b8[e] = fmaf(b5[e][3], z.w, fmaf(b5[e][2], z.z, fmaf(b5[e][1], z.y, fmaf(b5[e][0], z.x, b5[e][4]))));
+        }
       }
       const __half2* h2 = reinterpret_cast<const __half2*>(&raw[u]);
       uint4 ov;
@@ -108,9 +119,7 @@ __global__ void __launch_bounds__(256) sn_apply_kernel(const SnParams p) {
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
           const int e = 2 * e2 + k;
-          const float a = fmaf(a5[e][3], z.w, fmaf(a5[e][2], z.z, fmaf(a5[e][1], z.y, fmaf(a5[e][0], z.x, a5[e][4]))));
-          const float b = fmaf(b5[e][3], z.w, fmaf(b5[e][2], z.z, fmaf(b5[e][1], z.y, fmaf(b5[e][0], z.x, b5[e][4]))));
-          const float t = fmaf(k ? f.y : f.x, a, b);
+          const float t = fmaf(k ? f.y : f.x, a8[e], b8[e]);
           o[k] = p.act ? silu_f(t) : t;
         }
         oh[e2] = __floats2half2_rn(o[0], o[1]);

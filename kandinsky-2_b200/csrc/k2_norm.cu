@@ -512,7 +512,9 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const ApplyParams p) {
 // SM regardless, i.e. 592 blocks on 444 slots = a second wave with one block per SM (profiles/README.md, round 2).
 static int pick_chunk(int HW, int ctiles, int NB, int blocks_per_sm = 4) {
   const int target_blocks = blocks_per_sm * num_sms();
-  int chunks = (target_blocks + ctiles * NB - 1) / (ctiles * NB);
+  // rounded DOWN: the grid must not exceed the resident slots by a few blocks (a second wave of 36 blocks on 444 slots cost
+  // the level-1 applies ~40 % of their duration: sm__cycles_active 60 % of elapsed under ncu, profiles/README.md round 2)
+  int chunks = target_blocks / (ctiles * NB);
   int max_chunks = (HW + PY - 1) / PY;
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;

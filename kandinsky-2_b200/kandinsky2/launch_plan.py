@@ -14,6 +14,7 @@ from . import ops
 # 21-23; <= 9 (levels 2-3) 18-21 vs 15-17 -> fold below level 0 only.
 FOLD_MAX_RG = int(os.environ.get("K2_GN_FOLD_MAX_RG", "18"))
 TUNE = os.environ.get("K2_AUTOTUNE", "1") != "0"
+FORK = os.environ.get("K2_FORK", "1") != "0"
 _tune_cache = {}
 
 
@@ -65,6 +66,9 @@ class LaunchPlan:
         self._scratch = {}
         self.steps = []
         self.graph = None
+        self._side_stream = None   # forked branch of the launch DAG (see _side)
+        self._side_open = False
+        self._serial = False       # profile passes run the side branch in line so that every launch is timed on one stream
 
     # buffers -----------------------------------------------------------------------------------
     def _tmp(self, slot, *shape, dtype=torch.float16):
@@ -83,6 +87,42 @@ class LaunchPlan:
         """Record a launch AND run it once now (build = eager trace)."""
         fn()
         self.steps.append((fn, kind, flops))
+
+    # A second stream for launches that are off the critical path (the step's time / FiLM linears next to the stem conv, the
+    # up ResBlocks' skip upsampling next to norm -> conv): _side() forks after the launches recorded so far, _join() makes
+    # everything recorded afterwards wait for the branch.  Under graph capture the branch becomes a parallel chain of the
+    # CUDA graph.  FORK = os.environ K2_FORK (default on).
+    def _side(self, fn, kind="misc", flops=0):
+        if not FORK:
+            return self._add(fn, kind, flops)
+        first = not self._side_open
+        self._side_open = True
+
+        def step():
+            if self._serial:
+                return fn()
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream(device=self.dev)
+            if first:
+                ev = torch.cuda.Event()
+                ev.record()
+                self._side_stream.wait_event(ev)
+            with torch.cuda.stream(self._side_stream):
+                fn()
+        self._add(step, kind, flops)
+
+    def _join(self):
+        if not self._side_open:
+            return
+        self._side_open = False
+
+        def step():
+            if self._serial:
+                return
+            ev = torch.cuda.Event()
+            ev.record(self._side_stream)
+            torch.cuda.current_stream().wait_event(ev)
+        self._add(step, "join", 0)
 
     def _conv(self, srcs, w, cout, out, flops, bias=None, residual=None, want_stats=True, part_slot=None, out_mode=0,
               geom=None, w_batch_stride=0, kind="conv_gemm"):
@@ -152,6 +192,7 @@ class LaunchPlan:
 
     def _timed_pass(self):
         evs = []
+        self._serial = True
         torch.cuda.synchronize()
         torch.cuda._sleep(int(4e7))  # the host runs ahead: events are not skewed by launch latency
         for fn, kind, flops in self.steps:
@@ -162,6 +203,7 @@ class LaunchPlan:
             e.record()
             evs.append((s, e))
         torch.cuda.synchronize()
+        self._serial = False
         return [s.elapsed_time(e) for s, e in evs]
 
     def profile_detail(self, reps=3):
@@ -176,6 +218,8 @@ class LaunchPlan:
         """Per-kernel-family device time of one eager pass -> {kind: dict(ms=..., launches=..., flops=...)}."""
         agg = {}
         for kind, flops, ms in self.profile_detail(reps):
+            if kind == "join":
+                continue
             a = agg.setdefault(kind, dict(ms=0.0, launches=0, flops=0))
             a["ms"] += ms
             a["launches"] += 1

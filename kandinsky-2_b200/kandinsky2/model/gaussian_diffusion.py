@@ -15,7 +15,7 @@ configs.py:150-162) is implemented.
 import numpy as np
 import torch
 
-from .. import ops
+from .. import ops, parallel
 from .._native import K2Error
 
 
@@ -97,6 +97,7 @@ class SpacedDiffusion:
         tab[:, 4] = self.posterior_log_variance_clipped
         tab[:, 5] = np.log(self.betas)
         tab[:, 6] = (np.arange(n) != 0).astype(np.float64)
+        tab[:, 7] = np.sqrt(self.alphas_cumprod_prev)  # 2.2 inpainting: the known region is re-noised to the NEXT timestep
         return tab.astype(np.float32)  # the reference casts each extracted scalar with .float() (:825-826)
 
     def _tables(self, device):
@@ -113,7 +114,7 @@ class SpacedDiffusion:
     def p_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, model_kwargs=None,
                       device=None, progress=False, init_step=None, *, guidance_scale=1.0, cond_first=True,
                       clip_range=2.0, inpaint_init=None, inpaint_mask=None, step_noise=None, callback=None,
-                      sample_generators=None):
+                      sample_generators=None, inpaint_renoise=False):
         """Reference signature (gaussian_diffusion.py:384-425) with `model` being the k2b200 UNet module itself:
         the CFG closure, the clamp of denoised_fun and the optional inpainting blend are fused into the step
         kernel and selected by the keyword-only arguments.  shape = (2*B, 4, h, w) as in the reference (CFG
@@ -122,17 +123,20 @@ class SpacedDiffusion:
         applied to the whole batch, :284-294); False keeps only the +-clip_range clamp (Kandinsky 2.2 DDPM).
         step_noise: optional fp32 [num_steps, B, 4, h, w] injected instead of torch.randn (parity tests).
         sample_generators: optional list of B torch.Generator (device of the model), one per sample, so that the
-        noise stream of an image does not depend on which rank / batch position it runs at."""
+        noise stream of an image does not depend on which rank / batch position it runs at.
+        inpaint_renoise=False: Kandinsky 2.1 inpainting (the known region replaces x0 inside the step); True: the diffusers
+        KandinskyV22InpaintPipeline rule (x_{t-1} of the known region = the clean latent noised to the next timestep with the
+        run's INITIAL noise; the last step blends with the clean latent)."""
         if denoised_fn is not None:
             raise K2Error("denoised_fn closures are fused: pass clip_range / inpaint_init / inpaint_mask instead")
         return _sampling_loop(self, model, shape, noise, model_kwargs, device, progress, init_step, guidance_scale,
                               cond_first, clip_range, 1 if clip_denoised else 0, inpaint_init, inpaint_mask, step_noise,
-                              callback, sample_generators)
+                              callback, sample_generators, inpaint_renoise=inpaint_renoise)
 
 
 def _sampling_loop(schedule, model, shape, noise, model_kwargs, device, progress, init_step, guidance_scale, cond_first,
                    clip_range, threshold_mode, inpaint_init, inpaint_mask, step_noise, callback, sample_generators,
-                   needs_noise=True):
+                   needs_noise=True, inpaint_renoise=False):
     """Shared host loop: `schedule` provides num_timesteps and _tables(device) -> (coef [n, 8], model timesteps [n])."""
     model_kwargs = dict(model_kwargs or {})
     if device is None:
@@ -153,7 +157,7 @@ def _sampling_loop(schedule, model, shape, noise, model_kwargs, device, progress
         except ImportError:
             pass
     step = FusedStep(model, B, H, W, model_kwargs, guidance_scale, cond_first, clip_range, threshold_mode, inpaint_init,
-                     inpaint_mask)
+                     inpaint_mask, inpaint_noise=x if inpaint_renoise else None)
     order = [int(i) for i in indices]
     n = len(order)
     # the whole run's per-step noise is drawn up front (one stream per image when sample_generators are given, so an image's
@@ -311,7 +315,7 @@ class FusedStep:
     run(x, t, coef_row) is the step-at-a-time form (explicit timestep / coefficients; profiling scripts, PLMS)."""
 
     def __init__(self, model, B, H, W, model_kwargs, guidance_scale, cond_first, clip_range, threshold_mode,
-                 inpaint_init=None, inpaint_mask=None):
+                 inpaint_init=None, inpaint_mask=None, inpaint_noise=None):
         self.model = model
         if model._packed is None:
             model.finalize()
@@ -323,7 +327,8 @@ class FusedStep:
         self.guidance, self.cond_first, self.clip, self.mode = guidance_scale, int(cond_first), clip_range, threshold_mode
         has_inpaint = inpaint_init is not None
         # buffers and the captured step graph live on the plan, keyed by everything the graph bakes in as a kernel argument
-        key = (float(guidance_scale), int(cond_first), float(clip_range), int(threshold_mode), has_inpaint)
+        renoise = inpaint_noise is not None
+        key = (float(guidance_scale), int(cond_first), float(clip_range), int(threshold_mode), has_inpaint, renoise)
         states = self.plan.__dict__.setdefault("_step_states", {})
         st = states.get(key)
         if st is None:
@@ -332,14 +337,17 @@ class FusedStep:
                       work=torch.empty(B * 4 * H * W + 4096, **f32), counter=torch.zeros(2, device=dev, dtype=torch.int32),
                       ts_seq=torch.zeros(4096, **f32), coef_seq=torch.zeros(4096, 8, **f32), noise_seq=None, graph=None,
                       init=torch.zeros(B, 4, H, W, **f32) if has_inpaint else None,
-                      mask=torch.zeros(B, 1, H, W, **f32) if has_inpaint else None, x=torch.zeros(B, 4, H, W, **f32))
+                      mask=torch.zeros(B, 1, H, W, **f32) if has_inpaint else None, x=torch.zeros(B, 4, H, W, **f32),
+                      rnoise=torch.zeros(B, 4, H, W, **f32) if renoise else None)
             states[key] = st
         self.st = st
         self.noise, self.coef, self.work = st["noise"], st["coef"], st["work"]
-        self.init, self.mask = st["init"], st["mask"]
+        self.init, self.mask, self.rnoise = st["init"], st["mask"], st["rnoise"]
         if has_inpaint:
             self.init.copy_(inpaint_init.float()[:B])
             self.mask.copy_(inpaint_mask.float()[:B])
+        if renoise:
+            self.rnoise.copy_(inpaint_noise.float()[:B])
         if model._inpainting:
             img = model_kwargs.get("inpaint_image")
             msk = model_kwargs.get("inpaint_mask")
@@ -364,20 +372,38 @@ class FusedStep:
         self._use_noise_seq = noise_seq is not None
         st["counter"].copy_(torch.tensor([0, n], dtype=torch.int32))
 
-    def _launch_step(self, x, noise_seq):
+    def _launch_step(self, x, noise_seq, plan_graph=False):
         st, p = self.st, self.plan
         ops.step_begin(x, p.x_in, p.t_in, self.coef, st["ts_seq"], st["coef_seq"], noise_seq, self.noise, st["counter"])
-        p.launch()
-        ops.sampler_step(p.out, x, self.noise, self.coef, self.guidance, self.cond_first, self.clip, self.mode,
-                         self.init, self.mask, self.work)
+        if plan_graph:
+            p.run(True)
+        else:
+            p.launch()
+        args = (p.out, x, self.noise, self.coef, self.guidance, self.cond_first, self.clip)
+        if self._sync_threshold():
+            # Kandinsky 2.1 dynamic threshold under sharding: the reference clips the whole batch with the 99.5 % quantile of
+            # GLOBAL sample 0 (gaussian_diffusion.py:288-292), which lives on rank 0 -> x0 (+ the quantile on rank 0), ONE
+            # 4-byte broadcast, then the update
+            import torch.distributed as dist
+            ops.sampler_step(*args, 2 if parallel.world()[0] == 0 else 4, self.init, self.mask, self.work, self.rnoise)
+            n = x.numel()
+            dist.broadcast(self.work[n:n + 1], src=0)
+            ops.sampler_step(*args, 3, self.init, self.mask, self.work, self.rnoise)
+        else:
+            ops.sampler_step(*args, self.mode, self.init, self.mask, self.work, self.rnoise)
         ops.step_end(st["counter"])
+
+    def _sync_threshold(self):
+        return self.mode == 1 and parallel.world()[1] > 1
 
     def advance(self, x):
         """Next step of the schedule: x fp32 [B,4,H,W] -> x_{t-1} in place."""
         st = self.st
         nseq = st["noise_seq"] if self._use_noise_seq else None
-        if not self.model.use_cuda_graph:
-            self._launch_step(x, nseq)
+        if not self.model.use_cuda_graph or self._sync_threshold():
+            # (the per-step collective of the sharded 2.1 threshold stays outside a captured graph: the UNet plan's own graph
+            # is replayed, the scheduler launches around it are issued eagerly)
+            self._launch_step(x, nseq, plan_graph=self.model.use_cuda_graph)
             return x
         xs = st["x"]
         if x.data_ptr() != xs.data_ptr():
@@ -413,7 +439,7 @@ class FusedStep:
         self.coef.copy_(coef_row)
         p.run(self.model.use_cuda_graph)
         ops.sampler_step(p.out, x, self.noise, self.coef, self.guidance, self.cond_first, self.clip, self.mode,
-                         self.init, self.mask, self.work)
+                         self.init, self.mask, self.work, self.rnoise)
         return x
 
 

@@ -404,10 +404,13 @@ class _Plan(LaunchPlan):
         e1 = torch.empty(N, temb, **f32)
         emb = torch.empty(N, temb, **f32)
         film = torch.empty(N, pk["film_total"], **f32)
-        S(lambda: ops.timestep_embedding(self.t_in, mc, out=e0), "timestep_embedding")
-        S(lambda: ops.linear(e0, pk["te0_w"], pk["te0_b"], silu_out=True, out=e1), "linear")
-        S(lambda: ops.linear(e1, pk["te2_w"], pk["te2_b"], add=self.xf_proj, out=emb), "linear")
-        S(lambda: ops.linear(emb, pk["film_w"], pk["film_b"], silu_in=True, out=film), "linear")
+        # the time embedding and all 36 FiLM projections (one 215 MB weight stream) run on a forked branch next to the stem
+        # conv and the first ResBlock's norm -> conv; the first FiLM consumer joins it
+        B_ = self._side
+        B_(lambda: ops.timestep_embedding(self.t_in, mc, out=e0), "timestep_embedding")
+        B_(lambda: ops.linear(e0, pk["te0_w"], pk["te0_b"], silu_out=True, out=e1), "linear")
+        B_(lambda: ops.linear(e1, pk["te2_w"], pk["te2_b"], add=self.xf_proj, out=emb), "linear")
+        B_(lambda: ops.linear(emb, pk["film_w"], pk["film_b"], silu_in=True, out=film), "linear")
         self.film = film
 
         H, W = self.H, self.W
@@ -438,6 +441,7 @@ class _Plan(LaunchPlan):
         self._norm(h, None, pk["out_g"], pk["out_b"], hn)
         S(lambda: ops.conv_gemm([(hn, 9)], pk["out_w"], m.out_channels, bias=pk["out_c"], out=self.out, out_mode=1),
           "conv_gemm", 2 * N * H * W * m.out_channels * 9 * h.shape[-1])
+        self._join()
 
     def _layer(self, p, layer, a, b):
         pk, N, S = self.m._packed, self.N, self._add
@@ -462,12 +466,13 @@ class _Plan(LaunchPlan):
                 xres = self._tmp("xres", N, Ho, Wo, cin)
                 h1s = self._tmp("h1s", N, Hi, Wi, cin)
                 self._norm(a, b, d["g1"], d["b1"], h1s)
-                S(lambda: ops.upsample2x(a, out=xres), "upsample")
+                self._side(lambda: ops.upsample2x(a, out=xres), "upsample")
                 self._conv([(h1s, 4)], d["w1u"], cout, h2, flops1, bias=d["c1"], part_slot="part_h2")
             else:
                 xres = self._tmp("xres", N, Ho, Wo, cin)
                 self._norm(a, b, d["g1"], d["b1"], h1, resample=1 if updown == "down" else 2, xres=xres)
                 self._conv([(h1, 9)], d["w1"], cout, h2, flops1, bias=d["c1"], part_slot="part_h2")
+            self._join()  # FiLM rows (first ResBlock) / the skip upsampling (up ResBlocks) come from the forked branch
             self._norm(h2, None, d["g2"], d["b2"], h3, film=film)
             if cin == cout:
                 if b is not None:

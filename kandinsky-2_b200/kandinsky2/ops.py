@@ -352,14 +352,14 @@ def pack_stem_weight(w):
 # sampler / MoVQ helpers
 # ------------------------------------------------------------------------------------------------
 def sampler_step(model_out, x, noise, coef, guidance, cond_first, clip=2.0, threshold_mode=0, inpaint_init=None,
-                 inpaint_mask=None, work=None):
+                 inpaint_mask=None, work=None, inpaint_noise=None):
     lib = nat.load()
     B, _, H, W = x.shape
     if work is None:
         work = torch.empty(B * 4 * H * W + 4096, dtype=torch.float32, device=x.device)
     check(lib.k2_sampler_step(ptr(model_out), ptr(x), ptr(noise), ptr(coef), B, H, W, float(guidance),
                               int(cond_first), float(clip), int(threshold_mode), ptr(inpaint_init),
-                              ptr(inpaint_mask), ptr(work), stream_ptr()))
+                              ptr(inpaint_mask), ptr(inpaint_noise), ptr(work), stream_ptr()))
     return x
 
 

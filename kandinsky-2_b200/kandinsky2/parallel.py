@@ -4,9 +4,10 @@ The reference is single-device; the path is embarrassingly paral
 image's latent, CFG twin, noise stream and MoVQ decode are independent.  Rank r owns the contiguous block
 [r*B/W, (r+1)*B/W) of the global batch; rank 0 holds the conditioning embeddings and broadcasts them once
 (NCCL over NVLink on GPUs, gloo in the CPU tests); nothing else crosses ranks.  RNG is seeded per GLOBAL
-sample index so results do not depend on the world size.  (The 2.1 dynamic threshold uses sample 0's
-percentile for the whole batch, gaussian_diffusion.py:290: under sharding each rank uses ITS first sample --
-exact for 2.2, a documented deviation for 2.1 when world_size > 1.)
+sample index so results do not depend on the world size.  The 2.1 dynamic threshold uses GLOBAL sample 0's
+percentile for the whole batch (gaussian_diffusion.py:290): rank 0 owns that sample and broadcasts the one float
+per step (kandinsky2/model/gaussian_diffusion.py: FusedStep._launch_step) -- the 2.1 p_sampler path's second,
+4-byte collective; Kandinsky 2.2 has no threshold and keeps exactly one broadcast per generation.
 """
 import torch
 

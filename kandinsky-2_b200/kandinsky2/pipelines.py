@@ -156,6 +156,8 @@ class Kandinsky2_1(_DecoderBase):
         if noise is None:
             x = self._latents(lo, hi, (4, new_h, new_w))
             noise = torch.cat([x, x], 0)
+        elif noise.shape[0] == 2 * batch_size and ws > 1:
+            noise = noise[rows].contiguous()   # a caller-supplied start latent covers the GLOBAL batch: keep this rank's rows
         self.model.del_cache()
         if sampler == "p_sampler":
             samples = diffusion.p_sample_loop(self.model, (2 * B, 4, new_h, new_w), device=self.device, noise=noise,
@@ -255,12 +257,17 @@ class Kandinsky2_2(_DecoderBase):
         if latents is None:
             x = self._latents(lo, hi, (4, H, W))
             latents = torch.cat([x, x], 0)
+        elif latents.shape[0] == 2 * batch_size and ws > 1:
+            latents = latents[rows].contiguous()   # caller-supplied start latents cover the GLOBAL batch
         extra = {}
         if inpaint_latent is not None:
             kw["inpaint_image"] = (inpaint_latent * inpaint_mask).repeat(2 * B, 1, 1, 1).to(self.device)
             kw["inpaint_mask"] = inpaint_mask.repeat(2 * B, 1, 1, 1).to(self.device)
+            # diffusers KandinskyV22InpaintPipeline (the reference delegates to it, kandinsky2_2_model.py:143-173): after every
+            # scheduler step the known region (mask = 1) is the clean latent noised to the next timestep with the run's initial
+            # noise, and the result is blended with the clean latent at the end -- k2_sampler_step's inpaint_noise mode
             extra = dict(inpaint_init=inpaint_latent.repeat(B, 1, 1, 1).to(self.device),
-                         inpaint_mask=inpaint_mask.repeat(B, 1, 1, 1).to(self.device))
+                         inpaint_mask=inpaint_mask.repeat(B, 1, 1, 1).to(self.device), inpaint_renoise=True)
         diffusion = create_ddpm_v22(steps)
         self.model.del_cache()
         out = diffusion.p_sample_loop(self.model, (2 * B, 4, H, W), device=self.device, noise=latents,

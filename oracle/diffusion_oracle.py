@@ -153,3 +153,54 @@ def plms_sample_loop(unet_fn, x_T, num_steps, guidance):
         if len(old) >= 4:
             old.pop(0)
     return x
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# Kandinsky 2.2 decoder loop.  PARITY UNPINNED: /root/reference delegates to an un-vendored `diffusers`
+# (kandinsky2_2_model.py:8-12,26-42; setup.py:27 leaves the version open); this restates the published algorithm of
+# diffusers' DDPMScheduler (variance_type="learned_range", clip_sample_range 2.0, "leading" timestep spacing) and of
+# KandinskyV22Pipeline / KandinskyV22InpaintPipeline.__call__ as of the release the reference was written against (mask: 1 =
+# keep, the reference README's convention: `mask = np.ones(...); mask[:, :550] = 0` repaints the left part).
+# ------------------------------------------------------------------------------------------------------------------------
+def ddpm_v22_loop(unet_fn, x_T, steps, guidance, step_noise, train_steps=1000, beta_start=0.00085, beta_end=0.012,
+                  inpaint_init=None, inpaint_mask=None):
+    """unet_fn(x[2B], t[2B]) -> [2B, 8, h, w] with the UNCONDITIONAL rows first; x_T [B,4,h,w]; step_noise [steps,B,4,h,w]
+    replaces the scheduler's randn.  With inpaint_init / inpaint_mask the inpainting pipeline's blending is applied."""
+    betas = np.linspace(beta_start, beta_end, train_steps, dtype=np.float64)
+    ac = np.cumprod(1.0 - betas)
+    ratio = train_steps // steps
+    timesteps = (np.arange(steps) * ratio)[::-1]          # leading spacing, descending
+    x = x_T.clone()
+    noise0 = x_T.clone()
+    B = x.shape[0]
+    f32 = lambda v: float(np.float32(v))
+    for n, t in enumerate(timesteps):
+        out = unet_fn(torch.cat([x, x], 0), torch.full((2 * B,), float(t)))
+        eps, var = out[:, :4], out[:, 4:]
+        eps_u, eps_c = eps[:B], eps[B:]
+        e = eps_u + guidance * (eps_c - eps_u)
+        v = var[B:]                                         # the pipeline keeps the TEXT half's variance prediction
+        prev_t = t - ratio
+        a_t, a_prev = ac[t], (ac[prev_t] if prev_t >= 0 else 1.0)
+        b_t, b_prev = 1.0 - a_t, 1.0 - a_prev
+        cur_alpha = a_t / a_prev
+        cur_beta = 1.0 - cur_alpha
+        x0 = (x - f32(b_t ** 0.5) * e) / f32(a_t ** 0.5)
+        x0 = x0.clamp(-2.0, 2.0)
+        mean = f32(a_prev ** 0.5 * cur_beta / b_t) * x0 + f32(cur_alpha ** 0.5 * b_prev / b_t) * x
+        if t > 0:
+            min_log = np.log(max(b_prev / b_t * cur_beta, 1e-20))
+            max_log = np.log(cur_beta)
+            frac = (v + 1) / 2
+            logvar = frac * f32(max_log) + (1 - frac) * f32(min_log)
+            mean = mean + torch.exp(0.5 * logvar) * step_noise[n]
+        x = mean
+        if inpaint_mask is not None:
+            proper = inpaint_init
+            if n < len(timesteps) - 1:
+                a_n = ac[timesteps[n + 1]]
+                proper = f32(a_n ** 0.5) * inpaint_init + f32((1.0 - a_n) ** 0.5) * noise0
+            x = inpaint_mask * proper + (1 - inpaint_mask) * x
+    if inpaint_mask is not None:
+        x = inpaint_mask * inpaint_init + (1 - inpaint_mask) * x
+    return x

@@ -1,0 +1,75 @@
+"""2 GPUs (skipped on a 1-GPU box): the sharded pipelines reproduce the single-GPU images.
+
+One process per GPU over NCCL; rank r denoises and decodes its contiguous block of the batch; the ONLY collective on the 2.2
+path is the conditioning broadcast (plus, for Kandinsky 2.1's p_sampler, one 4-byte broadcast per step of the dynamic threshold,
+which the reference takes from GLOBAL sample 0 for the whole batch, gaussian_diffusion.py:288-292).  Images are compared as
+uint8: a rank's UNet batch is half the single-GPU one, which changes the launch geometry (tile boxes at the 12x12 / tiny
+levels may hold several images) and with it the fp32 summation ORDER of the GroupNorm partial sums -- nothing else -- so the
+bound is one uint8 step on a handful of pixels, not byte equality."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _tiny_overrides():
+    return {"model_config": dict(num_channels=64, num_res_blocks=1, model_dim=128, channel_mult="1,2",
+                                 attention_resolutions="32"),
+            "image_enc_params": dict(params=dict(embed_dim=4, n_embed=64, ddconfig=dict(
+                double_z=False, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=32, ch_mult=[1, 1, 2, 2],
+                num_res_blocks=1, attn_resolutions=[32], dropout=0.0)))}
+
+
+def _generate(version, batch):
+    from kandinsky2 import get_kandinsky2
+    pipe = get_kandinsky2("cuda", task_type="text2img", model_version=version, cache_dir="/nonexistent",
+                          config_overrides=_tiny_overrides())
+    if version == "2.2":
+        imgs = pipe.generate_text2img("a red cat", batch_size=batch, decoder_steps=4, h=128, w=128)
+    else:  # p_sampler: DDPM with the per-step dynamic threshold of global sample 0
+        imgs = pipe.generate_text2img("a red cat", num_steps=4, batch_size=batch, guidance_scale=4, h=128, w=128, sampler="p_sampler")
+    return np.stack([np.asarray(im) for im in imgs])
+
+
+def _worker(rank, world, port, version, batch, q):
+    for p in (ROOT, os.path.join(ROOT, "kandinsky-2_b200")):
+        sys.path.insert(0, p)
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    imgs = _generate(version, batch)   # each rank returns ITS images (contiguous block of the global batch)
+    q.put((rank, imgs.copy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("version", ["2.2", "2.1"])
+def test_two_gpus_reproduce_one_gpu(version):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    batch = 4
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, version, batch, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=600) for _ in procs)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    multi = np.concatenate([got[0], got[1]])
+    single = _generate(version, batch)
+    assert multi.shape == single.shape == (batch, 128, 128, 3)
+    diff = np.abs(multi.astype(np.int16) - single.astype(np.int16))
+    frac = float((diff > 0).mean())
+    print(f"{version}: max uint8 difference {diff.max()}, differing pixels {frac:.2e}")
+    assert diff.max() <= 2 and frac < 5e-3, (int(diff.max()), frac)
