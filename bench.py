@@ -254,12 +254,17 @@ OTHER_CONFIGS = [
     ("cfg-2p text2img 512x768 (north_star's 4x64x96 latents), batch 4", 4, 64, 96, False),
     ("cfg-3 text2img 1024x1024, batch 16 over 8 GPUs = 2 images per GPU (BASELINE configs[2])", 2, 128, 128, False),
     ("cfg-4 inpainting 768x768, batch 4, 9-channel masked-latent stem (BASELINE configs[3])", 4, 96, 96, True),
+    ("cfg-5 ControlNet-depth 768x768, batch 8 over 4 GPUs = 2 images per GPU, 8-channel stem = latent + hint features "
+     "(BASELINE configs[4]; the hint stem runs once per generation, outside the step)", 2, 96, 96, "hint"),
 ]
 
 
 def build_unet(dev, inpaint=False):
     from kandinsky2.model.unet import InpaintText2ImUNet, Text2ImUNet
-    model = (InpaintText2ImUNet if inpaint else Text2ImUNet)(**UNET_CFG, device=dev, param_dtype=torch.float16)
+    if inpaint == "hint":
+        model = Text2ImUNet(**dict(UNET_CFG, in_channels=8), hint_channels=4, device=dev, param_dtype=torch.float16)
+    else:
+        model = (InpaintText2ImUNet if inpaint else Text2ImUNet)(**UNET_CFG, device=dev, param_dtype=torch.float16)
     model.init_synthetic_(seed=0)
     model.finalize(release_params=True)
     return model
@@ -319,7 +324,9 @@ def run_k2(args):
 
     def make_step(mdl, b, h, w, emb_rows, inpaint):
         kw, extra = dict(image_emb=emb_rows), {}
-        if inpaint:  # masked-latent path: the stem sees [x, image*mask, mask]; x0 is blended with the clean latent in the step
+        if inpaint == "hint":  # ControlNet-depth: a depth map at image resolution feeds the hint stem once per generation
+            kw["hint"] = torch.rand(1, 3, 8 * h, 8 * w, device=dev, generator=g).expand(2 * b, -1, -1, -1).contiguous()
+        elif inpaint:  # masked-latent path: the stem sees [x, image*mask, mask]; x0 is blended with the clean latent in the step
             init = torch.randn(1, 4, h, w, device=dev, generator=g)
             mask = (torch.rand(1, 1, h, w, device=dev, generator=g) > 0.5).float()
             kw["inpaint_image"] = (init * mask).repeat(2 * b, 1, 1, 1)

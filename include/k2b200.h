@@ -178,6 +178,9 @@ int k2_layernorm(const float* x, const float* gamma, const float* beta, float* y
 int k2_timestep_embedding(const float* t, float* out, int B, int dim, float max_period, k2_stream_t stream);
 /* fp32 rows -> fp16 rows (context tokens), and generic strided copy helpers */
 int k2_f32_to_f16(const float* x, void* y, long long n, k2_stream_t stream);
+/* y = silu(x) on n fp16 elements, may run in place: the activations of the Kandinsky 2.2 ControlNet hint stem (diffusers
+ * ImageHintTimeEmbedding.input_hint_block, once per generation; BASELINE configs[4]) */
+int k2_silu_f16(const void* x, void* y, long long n, k2_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Stem im2col: fp32 NCHW latent (+ optional inpaint image*mask and mask, text2im_model2_1.py:146-155)

@@ -629,6 +629,28 @@ int k2_timestep_embedding(const float* t, float* out, int B, int dim, float max_
   return 0;
 }
 
+// SiLU on fp16, in place or out of place: the activations between the convolutions of the ControlNet hint stem (diffusers
+// ImageHintTimeEmbedding.input_hint_block; once per generation, not on the per-step path)
+static __global__ void __launch_bounds__(256) silu_f16_kernel(const __half2* __restrict__ x, __half2* __restrict__ y, long long n2) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n2;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float2 v = __half22float2(x[i]);
+    y[i] = __floats2half2_rn(silu_f(v.x), silu_f(v.y));
+  }
+}
+
+int k2_silu_f16(const void* x, void* y, long long n, k2_stream_t stream) {
+  K2_REQUIRE(x && y && n > 0 && n % 2 == 0, "silu_f16: n must be a positive even element count");
+  K2_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 3) == 0, "silu_f16: 4-byte alignment");
+  long long blocks = (n / 2 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  silu_f16_kernel<<<static_cast<unsigned int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __half2*>(x), reinterpret_cast<__half2*>(y), n / 2);
+  K2_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
 int k2_f32_to_f16(const float* x, void* y, long long n, k2_stream_t stream) {
   K2_REQUIRE(x && y && n > 0, "f32_to_f16: bad arguments");
   long long blocks = (n + 255) / 256;

@@ -21,8 +21,7 @@ namespace {
 
 constexpr int VX = 16;   // channel vectors (8 fp16 = 16 B) per block: a half warp covers 256 contiguous bytes of a pixel
 constexpr int PY = 16;   // pixel lanes per block
-constexpr int UN = 8;    // vectors per thread per iteration, two iterations in flight: the 80 coefficient registers cap the
-                         // kernel at one 256-thread block per SM, so each thread keeps 16 loads (256 B) in flight instead
+constexpr int UN = 8;    // vectors per thread per iteration, two iterations in flight (16 x 16 B loads per thread)
 
 struct SnParams {
   const __half* x;
@@ -38,27 +37,26 @@ struct SnParams {
   __half* y;
   int ldy;
   int chunk;            // pixels per block
+  int zshift;           // log2(H / zh) when H / zh == W / zw is a power of two (nearest resize = a shift), else -1
 };
 
-__global__ void __launch_bounds__(256) sn_apply_kernel(const SnParams p) {
+__global__ void __launch_bounds__(256, 2) sn_apply_kernel(const SnParams p) {
+  // the block's 128 channels x 10 folded coefficients live in shared memory as [k][vx][8 channels]: a thread re-reads its
+  // 80 values (20 LDS.128, conflict-free: a half warp covers 512 contiguous bytes) only when the latent pixel under it changes,
+  // which keeps the kernel at <= 128 registers = two resident blocks per SM with 16 x 16 B loads in flight per thread
+  __shared__ __align__(16) float cs[10][VX][8];
   const int vx = threadIdx.x % VX;
   const int py = threadIdx.x / VX;
   const int v = blockIdx.y * VX + vx;
   const int n = blockIdx.z;
+  const int CV = p.C / 8;
   pdl_wait();
   pdl_launch();
-  if (v >= p.C / 8) return;
-  const int c0 = v * 8;
-  const int HW = p.H * p.W;
-  const int p0 = blockIdx.x * p.chunk;
-  const int p1 = min(HW, p0 + p.chunk);
-
-  float a5[8][5], b5[8][5];
   {
     const int cpg = p.C / p.groups;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int c = c0 + e;
+    for (int i = threadIdx.x; i < VX * 8; i += blockDim.x) {  // one thread per channel of the slab
+      const int c = blockIdx.y * VX * 8 + i;
+      if (c >= p.C) continue;
       const float2 st = __ldg(reinterpret_cast<const float2*>(p.stats + (static_cast<long long>(n) * p.groups + c / cpg) * 2));
       const float A = __ldg(p.gamma + c) * st.y;
       const float B = __ldg(p.beta + c) - st.x * A;
@@ -66,11 +64,17 @@ __global__ void __launch_bounds__(256) sn_apply_kernel(const SnParams p) {
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
         const float wy = __ldg(w + k), wb = __ldg(w + 5 + k);
-        a5[e][k] = A * wy;
-        b5[e][k] = fmaf(B, wy, wb);
+        cs[k][i >> 3][i & 7] = A * wy;
+        cs[5 + k][i >> 3][i & 7] = fmaf(B, wy, wb);
       }
     }
   }
+  __syncthreads();
+  if (v >= CV) return;
+  const int c0 = v * 8;
+  const int HW = p.H * p.W;
+  const int p0 = blockIdx.x * p.chunk;
+  const int p1 = min(HW, p0 + p.chunk);
   const __half* xb = p.x + c0;
   __half* yb = p.y + c0;
   const long long img = static_cast<long long>(n) * HW;
@@ -94,19 +98,38 @@ __global__ void __launch_bounds__(256) sn_apply_kernel(const SnParams p) {
   for (; pp < p1; pp += UN * PY) {
     const int npp = pp + UN * PY;
     if (npp < p1) load_set(npp, nxt);
+    // one division per run of UN pixels: runs start at multiples of UN and W % UN == 0 on the fast path, so a run never
+    // leaves its image row; the latent pixel is a shift where the scale is a power of two (all MoVQ decoder levels)
+    const int y_run = pp / p.W, x_run = pp - y_run * p.W;
+    const bool fast = (p.W % UN == 0) && (p.zshift >= 0);
 #pragma unroll
     for (int u = 0; u < UN; ++u) {
       const int q = pp + u;
       if (q >= p1) break;
-      const int yi = q / p.W, xi = q - yi * p.W;
-      const int zi = ((yi * p.zh) / p.H) * p.zw + (xi * p.zw) / p.W;   // nearest: floor(dst * in / out)
+      int zi;
+      if (fast) {
+        zi = (y_run >> p.zshift) * p.zw + ((x_run + u) >> p.zshift);
+      } else {
+        const int yi = q / p.W, xi = q - yi * p.W;
+        zi = ((yi * p.zh) / p.H) * p.zw + (xi * p.zw) / p.W;   // nearest: floor(dst * in / out)
+      }
       if (zi != last_z) {
         last_z = zi;
         const float4 z = __ldg(zb + zi);
+        const float zz[4] = {z.x, z.y, z.z, z.w};
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          a8[e] = fmaf(a5[e][3], z.w, fmaf(a5[e][2], z.z, fmaf(a5[e][1], z.y, fmaf(a5[e][0], z.x, a5[e][4]))));
-          b8[e] = fmaf(b5[e][3], z.w, fmaf(b5[e][2], z.z, fmaf(b5[e][1], z.y, fmaf(b5[e][0], z.x, b5[e][4]))));
+        for (int hh = 0; hh < 2; ++hh) {  // channels 4*hh .. 4*hh+3
+          float4 ta = *reinterpret_cast<const float4*>(&cs[4][vx][4 * hh]);
+          float4 tb = *reinterpret_cast<const float4*>(&cs[9][vx][4 * hh]);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float4 wa = *reinterpret_cast<const float4*>(&cs[k][vx][4 * hh]);
+            const float4 wb = *reinterpret_cast<const float4*>(&cs[5 + k][vx][4 * hh]);
+            ta.x = fmaf(wa.x, zz[k], ta.x); ta.y = fmaf(wa.y, zz[k], ta.y); ta.z = fmaf(wa.z, zz[k], ta.z); ta.w = fmaf(wa.w, zz[k], ta.w);
+            tb.x = fmaf(wb.x, zz[k], tb.x); tb.y = fmaf(wb.y, zz[k], tb.y); tb.z = fmaf(wb.z, zz[k], tb.z); tb.w = fmaf(wb.w, zz[k], tb.w);
+          }
+          a8[4 * hh] = ta.x; a8[4 * hh + 1] = ta.y; a8[4 * hh + 2] = ta.z; a8[4 * hh + 3] = ta.w;
+          b8[4 * hh] = tb.x; b8[4 * hh + 1] = tb.y; b8[4 * hh + 2] = tb.z; b8[4 * hh + 3] = tb.w;
         }
       }
       const __half2* h2 = reinterpret_cast<const __half2*>(&raw[u]);
@@ -115,14 +138,9 @@ __global__ void __launch_bounds__(256) sn_apply_kernel(const SnParams p) {
 #pragma unroll
       for (int e2 = 0; e2 < 4; ++e2) {
         const float2 f = __half22float2(h2[e2]);
-        float o[2];
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const int e = 2 * e2 + k;
-          const float t = fmaf(k ? f.y : f.x, a8[e], b8[e]);
-          o[k] = p.act ? silu_f(t) : t;
-        }
-        oh[e2] = __floats2half2_rn(o[0], o[1]);
+        const float t0 = fmaf(f.x, a8[2 * e2], b8[2 * e2]);
+        const float t1 = fmaf(f.y, a8[2 * e2 + 1], b8[2 * e2 + 1]);
+        oh[e2] = __floats2half2_rn(p.act ? silu_f(t0) : t0, p.act ? silu_f(t1) : t1);
       }
       *reinterpret_cast<uint4*>(yb + (img + q) * p.ldy) = ov;
     }
@@ -176,10 +194,18 @@ int k2_sn_apply(const void* x, int C, int ldx, int NB, int H, int W, int groups,
   p.C = C; p.ldx = ldx; p.NB = NB; p.H = H; p.W = W; p.groups = groups;
   p.stats = stats; p.gamma = gamma; p.beta = beta; p.zq = zq; p.zh = zh; p.zw = zw; p.sn_w = sn_w; p.act = act;
   p.y = reinterpret_cast<__half*>(y); p.ldy = ldy;
+  p.zshift = -1;
+  if (H % zh == 0 && W % zw == 0 && H / zh == W / zw) {
+    const int sc = H / zh;
+    if ((sc & (sc - 1)) == 0) {
+      p.zshift = 0;
+      while ((1 << p.zshift) < sc) ++p.zshift;
+    }
+  }
   const int ctiles = (C / 8 + VX - 1) / VX;
   const int HW = H * W;
-  // ~6 blocks per SM in total, each thread at least one full double-buffered iteration
-  int chunks = (6 * num_sms() + ctiles * NB - 1) / (ctiles * NB);
+  // 2 resident blocks per SM x 3 waves, each thread at least one full double-buffered iteration
+  int chunks = (6 * num_sms()) / (ctiles * NB);
   const int max_chunks = (HW + UN * PY - 1) / (UN * PY);
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;

@@ -58,6 +58,7 @@ SIGNATURES = {
     "k2_layernorm": (_I, [_P, _P, _P, _P, _I, _I, _F, _P]),
     "k2_timestep_embedding": (_I, [_P, _P, _I, _I, _F, _P]),
     "k2_f32_to_f16": (_I, [_P, _P, _LL, _P]),
+    "k2_silu_f16": (_I, [_P, _P, _LL, _P]),
     "k2_stem_im2col": (_I, [_P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _P, _I, _P]),
     "k2_sampler_step": (_I, [_P, _P, _P, _P, _I, _I, _I, _F, _I, _F, _I, _P, _P, _P, _P, _P]),
     "k2_step_begin": (_I, [_P, _P, _LL, _P, _I, _P, _P, _P, _P, _P, _P, _P]),

@@ -81,7 +81,7 @@ def diffusers_unet_to_k2(sd, in_channels=4, model_channels=384, channel_mult=(1,
                          attention_ds=(2, 4, 8), head_dim=64):
     """diffusers `UNet2DConditionModel` state dict (Kandinsky 2.2 decoder) -> `Text2ImUNet(cond_version="2.2")` keys.
     Linear q/k/v/out weights [C, C] become k=1 Conv1d weights [.., C, 1]; q|k|v and add_k|add_v are head-interleaved."""
-    out = {}
+    out = {k: v for k, v in sd.items() if k.startswith("add_embedding.input_hint_block.")}  # ControlNet hint stem: same names
     for d, k in _TOP.items():
         for suffix in ("weight", "bias"):
             if f"{d}.{suffix}" in sd:
@@ -110,7 +110,7 @@ def diffusers_unet_to_k2(sd, in_channels=4, model_channels=384, channel_mult=(1,
 def k2_to_diffusers_unet(sd, in_channels=4, model_channels=384, channel_mult=(1, 2, 3, 4), num_res_blocks=3,
                          attention_ds=(2, 4, 8), head_dim=64):
     """Inverse of diffusers_unet_to_k2 (export, and the round-trip test)."""
-    out = {}
+    out = {k: v for k, v in sd.items() if k.startswith("add_embedding.input_hint_block.")}
     for d, k in _TOP.items():
         for suffix in ("weight", "bias"):
             if f"{k}.{suffix}" in sd:

@@ -319,7 +319,8 @@ class FusedStep:
         self.model = model
         if model._packed is None:
             model.finalize()
-        cond = model.get_text_emb(**{k: model_kwargs.get(k) for k in ("full_emb", "pooled_emb", "image_emb")})
+        keys = ("full_emb", "pooled_emb", "image_emb") + (("hint",) if getattr(model, "hint_channels", 0) else ())
+        cond = model.get_text_emb(**{k: model_kwargs.get(k) for k in keys})
         self.plan = model._plan(2 * B, H, W, cond["xf_out"].shape[1])
         self.plan.bind(cond)
         dev = self.plan.dev

@@ -161,3 +161,74 @@ def sample_prior(model, text_emb, text_enc, mask, use_steps, guidance, clip_mean
         if i != 0:
             x = x + math.exp(0.5 * float(np.float32(post_logvar[i]))) * step_noise[n]
     return x * clip_std + clip_mean
+
+
+class PriorEmbedder:
+    """The diffusion prior behind the pipelines' `embedder` protocol (kandinsky2/pipelines.py): what
+    Kandinsky2_1.generate_clip_emb does (kandinsky2_1_model.py:159-182) -- CLIP text features of [prompt x B | negative
+    prompt x B] -> PriorDiffusionModel sampling with classifier-free guidance -> CLIP image embedding [B, clip_dim].
+
+    The CLIP text tower, its tokenizer and the decoder's XLM-R text encoder are conditioning PRODUCERS outside the hot path
+    (SURVEY.md section 2 rows 15-16): they enter as callables, so a deployment wraps its own models and the tests use
+    deterministic stand-ins:
+        clip_text(list[str])  -> (txt_feat [n, clip_dim], txt_feat_seq [n, text_ctx, clip_xf_width], mask [n, text_ctx] bool)
+        text_encoder(prompt, batch_size) -> (full_emb [2B, L, D1], pooled_emb [2B, D2])           (2.1 decoder only)
+        clip_image(PIL.Image) -> [1, clip_dim]                                                    (mix_images with images)
+    """
+
+    def __init__(self, prior, clip_text, clip_mean, clip_std, prior_steps="25", prior_cf_scale=4.0, negative_prior_prompt="",
+                 zero_image_emb=None, text_encoder=None, clip_image=None, seed=0):
+        self.prior, self.clip_text, self.text_encoder, self.clip_image = prior, clip_text, text_encoder, clip_image
+        self.clip_mean, self.clip_std = clip_mean, clip_std
+        self.prior_steps, self.prior_cf_scale, self.negative_prior_prompt = int(prior_steps), float(prior_cf_scale), negative_prior_prompt
+        self._zero = zero_image_emb
+        self.seed = seed
+
+    @torch.no_grad()
+    def image_emb(self, prompt, batch_size):
+        dev = self.clip_mean.device
+        feat, seq, mask = self.clip_text([prompt] * batch_size + [self.negative_prior_prompt] * batch_size)
+        use_steps = sorted(_space_timesteps(1000, self.prior_steps))
+        import hashlib
+        g = torch.Generator(device=dev).manual_seed(
+            int.from_bytes(hashlib.sha256(f"{self.seed}:{prompt}".encode()).digest()[:7], "little"))
+        D = self.prior.clip_dim
+        x_T = torch.randn(batch_size, D, device=dev, generator=g)
+        noise = torch.randn(len(use_steps), batch_size, D, device=dev, generator=g)
+        return sample_prior(self.prior, feat.to(dev), seq.to(dev), mask.to(dev), use_steps, self.prior_cf_scale, self.clip_mean,
+                            self.clip_std, x_T, noise).float().cpu()
+
+    def zero_image_emb(self, batch_size):
+        """CLIP embedding of a black image (create_zero_img_emb, kandinsky2_1_model.py:295-297): supplied by the deployment
+        (it needs the CLIP vision tower); zeros when absent."""
+        z = self._zero if self._zero is not None else torch.zeros(1, self.prior.clip_dim)
+        return z.reshape(1, -1).float().cpu().repeat(batch_size, 1)
+
+    def text_emb(self, prompt, batch_size):
+        if self.text_encoder is None:
+            raise K2Error("PriorEmbedder: the Kandinsky 2.1 decoder also needs the XLM-R text encoder outputs: pass text_encoder=")
+        return self.text_encoder(prompt, batch_size)
+
+    def interpolate(self, items, weights, batch_size):
+        """mix_images (kandinsky2_1_model.py:346-383): weighted sum of the prior's embedding for texts and the CLIP image
+        embedding for images."""
+        acc = None
+        for it, w in zip(items, weights):
+            if isinstance(it, str):
+                e = self.image_emb(it, 1)
+            else:
+                if self.clip_image is None:
+                    raise K2Error("PriorEmbedder.interpolate: image items need clip_image=")
+                e = self.clip_image(it).float().cpu()
+            acc = e * w if acc is None else acc + e * w
+        return acc.repeat(batch_size, 1)
+
+
+def _space_timesteps(num_timesteps, count):
+    """respace.py:24-72 with one section (the prior's timestep_respacing=str(prior_steps))."""
+    stride = 1 if count <= 1 else (num_timesteps - 1) / (count - 1)
+    cur, out = 0.0, set()
+    for _ in range(count):
+        out.add(round(cur))
+        cur += stride
+    return out

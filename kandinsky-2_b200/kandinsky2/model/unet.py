@@ -30,6 +30,10 @@ from ..launch_plan import LaunchPlan
 _UP2 = os.environ.get("K2_UP2", "1") != "0"
 
 
+# diffusers ImageHintTimeEmbedding.input_hint_block: (Cin, Cout, stride) of its eight 3x3 convolutions (SiLU between them)
+_HINT_STEM = [(3, 16, 1), (16, 16, 1), (16, 32, 2), (32, 32, 1), (32, 96, 2), (96, 96, 1), (96, 256, 2), (256, 4, 1)]
+
+
 def _topology(in_ch, mc, mult, nrb, attention_ds):
     """Stages as lists of blocks; block = list of ('conv', cin, cout) | ('res', cin, cout, updown) | ('attn', ch)."""
     ch = mult[0] * mc
@@ -73,7 +77,7 @@ class Text2ImUNet(nn.Module):
                  num_res_blocks, attention_resolutions, dropout=0, channel_mult=(1, 2, 4, 8), conv_resample=True,
                  dims=2, num_classes=None, use_checkpoint=False, use_fp16=False, num_heads=1, num_head_channels=-1,
                  num_heads_upsample=-1, use_scale_shift_norm=False, resblock_updown=False, cache_text_emb=True,
-                 use_flash_attention=False, cond_version="2.1", device=None, param_dtype=torch.float32):
+                 use_flash_attention=False, cond_version="2.1", device=None, param_dtype=torch.float32, hint_channels=0):
         super().__init__()
         if not (use_scale_shift_norm and resblock_updown and num_head_channels == 64 and dims == 2 and
                 num_classes is None and dropout == 0):
@@ -94,6 +98,11 @@ class Text2ImUNet(nn.Module):
         self.pooling_type = pooling_type
         self.cache_text_emb = cache_text_emb
         self.cond_version = cond_version
+        # Kandinsky 2.2 ControlNet-depth (BASELINE configs[4]; diffusers addition_embed_type="image_hint"): `hint_channels` of
+        # the in_channels come from add_embedding.input_hint_block(hint) instead of the caller's x
+        self.hint_channels = hint_channels
+        if hint_channels and (cond_version != "2.2" or hint_channels != 4):
+            raise NotImplementedError("the hint stem belongs to the 2.2 head and produces 4 feature channels")
         self.use_fp16 = use_fp16
         self.dtype = torch.float16 if use_fp16 else torch.float32  # reported only; storage is always fp16 NHWC
         self.image_encoder_in_dim = image_encoder_in_dim
@@ -158,6 +167,10 @@ class Text2ImUNet(nn.Module):
             P("encoder_hid_proj.norm.weight", model_dim); P("encoder_hid_proj.norm.bias", model_dim)
             P("add_embedding.image_proj.weight", temb, image_encoder_in_dim); P("add_embedding.image_proj.bias", temb)
             P("add_embedding.image_norm.weight", temb); P("add_embedding.image_norm.bias", temb)
+            if hint_channels:
+                for i, (ci, co, _) in enumerate(_HINT_STEM):
+                    P(f"add_embedding.input_hint_block.{2 * i}.weight", co, ci, 3, 3)
+                    P(f"add_embedding.input_hint_block.{2 * i}.bias", co)
 
     @torch.no_grad()
     def init_synthetic_(self, seed=0):
@@ -268,6 +281,13 @@ class Text2ImUNet(nn.Module):
             pk["ipn_w"], pk["ipn_b"] = f32("encoder_hid_proj.norm.weight"), f32("encoder_hid_proj.norm.bias")
             pk["ae_w"], pk["ae_b"] = f32("add_embedding.image_proj.weight"), f32("add_embedding.image_proj.bias")
             pk["aen_w"], pk["aen_b"] = f32("add_embedding.image_norm.weight"), f32("add_embedding.image_norm.bias")
+            if self.hint_channels:
+                hw = []
+                for i, (ci, co, _) in enumerate(_HINT_STEM):
+                    w = self._param(f"add_embedding.input_hint_block.{2 * i}.weight")
+                    wp = ops.pack_stem_weight(w) if i == 0 else ops.pack_conv_weight(w)
+                    hw.append((ops.pad_rows(wp, 16), f32(f"add_embedding.input_hint_block.{2 * i}.bias")))
+                pk["hint"] = hw
         self._packed = pk
         self._plans = {}
         self.cache = None
@@ -285,7 +305,26 @@ class Text2ImUNet(nn.Module):
         return d[key]
 
     # ---------------------------------------------------------------- conditioning (once per generation)
-    def get_text_emb(self, full_emb=None, pooled_emb=None, image_emb=None):
+    def hint_features(self, hint):
+        """diffusers ImageHintTimeEmbedding.input_hint_block: hint fp32 [N, 3, 8h, 8w] -> features fp32 NCHW [N, 4, h, w]
+        (eight 3x3 convolutions on tensor cores, SiLU between them, three of them stride 2 = 'same' conv + keeping the even
+        pixels).  Runs once per generation."""
+        pk = self._packed
+        hint = hint.float().contiguous()
+        h = None
+        for i, ((ci, co, stride), (w, b)) in enumerate(zip(_HINT_STEM, pk["hint"])):
+            last = i + 1 == len(_HINT_STEM)
+            if i == 0:
+                h = ops.conv_gemm([(ops.stem_im2col(hint), 1)], w, co, bias=b)
+            else:
+                h = ops.conv_gemm([(h, 9)], w, co, bias=b, out_mode=1 if last else 0)
+            if stride == 2:
+                h = ops.subsample2(h, 0, 0)
+            if not last:
+                ops.silu_f16_(h)
+        return h
+
+    def get_text_emb(self, full_emb=None, pooled_emb=None, image_emb=None, hint=None):
         """text2im_model2_1.py:57-80. Returns and caches dict(xf_proj fp32 [N,4mc], xf_out fp16 [N,ctx,model_dim],
         enc_kv {attention layer -> fp16 [N,ctx,2C]}): the encoder K/V projections are constant over the
         sampling loop, so they are hoisted out of the per-step forward."""
@@ -314,20 +353,24 @@ class Text2ImUNet(nn.Module):
         for p, a in pk["attn"].items():
             enc_kv[p] = ops.gemm_rows(xf16, a["wenc"], a["wenc"].shape[0], bias=a["benc"])
         out = dict(xf_proj=xf_proj, xf_out=xf16, enc_kv=enc_kv)
+        if self.hint_channels:
+            if hint is None:
+                raise K2Error("this UNet was built with a ControlNet hint stem: pass hint= [N, 3, 8h, 8w]")
+            out["hint_feat"] = self.hint_features(hint)
         if self.cache_text_emb:
             self.cache = out
         return out
 
     # ---------------------------------------------------------------- forward
     def forward(self, x, timesteps, full_emb=None, pooled_emb=None, image_emb=None, inpaint_image=None,
-                inpaint_mask=None):
+                inpaint_mask=None, hint=None):
         """x [N, 4, h, w] (any float dtype), timesteps [N] -> [N, out_channels, h, w] in x.dtype
         (text2im_model2_1.py:85-103; inpaint variant :146-155)."""
         if not x.is_cuda:
             raise K2Error("k2b200 UNet: input must be a CUDA tensor (no CPU fallback)")
         if self._packed is None:
             self.finalize()
-        cond = self.get_text_emb(full_emb=full_emb, pooled_emb=pooled_emb, image_emb=image_emb)
+        cond = self.get_text_emb(full_emb=full_emb, pooled_emb=pooled_emb, image_emb=image_emb, hint=hint)
         N, _, H, W = x.shape
         plan = self._plan(N, H, W, cond["xf_out"].shape[1])
         plan.bind(cond)
@@ -369,8 +412,10 @@ class _Plan(LaunchPlan):
         self.m = model
         self.N, self.H, self.W, self.ctx = N, H, W, ctx
         f32 = dict(device=dev, dtype=torch.float32)
-        lat = model._latent_channels if model._inpainting else model.in_channels
+        lat = model._latent_channels if model._inpainting else model.in_channels - model.hint_channels
         self.x_in = torch.zeros(N, lat, H, W, **f32)
+        if model.hint_channels:
+            self.hint_in = torch.zeros(N, model.hint_channels, H, W, **f32)
         self.t_in = torch.zeros(N, **f32)
         if model._inpainting:
             self.img_in = torch.zeros(N, lat, H, W, **f32)
@@ -386,6 +431,8 @@ class _Plan(LaunchPlan):
         if self._bound is cond:
             return
         self.xf_proj.copy_(cond["xf_proj"])
+        if self.m.hint_channels:
+            self.hint_in.copy_(cond["hint_feat"])
         for p, buf in self.enc_kv.items():
             src = cond["enc_kv"][p]
             if buf.shape != src.shape:
@@ -422,6 +469,8 @@ class _Plan(LaunchPlan):
         h = self._new(N, H, W, inp[0][0][2])
         if m._inpainting:
             S(lambda: ops.stem_im2col(self.x_in, self.img_in, self.mask_in, mul23=True, kpad=kpad, out=patches), "stem_im2col")
+        elif m.hint_channels:  # conv_in sees cat([x, hint features])
+            S(lambda: ops.stem_im2col(self.x_in, self.hint_in, kpad=kpad, out=patches), "stem_im2col")
         else:
             S(lambda: ops.stem_im2col(self.x_in, kpad=kpad, out=patches), "stem_im2col")
         self._conv([(patches, 1)], pk["stem_w"], h.shape[-1], h, 2 * N * H * W * h.shape[-1] * 9 * cin, bias=pk["stem_b"])

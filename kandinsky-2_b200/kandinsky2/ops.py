@@ -322,6 +322,14 @@ def f32_to_f16(x, out=None):
     return out
 
 
+def silu_f16_(x):
+    """SiLU in place on a contiguous fp16 tensor."""
+    lib = nat.load()
+    assert x.dtype == torch.float16 and x.is_contiguous()
+    check(lib.k2_silu_f16(ptr(x), ptr(x), x.numel(), stream_ptr()))
+    return x
+
+
 def stem_im2col(x, x2=None, x3=None, mul23=False, kpad=None, out=None):
     """fp32 NCHW inputs -> fp16 [NB, H, W, kpad] 3x3 patches of cat([x, x2*(x3 if mul23), x3], 1)."""
     lib = nat.load()

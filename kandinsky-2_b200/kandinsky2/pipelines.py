@@ -79,6 +79,8 @@ class _DecoderBase:
         self.task_type = task_type
         self.use_fp16 = True
         mc = dict(config["model_config"])
+        if task_type == "controlnet":  # Kandinsky 2.2 ControlNet-depth (BASELINE configs[4]): 4 latent + 4 hint-feature channels
+            mc.update(in_channels=mc["in_channels"] + 4, hint_channels=4)
         self.model = create_model(**mc, up=False, inpainting=(task_type == "inpainting"), device=self.device,
                                   param_dtype=torch.float16)
         if unet_state_dict is not None:
@@ -244,7 +246,7 @@ class Kandinsky2_2(_DecoderBase):
 
     @torch.no_grad()
     def _decode_loop(self, image_embeds, negative_embeds, batch_size, steps, guidance, h, w, latents=None,
-                     inpaint_latent=None, inpaint_mask=None, init_step=None):
+                     inpaint_latent=None, inpaint_mask=None, init_step=None, hint=None):
         """The body of diffusers KandinskyV22Pipeline.__call__ (reference call sites kandinsky2_2_model.py:78-80,
         106-111,138-141,168-172): uncond rows first, DDPM learned-range step, +-2 clip, no dynamic threshold."""
         H, W = h // 8, w // 8
@@ -254,6 +256,8 @@ class Kandinsky2_2(_DecoderBase):
         parallel.broadcast_conditioning(cond, src=0)
         rows = list(range(lo, hi)) + list(range(batch_size + lo, batch_size + hi))
         kw = {"image_emb": cond["image_emb"][rows].contiguous()}
+        if hint is not None:  # one depth map for the whole batch (cond and uncond rows alike, as the diffusers pipeline does)
+            kw["hint"] = hint.to(self.device).float().expand(2 * B, -1, -1, -1).contiguous()
         if latents is None:
             x = self._latents(lo, hi, (4, H, W))
             latents = torch.cat([x, x], 0)
@@ -311,6 +315,23 @@ class Kandinsky2_2(_DecoderBase):
         x = ac ** 0.5 * lat + (1.0 - ac) ** 0.5 * noise
         return self._decode_loop(pos, neg, batch_size, decoder_steps, decoder_guidance_scale, h, w,
                                  latents=x.repeat(2 * batch_size, 1, 1, 1), init_step=start)
+
+    def generate_controlnet(self, prompt, hint, batch_size=1, decoder_steps=50, prior_steps=25, decoder_guidance_scale=4,
+                            prior_guidance_scale=4, h=512, w=512, negative_prior_prompt="", negative_decoder_prompt=""):
+        """Kandinsky 2.2 ControlNet-depth (BASELINE configs[4]).  The reference package has no method for it -- its
+        notebooks/kandinsky2_2_controlnet.ipynb calls diffusers' KandinskyV22ControlnetPipeline(image_embeds=...,
+        negative_image_embeds=..., hint=hint, height=h, width=w) directly -- so this follows the sibling methods' signature.
+        hint: depth map tensor [1, 3, h, w] in [0, 1] (the pipeline object must be built with task_type="controlnet")."""
+        if self.task_type != "controlnet":
+            raise ValueError("generate_controlnet needs a pipeline built with task_type='controlnet'")
+        h, w = self.get_new_h_w(h, w)
+        pos, neg = self._embeds(prompt, batch_size, negative_decoder_prompt)
+        hint = torch.as_tensor(hint).float()
+        if hint.dim() == 3:
+            hint = hint[None]
+        if tuple(hint.shape[-2:]) != (h, w):
+            hint = torch.nn.functional.interpolate(hint, (h, w), mode="bilinear", align_corners=False)
+        return self._decode_loop(pos, neg, batch_size, decoder_steps, decoder_guidance_scale, h, w, hint=hint)
 
     def generate_inpainting(self, prompt, pil_img, img_mask, batch_size=1, decoder_steps=50, prior_steps=25,
                             decoder_guidance_scale=4, prior_guidance_scale=4, h=512, w=512, negative_prior_prompt="",

@@ -317,3 +317,21 @@ def test_plms_loop_matches_oracle_rule():
     rel = ((out[:B] - x).norm() / x.norm()).item()
     assert rel < 3e-2, rel
 
+
+
+def test_pipeline_controlnet_22():
+    """Kandinsky2_2(task_type="controlnet").generate_controlnet (BASELINE configs[4]): surface, determinism, and the hint
+    actually steering the result."""
+    from kandinsky2 import get_kandinsky2
+    pipe = get_kandinsky2("cuda", task_type="controlnet", model_version="2.2", cache_dir="/nonexistent",
+                          config_overrides=_tiny_overrides())
+    g = torch.Generator().manual_seed(3)
+    hint = torch.rand(1, 3, 64, 64, generator=g)
+    a = pipe.generate_controlnet("a red cat", hint, batch_size=2, decoder_steps=3, h=64, w=64)
+    b = pipe.generate_controlnet("a red cat", hint, batch_size=2, decoder_steps=3, h=64, w=64)
+    c = pipe.generate_controlnet("a red cat", 1.0 - hint, batch_size=2, decoder_steps=3, h=64, w=64)
+    assert len(a) == 2 and a[0].size == (64, 64)
+    assert all(x.tobytes() == y.tobytes() for x, y in zip(a, b))
+    assert a[0].tobytes() != c[0].tobytes()
+    with pytest.raises(ValueError):
+        get_kandinsky2("cuda", task_type="controlnet", model_version="2.1", cache_dir="/nonexistent")

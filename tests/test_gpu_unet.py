@@ -297,3 +297,76 @@ def test_unet_without_conditioning_cache():
     _check(m(x, t, **k1), uo.unet_forward(sdc, cfg, x, t, **k1))
     _check(m(x, t, **k2), uo.unet_forward(sdc, cfg, x, t, **k2))   # no stale conditioning
     assert m.cache is None
+
+
+def test_unet2dconditionmodel_shaped_front():
+    """K2UNet2DConditionModel (kandinsky2/diffusers_compat.py): built from a diffusers-named state dict, called the way the
+    Kandinsky 2.2 pipelines call `self.unet` (kandinsky2_2_model.py:26-42 hands a UNet2DConditionModel to the pipelines) --
+    same numbers as the Text2ImUNet it wraps, and the fp32 oracle within the usual bound."""
+    from kandinsky2.checkpoints import k2_to_diffusers_unet
+    from kandinsky2.diffusers_compat import K2UNet2DConditionModel
+    from oracle import synth
+    from oracle import unet_oracle as uo
+    _no_tf32()
+    cfg = dict(uo.CONFIG_2_2, model_channels=128, num_res_blocks=2, model_dim=256)
+    sd = synth.synth_state_dict(uo.unet_param_spec(cfg), seed=6)
+    dsd = k2_to_diffusers_unet(sd, model_channels=128, num_res_blocks=2)
+    assert any(k.startswith("down_blocks.") for k in dsd) and not any(k.startswith("input_blocks.1") for k in dsd)
+    front = K2UNet2DConditionModel.from_state_dict(dsd, model_channels=128, num_res_blocks=2, model_dim=256)
+    assert front.config.in_channels == 4 and front.config.out_channels == 8 and front.dtype == torch.float16
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(4, 4, 32, 32, generator=g).cuda().half()
+    emb = torch.randn(4, 1280, generator=g).cuda().half()
+    out = front(sample=x, timestep=torch.tensor(640), encoder_hidden_states=None, added_cond_kwargs={"image_embeds": emb},
+                return_dict=False)[0]
+    assert out.shape == (4, 8, 32, 32) and out.dtype == torch.float16
+    out2 = front(x, 640.0, added_cond_kwargs={"image_embeds": emb}).sample
+    assert torch.equal(out, out2)
+    direct = _build(cfg, sd)(x, torch.full((4,), 640.0).cuda(), image_emb=emb)
+    assert torch.equal(out, direct)
+    with torch.no_grad():
+        ref = uo.unet_forward({k: v.cuda() for k, v in sd.items()}, cfg, x.float(), torch.full((4,), 640.0).cuda(), image_emb=emb.float())
+    _check(out.float(), ref, max_frac=1.5e-2, rel_l2=3e-3)   # + fp16 rounding of the inputs and of the returned tensor
+    emb2 = torch.randn(4, 1280, generator=g).cuda().half()    # new embeddings must not hit the stale conditioning cache
+    out3 = front(x, 640, added_cond_kwargs={"image_embeds": emb2}).sample
+    assert not torch.equal(out3, out)
+
+
+def test_controlnet_depth_unet_vs_restated_oracle():
+    """BASELINE configs[4]: the Kandinsky 2.2 ControlNet-depth denoiser = the 2.2 backbone with in_channels 8 on
+    cat([latent, input_hint_block(depth hint)]) (diffusers ImageHintTimeEmbedding; PARITY UNPINNED, restated in
+    oracle/controlnet_oracle.py).  Mid-size topology, hint 8x the latent size; also through the UNet2DConditionModel-shaped
+    front with added_cond_kwargs={"image_embeds", "hint"}, and the hint features alone."""
+    from kandinsky2.diffusers_compat import K2UNet2DConditionModel
+    from kandinsky2.model.unet import Text2ImUNet
+    from oracle import controlnet_oracle as co, synth
+    from oracle import unet_oracle as uo
+    _no_tf32()
+    cfg = dict(co.CONFIG_2_2_HINT, model_channels=128, num_res_blocks=2, model_dim=256)
+    sd = synth.synth_state_dict(co.param_spec(cfg), seed=7)
+    m = Text2ImUNet(model_dim=256, image_encoder_in_dim=1280, num_image_embs=32, pooling_type="from_model", in_channels=8,
+                    model_channels=128, out_channels=8, num_res_blocks=2, attention_resolutions=(2, 4, 8), channel_mult=(1, 2, 3, 4),
+                    use_fp16=True, num_head_channels=64, use_scale_shift_norm=True, resblock_updown=True, cond_version="2.2",
+                    hint_channels=4)
+    m.load_state_dict(sd, strict=True)
+    m.to("cuda")
+    g = torch.Generator().manual_seed(14)
+    B, H, W = 2, 24, 32
+    x = torch.randn(B, 4, H, W, generator=g).cuda()
+    t = torch.tensor([900.0, 80.0]).cuda()
+    emb = torch.randn(B, 1280, generator=g).cuda()
+    hint = torch.rand(B, 3, 8 * H, 8 * W, generator=g).cuda()
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    m.finalize()
+    feat = m.hint_features(hint)
+    with torch.no_grad():
+        feat_ref = co.hint_features(sdc, hint)
+        ref = co.unet_forward(sdc, cfg, x, t, emb, hint)
+    assert feat.shape == feat_ref.shape == (B, 4, H, W)
+    assert ((feat - feat_ref).norm() / feat_ref.norm()).item() < 4e-3
+    y = m(x, t, image_emb=emb, hint=hint)
+    err, rel = _check(y, ref)
+    print(f"controlnet-depth UNet: max abs {err:.3e} rel L2 {rel:.3e}")
+    front = K2UNet2DConditionModel(m)
+    y2 = front(x, t, added_cond_kwargs={"image_embeds": emb, "hint": hint}, return_dict=False)[0]
+    assert torch.equal(y2, y)

@@ -60,3 +60,39 @@ def test_prior_sampling_matches_reference_golden():
     ref = fx["sample"].cuda()
     rel = ((s - ref).norm() / ref.norm()).item()
     assert rel < 3e-2, rel
+
+
+def test_prior_embedder_drives_the_pipeline():
+    """The prior wired in behind the pipelines' embedder protocol (kandinsky2_1_model.py:159-182, 300-344: generate_clip_emb
+    -> generate_img): CLIP-text stand-in -> k2 prior sampling -> image embedding -> Kandinsky2_1.generate_text2img."""
+    from kandinsky2 import get_kandinsky2
+    from kandinsky2.model.prior import PriorEmbedder, PriorTransformer
+    from kandinsky2.pipelines import SyntheticEmbedder
+    from tests.test_gpu_movq_sampler import _tiny_overrides
+    torch.manual_seed(0)
+    prior = PriorTransformer(text_ctx=16, xf_width=128, xf_layers=2, xf_heads=2, xf_final_ln=True, xf_padding=False, clip_dim=768,
+                             clip_xf_width=96, device="cuda")
+    for p in prior.parameters():
+        p.data.normal_(0.0, 0.05) if p.dim() > 1 else p.data.normal_(0.0, 0.02).add_(1.0 if p.dim() == 1 and p.numel() == 128 else 0.0)
+    calls = []
+
+    def clip_text(prompts):  # deterministic stand-in for tokenizer + CLIP text tower
+        calls.append(list(prompts))
+        outs = []
+        for p in prompts:
+            g = torch.Generator().manual_seed(len(p) + 17 * sum(map(ord, p)))
+            outs.append((torch.randn(768, generator=g), torch.randn(16, 96, generator=g), torch.arange(16) < 3 + len(p) % 8))
+        return tuple(torch.stack(t) for t in zip(*outs))
+
+    syn = SyntheticEmbedder(768)
+    emb = PriorEmbedder(prior, clip_text, clip_mean=torch.zeros(768, device="cuda"), clip_std=torch.ones(768, device="cuda"),
+                        prior_steps="5", prior_cf_scale=4, text_encoder=syn.text_emb)
+    e1, e2 = emb.image_emb("a red cat", 2), emb.image_emb("a red cat", 2)
+    assert e1.shape == (2, 768) and torch.equal(e1, e2) and torch.isfinite(e1).all()
+    assert calls[0] == ["a red cat", "a red cat", "", ""]      # [prompt x B | negative prior prompt x B]
+    assert not torch.allclose(e1, emb.image_emb("a blue dog", 2))
+    pipe = get_kandinsky2("cuda", task_type="text2img", model_version="2.1", cache_dir="/nonexistent", embedder=emb,
+                          config_overrides=_tiny_overrides())
+    imgs = pipe.generate_text2img("a red cat", num_steps=3, batch_size=2, guidance_scale=4, h=64, w=64, sampler="p_sampler")
+    mixed = pipe.mix_images(["a cat", "a dog"], [0.4, 0.6], num_steps=3, batch_size=1, h=64, w=64, sampler="p_sampler")
+    assert len(imgs) == 2 and imgs[0].size == (64, 64) and len(mixed) == 1
