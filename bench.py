@@ -157,9 +157,9 @@ def run_reference(args):
     per_fwd = sum(times) / len(times)
     ms_per_step = per_fwd * args.batch * 1e3
     value = 1e3 / ms_per_step
-    sample = (f"each timed step = one CFG-doubled fp32 forward of 1 of the {args.batch} images (UNet batch 2 of "
-              f"{2 * args.batch}) at {lat_h}x{lat_w}, full 1.22B model, oracle port of the reference modules; "
-              f"step time scaled x{args.batch}")
+    sample = (f"EXTRAPOLATED: each timed step = one CFG-doubled fp32 forward of 1 of the {args.batch} images (UNet batch 2 "
+              f"of {2 * args.batch}) at {lat_h}x{lat_w}, full 1.22B model, oracle port of the reference modules (the reference "
+              f"itself is Python and is not on this box); step time = that forward x{args.batch}")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -463,8 +463,8 @@ def run_k2(args):
         t = cpu_oracle_sample(1, H, W, threads, reps=1, warm=0)[0]
         v = 1.0 / (t * B)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": f"one CFG-doubled fp32 oracle forward of 1 of the {B} images at {H}x{W} "
-                                          f"({t:.1f} s), step time scaled x{B}"}
+                                "sample": f"EXTRAPOLATED: one CFG-doubled fp32 oracle forward of 1 of the {B} images at "
+                                          f"{H}x{W} ({t:.1f} s), step time = that x{B}"}
     if not args.no_images:
         # BASELINE's second figure: images/s of the whole decoder call (50 denoising steps + MoVQ decode + uint8), through
         # the public pipeline API, each rank generating its own `batch` images.

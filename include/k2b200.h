@@ -162,6 +162,13 @@ int k2_attention_d64(const void* qkv, int ldq, int hs, int q_off, int k_off, int
                      int lde, int ehs, int ek_off, int ev_off, int B, int heads, int T, int Tc, float scale,
                      void* out, int ldo, k2_stream_t stream);
 
+/* One head of width 512 over T tokens, no [T, T] score matrix: the MoVQ AttnBlock (movq_modules.py:201-225; the encoder's
+ * twin vqgan_blocks.py:186-240).  qkv fp16 rows [B, T, ldq] with q / k / v at element offsets q_off / k_off / v_off (512 channels
+ * each); out fp16 [B, T, ldo] (512 channels); scale multiplies q.k (the reference: C ** -0.5).  A CTA owns 128 queries and half
+ * of the output channels (TMEM holds 256 columns of O + two score buffers), so the score tile is computed twice per query tile. */
+int k2_attention_d512(const void* qkv, int ldq, int q_off, int k_off, int v_off, int B, int T, float scale, void* out, int ldo,
+                      k2_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Small dense layers (fp32 math): nn.Linear (+ optional SiLU on the input and/or the output),
  * nn.LayerNorm, and the sinusoidal timestep embedding.

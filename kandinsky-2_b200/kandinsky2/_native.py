@@ -54,6 +54,7 @@ SIGNATURES = {
     "k2_gn_apply_fold": (_I, [_P, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P, _I, _P, _I, _F, _P, _P, _P, _I, _I, _I, _P, _I, _P,
                               _I, _P]),
     "k2_attention_d64": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P, _I, _P]),
+    "k2_attention_d512": (_I, [_P, _I, _I, _I, _I, _I, _I, _F, _P, _I, _P]),
     "k2_linear": (_I, [_P, _I, _P, _I, _P, _P, _I, _P, _I, _I, _I, _I, _I, _I, _P]),
     "k2_layernorm": (_I, [_P, _P, _P, _P, _I, _I, _F, _P]),
     "k2_timestep_embedding": (_I, [_P, _P, _I, _I, _F, _P]),

@@ -279,6 +279,17 @@ def attention_d64(qkv, heads, enc=None, scale=0.125, out=None, hs=192, q_off=0, 
     return out
 
 
+def attention_d512(qkv, scale, out=None, q_off=0, k_off=512, v_off=1024):
+    """qkv fp16 [B, T, >= 1536] (q | k | v of ONE head of width 512) -> fp16 [B, T, 512]; the MoVQ AttnBlock fused."""
+    lib = nat.load()
+    B, T = qkv.shape[:2]
+    if out is None:
+        out = torch.empty((B, T, 512), dtype=torch.float16, device=qkv.device)
+    check(lib.k2_attention_d512(ptr(qkv), qkv.stride(1), q_off, k_off, v_off, B, T, float(scale), ptr(out), out.stride(1),
+                                stream_ptr()))
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # small dense layers
 # ------------------------------------------------------------------------------------------------

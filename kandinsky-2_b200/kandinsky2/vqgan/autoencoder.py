@@ -17,12 +17,19 @@ ONE CUDA graph; nothing loops over images on the host.  Kernel program (activati
   Upsample                 no upsampled tensor: conv3x3(nearest_2x(h)) = four 2x2 phase convolutions over h itself
                            (k2_conv_gemm taps = 4, 2.25x fewer MACs; movq_modules.py:93-97)
 """
+import os
+
 import torch
 import torch.nn as nn
 
 from .. import ops
 from .._native import K2Error
 from ..launch_plan import LaunchPlan
+
+
+# MoVQ AttnBlock (one head, C = 512): fused tcgen05 flash kernel (k2_attention_d512) instead of two batched GEMMs around a
+# materialised [T, T] score matrix
+_FUSED_ATTN = os.environ.get("K2_MOVQ_FUSED_ATTN", "1") != "0"
 
 
 class _Node(nn.Module):
@@ -400,6 +407,13 @@ class _MovqPlan(LaunchPlan):
         self._sn(x, zq, d["n"], 0, hn)
         qkv = self._tmp("qkv", B, T, 3 * C)
         self._gemm(hn.view(B, T, C), d["wqkv"], 3 * C, qkv, 2 * B * T * 3 * C * C, bias=d["bqkv"])
+        if C == 512 and _FUSED_ATTN:
+            # fused flash kernel: no [T, T] score matrix (680 MB for four 768 x 768 images) in HBM
+            o = self._tmp("att", B, T, C)
+            self._add(lambda: ops.attention_d512(qkv, C ** -0.5, out=o), "attention", 4 * B * T * T * C)
+            out = self._x(B, H, W, C)
+            self._conv([(o.view(B, H, W, C), 1)], d["wp"], C, out, 2 * B * T * C * C, bias=d["bp"], residual=x)
+            return out
         vT = self._tmp("vT", B, C, T)
         self._add(lambda: ops.transpose_f16(qkv[:, :, 2 * C:], out=vT), "transpose")
         scores = self._tmp("scores", B, T, T)

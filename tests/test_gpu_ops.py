@@ -278,3 +278,20 @@ def test_transpose_and_batched_gemm():
     torch.cuda.synchronize()
     ref_o = torch.einsum("bts,bsc->btc", p.float(), qkv[:, :, 2 * C:].float())
     assert ((o.float() - ref_o).norm() / ref_o.norm()).item() < 1e-3
+
+
+@pytest.mark.parametrize("B,T", [(2, 384), (1, 1152), (2, 320)])
+def test_attention_d512(B, T):
+    """k2_attention_d512 (the MoVQ AttnBlock's softmax(q k^T / sqrt(512)) v, one head of width 512, fused) against torch fp32 on
+    the same fp16 q / k / v; T = 320 exercises a ragged last key block and query tile."""
+    from kandinsky2 import ops
+    g = torch.Generator(device="cuda").manual_seed(41)
+    qkv = torch.randn(B, T, 1536, device="cuda", generator=g).half()
+    qkv[:, :, :512] *= 2.0   # sharper softmax: exercises the running-maximum logic
+    out = ops.attention_d512(qkv, 512 ** -0.5)
+    torch.cuda.synchronize()
+    q, k, v = qkv.float().split(512, dim=-1)
+    ref = torch.softmax(torch.einsum("btc,bsc->bts", q, k) * 512 ** -0.5, dim=-1) @ v
+    err = (out.float() - ref).abs().max().item()
+    rel = ((out.float() - ref).norm() / ref.norm()).item()
+    assert rel < 3e-3 and err < 2e-2 * max(1.0, ref.abs().max().item()), (rel, err)
