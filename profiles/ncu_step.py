@@ -31,12 +31,18 @@ else:
     m = MOVQ(**CONFIG_2_2["image_enc_params"]["params"], device=dev, param_dtype=torch.float16).init_synthetic_(1)
     plan = m._plan("decode", 4, 96, 96)
     plan.x_in.normal_()
+plan._serial = True   # forked branches in line: the launch order under the profiler = the order printed here
 plan.launch()
 torch.cuda.synchronize()
 i = 0
-for fn, kind, flops in plan.steps:
-    print(f"launch {i:4d} {kind:16s} {flops / 1e9:9.2f} GFLOP", flush=True)
-    i += 1
+for fn, kind, flops in plan.steps:  # index = kernels launched before this step (a split-K conv is 2 kernels, a join none)
+    ops.reset_launch_count()
+    fn()
+    n = int(ops.launch_count())
+    if n:
+        print(f"launch {i:4d} {kind:16s} {flops / 1e9:9.2f} GFLOP" + (f"  ({n} kernels)" if n > 1 else ""), flush=True)
+    i += n
+torch.cuda.synchronize()
 torch.cuda.profiler.start()
 plan.launch()
 torch.cuda.synchronize()
