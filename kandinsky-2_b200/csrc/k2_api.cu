@@ -37,11 +37,11 @@ static int g_gn_bps = 0;
 int gn_apply_blocks_per_sm() { return g_gn_bps; }
 int attention_stagger() { return g_attn_stagger; }
 int attention_poly_mode() { return g_attn_poly; }
-static int g_attn_issue = -1;  // -1: take K2_ATTN_ISSUE from the environment at first use (default 0)
+static int g_attn_issue = -1;  // -1: take K2_ATTN_ISSUE from the environment at first use (default 2)
 int attention_issue_mode() {
   if (g_attn_issue < 0) {
     const char* e = getenv("K2_ATTN_ISSUE");
-    g_attn_issue = (e && e[0] == '1') ? 1 : 0;
+    g_attn_issue = (e && e[0] >= '0' && e[0] <= '4') ? (e[0] - '0') : 2;
   }
   return g_attn_issue;
 }
@@ -333,8 +333,8 @@ int k2_set_tuning(int key, int value) {
     g_gn_bps = value;
     return 0;
   }
-  if (key == 9) {  // attention MMA issue order: 0 fixed, 1 event driven
-    g_attn_issue = value ? 1 : 0;
+  if (key == 9) {  // attention variant / MMA issue order, see k2_attention_d64
+    g_attn_issue = (value >= 0 && value <= 4) ? value : 2;
     return 0;
   }
   if (key == 7) {  // diagnostics: device address of the attention trace buffer, low / high 32 bits

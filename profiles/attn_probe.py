@@ -1,4 +1,9 @@
-"""Attention kernel timing at the three UNet geometries for several warpgroup de-phasing delays (tuning key 5)."""
+"""Attention kernel A/B at the three UNet geometries: round-1 kernel (P through shared memory, key 9 = 0) against the
+tensor-memory-P kernel in its three issue orders (key 9 = 2 ping-pong, 3 fixed, 4 event driven), with the MUFU-free
+share of the exponentials (key 6) swept on the ping-pong variant.  Every variant is first checked against a torch fp32
+softmax(QK^T)V on a small slice, then timed with CUDA events; the last part prints the clock64 hand-over trace of
+CTA (0,0,0) in ping-pong mode (softmax points: 0 block start, 1 maximum exchanged, 2 turn taken, 3 / 4 first / second
+32 exponentials done, 5 P handed over; MMA points per tile: P arrived, PV issued, S buffer free, S(j+2) issued)."""
 import os
 import sys
 
@@ -9,21 +14,38 @@ import torch  # noqa: E402
 
 from kandinsky2 import ops  # noqa: E402
 
+
+def reference(qkv, enc, heads, b=0, nq=256):
+    B, T, _ = qkv.shape
+    x = qkv[b].float().view(T, heads, 3, 64)
+    e = enc[b].float().view(-1, heads, 2, 64)
+    q = x[:nq, :, 0]
+    k = torch.cat([e[:, :, 0], x[:, :, 1]], 0)
+    v = torch.cat([e[:, :, 1], x[:, :, 2]], 0)
+    w = torch.softmax(torch.einsum("qhd,khd->hqk", q, k) * 0.125, -1)
+    return torch.einsum("hqk,khd->qhd", w, v).reshape(nq, heads * 64)
+
+
 g = torch.Generator(device="cuda").manual_seed(0)
-for (B, heads, T, Tc) in [(8, 12, 2304, 32), (8, 18, 576, 32), (8, 24, 144, 32)]:
+geoms = [(8, 12, 2304, 32), (8, 18, 576, 32), (8, 24, 144, 32)]
+if len(sys.argv) > 1 and sys.argv[1] == "cfg3":
+    geoms = [(4, 12, 4096, 32), (4, 18, 1024, 32), (4, 24, 256, 32)]
+for (B, heads, T, Tc) in geoms:
     qkv = torch.randn(B, T, heads * 192, device="cuda", generator=g).half()
     enc = torch.randn(B, Tc, heads * 128, device="cuda", generator=g).half()
     out = torch.empty(B, T, heads * 64, device="cuda", dtype=torch.float16)
     flops = 4 * B * heads * T * (T + Tc) * 64
-    # tuning key 6: eighths of the exponentials on the FMA pipe; key 5: initial de-phasing of the two query tiles (cycles)
-    # key 9: MMA issue order (0 fixed per key block, 1 event driven)
-    for mode, delay, stag in ((0, 0, 300), (1, 0, 0), (1, 0, 300), (1, 0, 1000), (1, 0, 1700), (1, 0, 2400), (1, 2, 1700), (1, 3, 1700)):
+    nq = min(T, 384)
+    ref = reference(qkv, enc, heads, b=B - 1, nq=nq)
+    for mode, poly, stag in ((0, 0, 300), (2, 0, 0), (2, 0, 600), (2, 0, 1200), (2, 0, 1800), (2, 0, 2400), (2, 1, 1200), (2, 1, 1800)):
         ops.set_tuning(9, mode)
-        ops.set_tuning(6, delay)
+        ops.set_tuning(6, poly)
         ops.set_tuning(5, stag)
+        out.zero_()
         for _ in range(3):
             ops.attention_d64(qkv, heads, enc, out=out)
         torch.cuda.synchronize()
+        err = (out[B - 1, :nq].float() - ref).abs().max().item()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         for _ in range(20):
@@ -31,8 +53,42 @@ for (B, heads, T, Tc) in [(8, 12, 2304, 32), (8, 18, 576, 32), (8, 24, 144, 32)]
         e.record()
         torch.cuda.synchronize()
         us = s.elapsed_time(e) / 20 * 1e3
-        print(f"T={T} heads={heads} issue={mode} poly={delay}/8 stagger={stag}: {us:.1f} us {flops / us / 1e6:.0f} TF/s", flush=True)
+        print(f"T={T} heads={heads} mode={mode} poly={poly}/8 stagger={stag}: {us:.1f} us {flops / us / 1e6:.0f} TF/s "
+              f"max|err| vs fp32 {err:.2e}", flush=True)
 
-ops.set_tuning(9, 0)
+# hand-over trace, ping-pong mode
+B, heads, T, Tc = 8, 12, 2304, 32
+qkv = torch.randn(B, T, heads * 192, device="cuda", generator=g).half()
+enc = torch.randn(B, Tc, heads * 128, device="cuda", generator=g).half()
+out = torch.empty(B, T, heads * 64, device="cuda", dtype=torch.float16)
+trace = torch.zeros(3 * 16 * 8, device="cuda", dtype=torch.int64)
+addr = trace.data_ptr()
+
+
+def s32(v):
+    v &= 0xFFFFFFFF
+    return v - (1 << 32) if v >= (1 << 31) else v
+
+
+ops.set_tuning(7, s32(addr))
+ops.set_tuning(8, s32(addr >> 32))
+for mode in (2,):
+    ops.set_tuning(9, mode)
+    ops.set_tuning(6, 200)
+    ops.set_tuning(5, 1500)
+    trace.zero_()
+    for _ in range(3):
+        ops.attention_d64(qkv, heads, enc, out=out)
+    torch.cuda.synchronize()
+    t = trace.cpu().view(3, 16, 8).tolist()
+    base = min(v for r in t for b in r for v in b if v > 0)
+    print(f"== trace, key 9 = {mode}")
+    names = ["WG0", "WG1", "MMA"]
+    for r in range(3):
+        for j in range(16):
+            print(f"{names[r]} j={j}: " + " ".join(f"{(v - base) if v else -1:7d}" for v in t[r][j]))
 ops.set_tuning(6, 0)
+ops.set_tuning(7, 0)
+ops.set_tuning(8, 0)
+ops.set_tuning(9, 2)
 ops.set_tuning(5, 300)
