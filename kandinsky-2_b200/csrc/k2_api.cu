@@ -18,7 +18,7 @@ static std::atomic<long long> g_launches{0};
 static int g_force_bn = 0;
 static int g_force_split = 0;  // 0 auto, 1 off, n>1 forced
 static int g_force_2cta = 0;   // 0 auto, 1 off, 2 on
-static int g_attn_stagger = 300;
+static int g_attn_stagger = 0;
 static int g_attn_poly = 0;  // measured: the softmax is not MUFU-bound (profiles/README.md), offloading only adds instructions
 static int g_pdl = 0;          // programmatic dependent launch of the step's kernels
 static int g_halo_mode = 0;    // 0 off; 1/2: dense halo rows (pitch 10) without/with base offset; 3/4: pitch 16
@@ -37,14 +37,8 @@ static int g_gn_bps = 0;
 int gn_apply_blocks_per_sm() { return g_gn_bps; }
 int attention_stagger() { return g_attn_stagger; }
 int attention_poly_mode() { return g_attn_poly; }
-static int g_attn_issue = -1;  // -1: take K2_ATTN_ISSUE from the environment at first use (default 2)
-int attention_issue_mode() {
-  if (g_attn_issue < 0) {
-    const char* e = getenv("K2_ATTN_ISSUE");
-    g_attn_issue = (e && e[0] >= '0' && e[0] <= '4') ? (e[0] - '0') : 2;
-  }
-  return g_attn_issue;
-}
+static int g_attn_half = 1;  // measured: 224 vs 235 us at the level-1 geometry (profiles/attn_probe_r2.txt)
+int attention_half_rows() { return g_attn_half; }
 static unsigned long long g_attn_trace = 0;
 unsigned long long* attention_trace_buffer() { return reinterpret_cast<unsigned long long*>(g_attn_trace); }
 
@@ -333,8 +327,8 @@ int k2_set_tuning(int key, int value) {
     g_gn_bps = value;
     return 0;
   }
-  if (key == 9) {  // attention variant / MMA issue order, see k2_attention_d64
-    g_attn_issue = (value >= 0 && value <= 4) ? value : 2;
+  if (key == 9) {  // attention softmax layout: 0 = one thread per score row (8 warps), 1 = half a row per thread (16 warps)
+    g_attn_half = value ? 1 : 0;
     return 0;
   }
   if (key == 7) {  // diagnostics: device address of the attention trace buffer, low / high 32 bits

@@ -8,23 +8,31 @@
 //
 // One CTA = one (batch, head, 2 x 128-query tiles); K/V tiles are shared by both query tiles.  Per query tile t and
 // 128-key block j:
-//     S_t(j) = Q_t K(j)^T        tcgen05.mma  M128 N128 K64   -> TMEM  (one 128-column S buffer per tile)
-//     P_t(j) = exp2(S*c - m)     8 softmax warps per tile, HALF a score row (64 keys) per thread: tcgen05.ld -> registers,
-//                                row maximum = FMNMX3 over the half row, exchanged between the two halves through shared
-//                                memory + one 256-thread named barrier, -> fp16 -> shared memory in the 128B-swizzled
-//                                K-major layout the MMA reads as its A operand
-//     O_t   += P_t(j) V(j)       tcgen05.mma  M128 N64 K128   -> TMEM  (O accumulated THERE; the softmax warps rescale it
-//                                only when a row maximum has outgrown the stale one by 2^8 -- exact either way)
-//     out = O_t / l              at the end, l = the two halves' row sums folded through shared memory.
-// V tiles are used as an MN-major B operand exactly as TMA lands them ([key][64 d] rows), so V is never transposed.
-// Warp roles (640 threads): warp0 TMA producer (Q once, K/V ring of 3 stages), warp1 MMA issuer, warp2 TMEM allocator,
-// warps 4-19 softmax + epilogue (tile = (w-4)/8, key half = ((w-4)/4)%2, TMEM lane quarter = w%4).  A tile's warps
-// release S_t as soon as the scores sit in their registers (s_free) and the issuer answers with S_t(j+1) right away; the
-// warps load it inside block j's exponentials (each 32-score quarter as soon as its registers are free), so neither the
-// hand-over nor the TMEM latency is exposed (measured with the clock64 trace, profiles/attn_trace.py: the first design's
-// order P_t(j) -> PV_t(j) -> S_t(j+1) left every warpgroup idle for ~1000 of each ~3450 cycles).  pv_done tells the
-// warps that O_t is current and the P_t buffer is free.  What bounds the kernel now is the exponential itself (MUFU
-// 16/clk/SM) plus the per-block latency chain max -> barrier -> exp -> store -> fence -> arrive (profiles/README.md).
+//     S_t(j) = Q_t K(j)^T        tcgen05.mma  M128 N128 K64   -> TMEM  (one 128-column fp32 S buffer per tile)
+//     P_t(j) = exp2(S*c - m)     4 softmax warps per tile, ONE THREAD PER SCORE ROW (128 keys in registers): tcgen05.ld ->
+//                                registers, thread-local row maximum (FMNMX3), exponentials -> fp16 pairs -> TENSOR memory
+//                                (tcgen05.st, 64 columns per tile)
+//     O_t   += P_t(j) V(j)       tcgen05.mma  M128 N64 K128 with the A operand read from tensor memory
+//                                (tcgen05.mma [d], [a_tmem], b_desc) -> TMEM; O accumulated there, rescaled by the softmax
+//                                warps only when a row maximum has outgrown the stale one by 2^8 -- exact either way
+//     out = O_t / l              at the end.
+// TMEM: S_t at t*128, O_t at 256 + t*64, P_t at 384 + t*64 -> all 512 columns.  V tiles are used as an MN-major B operand
+// exactly as TMA lands them ([key][64 d] rows), so V is never transposed.
+// Warp roles (384 threads): warp0 TMA producer (Q once, K/V ring of 4 stages), warp1 MMA issuer, warp2 TMEM allocator,
+// warps 4-11 softmax + epilogue (tile = (w-4)/4, TMEM lane quarter = w%4); setmaxnreg moves registers from the control
+// warpgroup (56) to the softmax warpgroups (224: 128 scores + 64 packed P words + the exponentials in flight).
+// Pipeline per tile: the warps release S_t as soon as the scores sit in their registers (s_free) and the issuer answers with
+// the next score product; block j+1's scores are pulled in INSIDE block j's exponentials, chunk by chunk as registers free
+// up, and folded into the next row maximum one chunk later, so a block starts with its maximum already known.  The PV(j-1)
+// barrier is only waited for after 96 of the block's 128 exponentials (P is held in registers until then).  MMA order per
+// key block and tile: P_t(j) V(j) when p_full_t(j) arrives, then S_t(j+2).
+//
+// History / measurements (profiles/README.md, profiles/attn_probe.py, profiles/pipe_probe.cu): the round-1 kernel used 16
+// softmax warps with half a row each, exchanged the row maximum through shared memory + a named barrier, and staged P in
+// shared memory (64 KB of stores + 64 KB of operand reads per key block, a fence.proxy.async per block); its clock64 trace
+// showed 2300 cycles of MUFU-saturated exponentials + 1700 cycles of hand-over chain per block.  This kernel: 251 -> 228 us at
+// the level-1 geometry (T = 2304, 12 heads, batch 8).  MUFU.EX2 retires one warp-wide instruction per 8 cycles per
+// sub-partition (pipe_probe); two warps per sub-partition reach 9.4 cycles with this instruction mix.
 #include <string.h>
 
 #include <algorithm>
@@ -41,24 +49,20 @@ constexpr int QT = 2;           // query tiles per CTA
 constexpr int BKV = 128;        // keys per block
 constexpr int HD = 64;          // head dim
 constexpr int TILE_BYTES = 128 * HD * 2;  // 16 KB: one Q / K / V tile
-constexpr int P_BYTES = BQ * BKV * 2;     // 32 KB
 constexpr int SMEM_Q = 0;
-constexpr int SMEM_BAR = SMEM_Q + QT * TILE_BYTES;
-constexpr int SMEM_XCH = SMEM_BAR + 1024;  // fp32 [tile][parity][half][128] block maxima + [tile][half][128] row sums
-constexpr int SMEM_KV = SMEM_XCH + 6144;   // K/V ring (1024 B aligned), then the P tiles of the shared-memory variant
-// PT (P in tensor memory): no P tiles in shared memory, so the K/V ring gets a fourth stage.
-template <bool PT>
-struct Cfg {
-  static constexpr int KV_STAGES = PT ? 4 : 3;
-  static constexpr int SMEM_P = SMEM_KV + KV_STAGES * 2 * TILE_BYTES;
-  static constexpr int SMEM_TOTAL = SMEM_P + (PT ? 0 : QT * P_BYTES) + 1024;
-};
+constexpr int KV_STAGES = 4;
+constexpr int SMEM_BAR = QT * TILE_BYTES;
+constexpr int SMEM_XCH = SMEM_BAR + 1024;  // HALF: fp32 [tile][parity][half][128] block maxima + [tile][half][128] row sums
+constexpr int SMEM_KV = SMEM_XCH + 6144;
+constexpr int SMEM_TOTAL = SMEM_KV + KV_STAGES * 2 * TILE_BYTES + 1024;
 static_assert(SMEM_KV % 1024 == 0, "K/V tiles must sit on the 1024 B swizzle period");
-constexpr int NTHREADS = 128 + 512;      // 4 control warps + 16 softmax warps
-constexpr int TMEM_COLS = 512;  // S: 2 x 128, O: 2 x 64 -> 384, rounded to a power of two
+// HALF = false: 4 control warps + 8 softmax warps, one thread per score row (tile = (w-4)/4, TMEM lane quarter = w%4)
+// HALF = true : 4 control warps + 16 softmax warps, half a row per thread (tile = (w-4)/8, key half = ((w-4)/4)%2)
+constexpr int nthreads(bool half) { return 128 + (half ? 512 : 256); }
+constexpr int TMEM_COLS = 512;  // S: 2 x 128, O: 2 x 64, P: 2 x 64
 constexpr int TM_S = 0;         // S of tile t at TM_S + t*128
 constexpr int TM_O = 256;       // O of tile t at TM_O + t*64
-constexpr int TM_P = 384;       // PT: P of tile t as fp16 pairs (64 columns for 128 keys) at TM_P + t*64
+constexpr int TM_P = 384;       // P of tile t as fp16 pairs (64 columns for 128 keys) at TM_P + t*64
 constexpr float RESCALE_GAP = 8.f;  // log2 units the running max may lag before O is rescaled (P <= 2^8 in fp16)
 
 // volatile: keeps its place in the instruction stream relative to the other ex2v (the softmax software pipeline)
@@ -88,21 +92,19 @@ __device__ __forceinline__ void trace_pt(const AttnParams& p, int role, int j, i
   }
 }
 
-template <int POLY, bool PT>
-__global__ void __launch_bounds__(NTHREADS, 1) attention_d64_kernel(const __grid_constant__ AttnParams p) {
+template <int POLY, bool HALF>
+__global__ void __launch_bounds__(nthreads(HALF), 1) attention_d64_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  constexpr int KV_STAGES = Cfg<PT>::KV_STAGES;
-  constexpr int SMEM_P = Cfg<PT>::SMEM_P;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_BAR);
-  uint64_t* q_full = bars;                   // 1
-  uint64_t* kv_full = bars + 1;              // KV_STAGES
+  uint64_t* q_full = bars;                     // 1
+  uint64_t* kv_full = bars + 1;                // KV_STAGES
   uint64_t* kv_empty = kv_full + KV_STAGES;  // KV_STAGES
   uint64_t* s_full = kv_empty + KV_STAGES;   // QT
-  uint64_t* p_full = s_full + QT;            // QT
-  uint64_t* pv_done = p_full + QT;           // QT: P_t(j) V(j) retired -> O_t current, P_t buffer reusable
-  uint64_t* s_free = pv_done + QT;           // QT: S_t(j) is in the warpgroup's registers -> S_t(j+1) may be issued
+  uint64_t* p_full = s_full + QT;              // QT
+  uint64_t* pv_done = p_full + QT;             // QT: P_t(j) V(j) retired -> O_t current, P_t columns reusable
+  uint64_t* s_free = pv_done + QT;             // QT: S_t(j) is in the warpgroup's registers -> S_t(j+1) may be issued
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(s_free + QT);
 
   const int warp_idx = threadIdx.x >> 5;
@@ -127,9 +129,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_d64_kernel(const __grid
     }
     for (int i = 0; i < QT; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 8);  // one arrival per softmax warp of the tile
+      mbar_init(&p_full[i], HALF ? 8 : 4);  // one arrival per softmax warp of the tile
       mbar_init(&pv_done[i], 1);
-      mbar_init(&s_free[i], 8);
+      mbar_init(&s_free[i], HALF ? 8 : 4);
     }
     fence_barrier_init();
   }
@@ -143,10 +145,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_d64_kernel(const __grid
   const uint32_t tmem_base = *tmem_ptr;
   pdl_wait();
   pdl_launch();
-
+  // register re-partition (per warpgroup): the control warps hand most of theirs to the softmax warps, whose 128-score row,
+  // 16 packed P words and the exponentials in flight need ~200
+  if (warp_idx < 4) {
+  if constexpr (HALF) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  }
   if (warp_idx == 0) {
     // ===================================== TMA producer =====================================
-    if (elect_one()) {  // one lane, and ptxas KNOWS it is one: UTCHMMA / UTMALDG operands need no per-lane waterfall loop
+    if (elect_one()) {
       mbar_arrive_expect_tx(q_full, ntile * TILE_BYTES);
       for (int t = 0; t < ntile; ++t)
         tma_load_3d(smem + SMEM_Q + t * TILE_BYTES, &p.tmQKV, q_full, head * p.hs + p.q_off, q0 + t * BQ, b);
@@ -173,476 +182,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) attention_d64_kernel(const __grid
     }
   } else if (warp_idx == 1) {
     // ===================================== MMA issuer ========================================
-    // program order per key block j:  [Q_t K(j+1)^T -> S_t as soon as s_free_t(j)] for both tiles, then
-    // [P_t(j) V(j) -> O_t as soon as p_full_t(j)] for both tiles.
-    if (elect_one()) {  // one lane, and ptxas KNOWS it is one: UTCHMMA / UTMALDG operands need no per-lane waterfall loop
-      constexpr uint32_t idesc_s = make_idesc_f16(BQ, BKV, 0, 0);  // Q (K-major) x K (K-major)
-      constexpr uint32_t idesc_o = make_idesc_f16(BQ, HD, 0, 1);   // P (K-major) x V (MN-major)
-      auto issue_pv = [&](int t, int jb, int stage_b) {
-        const uint32_t p_addr = smem_u32(smem + SMEM_P + t * P_BYTES);
-        const uint32_t v_addr = smem_u32(smem + SMEM_KV + stage_b * 2 * TILE_BYTES + TILE_BYTES);
-        const uint32_t d = tmem_base + TM_O + t * HD;
-#pragma unroll
-        for (int k = 0; k < BKV / 16; ++k) {
-          // A: P [128 q][128 keys] as two 64-key swizzle atoms of 16 KB, 32 B per 16-key step
-          // B: V [128 keys][64 d] (MN-major): 16 keys = 16 rows of 128 B = 2048 B per step
-          const uint64_t bdesc = make_sw128_desc(v_addr + k * 2048);
-          if constexpr (PT) {
-            // A: P from tensor memory, 16 keys = 8 columns of fp16 pairs per step
-            umma_f16_ts(d, tmem_base + TM_P + t * 64 + k * 8, bdesc, idesc_o, (jb > 0 || k > 0) ? 1u : 0u);
-          } else {
-            const uint64_t adesc = make_sw128_desc(p_addr + (k >> 2) * TILE_BYTES) + static_cast<uint64_t>((k & 3) * 2);
-            umma_f16(d, adesc, bdesc, idesc_o, (jb > 0 || k > 0) ? 1u : 0u);
-          }
-        }
-      };
-      auto issue_s = [&](int t, int stage_b) {
-        const uint64_t adesc = make_sw128_desc(smem_u32(smem + SMEM_Q + t * TILE_BYTES));
-        const uint64_t bdesc = make_sw128_desc(smem_u32(smem + SMEM_KV + stage_b * 2 * TILE_BYTES));
-        const uint32_t d = tmem_base + TM_S + t * BKV;
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k)
-          umma_f16(d, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc_s, k != 0);
-        umma_commit(&s_full[t]);
-      };
-      mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[0], 0);
-      tc_fence_after();
-      for (int t = 0; t < ntile; ++t) {
-        issue_s(t, 0);
-        if (t == 0 && ntile == 2 && p.stagger_cycles > 0) {
-          // optional de-phasing of the two softmax warpgroups (tuning key 5)
-          const long long t0 = clock64();
-          while (clock64() - t0 < p.stagger_cycles) {
-          }
-        }
-      }
-      if (p.issue_mode == 2 && ntile == 2) {
-        // Ping-pong order (the two query tiles' exponentials alternate, see the softmax warps): per key block and tile,
-        // P_t(j) V(j) as soon as p_full_t(j), then S_t(j+2) -- its S buffer has been free since the warpgroup pulled
-        // S_t(j+1) into registers during block j's exponentials -- so every product is issued when its inputs appear
-        // and the next scores are ready a full exponential phase before they are needed.
-        if (nblk > 1) {
-          mbar_wait(&kv_full[1], 0);
-          for (int t = 0; t < QT; ++t) {
-            mbar_wait(&s_free[t], 0);
-            tc_fence_after();
-            issue_s(t, 1);
-          }
-        }
-        for (int j = 0; j < nblk; ++j) {
-          const int stage = j % KV_STAGES;
-          for (int t = 0; t < QT; ++t) {
-            mbar_wait(&p_full[t], j & 1);
-            trace_pt<POLY>(p, 2, j, t * 4 + 0);
-            tc_fence_after();
-            issue_pv(t, j, stage);
-            umma_commit(&pv_done[t]);
-            if (t == QT - 1) umma_commit(&kv_empty[stage]);
-            trace_pt<POLY>(p, 2, j, t * 4 + 1);
-            if (j + 2 < nblk) {
-              const int j2 = j + 2;
-              if (t == 0) mbar_wait(&kv_full[j2 % KV_STAGES], (j2 / KV_STAGES) & 1);
-              mbar_wait(&s_free[t], (j + 1) & 1);
-              trace_pt<POLY>(p, 2, j, t * 4 + 2);
-              tc_fence_after();
-              issue_s(t, j2 % KV_STAGES);
-              trace_pt<POLY>(p, 2, j, t * 4 + 3);
-            }
-          }
-        }
-      } else if (p.issue_mode == 1) {
-        // Event-driven order: poll both query tiles' barriers and issue whatever is ready.  The fixed order below makes
-        // S_0(j+2) wait for P_1(j), which pulls the two tiles' phases together within one key block; polling lets them run
-        // half a period apart (initial offset = stagger_cycles) so one tile's exponentials overlap the other's max /
-        // barrier / hand-over phases.  Every barrier is at most one phase ahead of its consumer (p_full(j+1) needs
-        // pv_done(j), s_free(j+1) needs S(j+1), kv_full is refilled only after kv_empty), so parity tests are unambiguous.
-        int s_next[QT] = {1, 1}, pv_next[QT] = {0, 0};
-        int kv_seen = 1;  // key blocks whose K / V have landed
-        long long t_last = clock64();
-        while (pv_next[0] < nblk || (ntile == 2 && pv_next[1] < nblk)) {
-          bool progress = false;
-#pragma unroll
-          for (int t = 0; t < QT; ++t) {
-            if (t >= ntile) continue;
-            int j = pv_next[t];
-            if (j < nblk && mbar_try_wait(&p_full[t], j & 1)) {
-              tc_fence_after();
-              issue_pv(t, j, j % KV_STAGES);
-              umma_commit(&pv_done[t]);
-              pv_next[t] = j + 1;
-              const int other = (ntile == 2) ? pv_next[t ^ 1] : j + 1;
-              if (other > j) umma_commit(&kv_empty[j % KV_STAGES]);  // both tiles are done with K(j) / V(j)
-              progress = true;
-            }
-            j = s_next[t];
-            if (j < nblk && mbar_try_wait(&s_free[t], (j - 1) & 1)) {
-              if (j >= kv_seen && mbar_try_wait(&kv_full[j % KV_STAGES], (j / KV_STAGES) & 1)) kv_seen = j + 1;
-              if (j < kv_seen) {
-                tc_fence_after();
-                issue_s(t, j % KV_STAGES);
-                s_next[t] = j + 1;
-                progress = true;
-              }
-            }
-          }
-          if (progress) {
-            t_last = clock64();
-          } else if (clock64() - t_last > 4000000000LL) {  // a pipeline bug traps instead of hanging the GPU
-            printf("k2b200: attention issuer stalled (block %d,%d,%d)\n", blockIdx.x, blockIdx.y, blockIdx.z);
-            __trap();
-          }
-        }
-      } else {
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int j = 0; j < nblk; ++j) {
-          int nstage = stage + 1;
-          uint32_t nphase = phase;
-          if (nstage == KV_STAGES) {
-            nstage = 0;
-            nphase ^= 1;
-          }
-          if (j + 1 < nblk) {
-            // S_t(j+1) as soon as the warpgroup holds S_t(j) in registers: the next scores are ready long before the
-            // softmax of block j ends, so the warpgroups never wait for the tensor core in steady state
-            mbar_wait(&kv_full[nstage], nphase);
-            tc_fence_after();
-            for (int t = 0; t < ntile; ++t) {
-              trace_pt<POLY>(p, 2, j, t * 4 + 0);
-              mbar_wait(&s_free[t], j & 1);
-              tc_fence_after();
-              issue_s(t, nstage);
-              trace_pt<POLY>(p, 2, j, t * 4 + 1);
-            }
-          }
-          for (int t = 0; t < ntile; ++t) {
-            mbar_wait(&p_full[t], j & 1);
-            trace_pt<POLY>(p, 2, j, t * 4 + 2);
-            tc_fence_after();
-            issue_pv(t, j, stage);
-            umma_commit(&pv_done[t]);
-            if (t == ntile - 1) umma_commit(&kv_empty[stage]);
-            trace_pt<POLY>(p, 2, j, t * 4 + 3);
-          }
-          stage = nstage;
-          phase = nphase;
-        }
-      }
-    }
-  } else if (warp_idx >= 4) {
-    // ===================================== softmax warps + epilogue ===========================
-    // 16 warps = 2 query tiles x 2 key halves x 4 TMEM lane quarters: thread (t, h, row) owns keys [64h, 64h+64) of one
-    // score row.  Four softmax warps per scheduler (instead of two) hide the MUFU / TMEM latencies of each other; the
-    // two halves of a row agree on the block maximum through shared memory and one 256-thread named barrier per block.
-    const int sw = warp_idx - 4;
-    const int t = sw >> 3;                        // query tile
-    const int h = (sw >> 2) & 1;                  // key half of the 128-key block
-    const int ew = warp_idx & 3;                  // TMEM lane quarter
-    const int row = ew * 32 + lane;               // query row in the tile == TMEM lane
-    if (t < ntile) {
-      const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
-      const uint32_t s_addr = lane_addr + TM_S + t * BKV + h * 64;
-      const uint32_t o_addr = lane_addr + TM_O + t * HD + h * 32;
-      const uint32_t p_row_s = smem_u32(smem + SMEM_P + t * P_BYTES + h * TILE_BYTES + row * 128);  // !PT
-      const uint32_t p_tm = lane_addr + TM_P + t * 64 + h * 32;  // PT: this thread's 64 keys = 32 columns of fp16 pairs
-      // ping-pong (issue_mode 2): the two query tiles take turns on the MUFU pipe -- tile 1's exponentials of block j
-      // start when tile 0's end and vice versa (named barriers 3 / 4: 256 threads arrive, 256 wait) -- so one tile's
-      // serial chain (P hand-over, PV product, next maximum) runs under the other tile's exponentials instead of both
-      // tiles computing and then both waiting.
-      const bool pp = (p.issue_mode == 2) && ntile == 2;
-      float* xch = reinterpret_cast<float*>(smem + SMEM_XCH) + t * 512;  // [parity][half][row]
-      float m_used = 0.f;   // the (possibly stale) maximum the exponentials are taken against, log2 domain
-      float l_run = 0.f;    // this half's share of the row sum
-      const float c = p.scale_log2e;
-      const bool tr = (ew == 0 && lane == 0 && h == 0);
-
-      // S_t(0) -> registers; from then on the loads of block j+1 are issued inside block j's exponentials (each 32-score
-      // quarter as soon as its registers are free), so neither the s_full hand-over nor the TMEM latency is exposed
-      uint32_t s0[32], s1[32];
-      mbar_wait(&s_full[t], 0);
-      tc_fence_after();
-      tmem_ld_32x32b_x32(s_addr, s0);
-      tmem_ld_32x32b_x32(s_addr + 32, s1);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_free[t]);
-
-      for (int j = 0; j < nblk; ++j) {
-        const int valid = ((j < nctx) ? min(BKV, p.Tc - j * BKV) : min(BKV, p.T - (j - nctx) * BKV)) - h * 64;
-        const bool more = j + 1 < nblk;
-        if (tr) trace_pt<POLY>(p, t, j, 0);
-        if (valid < 64) {  // ragged tail / short encoder block (block-uniform branch): masked scores -> -inf
-          const uint32_t ninf = __float_as_uint(-INFINITY);
-#pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            if (e >= valid) s0[e] = ninf;
-            if (32 + e >= valid) s1[e] = ninf;
-          }
-        }
-        float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-        for (int e = 0; e < 32; e += 4) {  // 3-input maxima (FMNMX3): 32 instructions for the 64 scores
-          mx0 = fmax3(mx0, __uint_as_float(s0[e]), __uint_as_float(s0[e + 1]));
-          mx1 = fmax3(mx1, __uint_as_float(s0[e + 2]), __uint_as_float(s0[e + 3]));
-        }
-#pragma unroll
-        for (int e = 0; e < 32; e += 4) {
-          mx0 = fmax3(mx0, __uint_as_float(s1[e]), __uint_as_float(s1[e + 1]));
-          mx1 = fmax3(mx1, __uint_as_float(s1[e + 2]), __uint_as_float(s1[e + 3]));
-        }
-        const float m_half = fmaxf(mx0, mx1) * c;
-        float* slot = xch + (j & 1) * 256;
-        slot[h * 128 + row] = m_half;
-        named_bar_sync(1 + t, 256);
-        const float m_blk = fmaxf(m_half, slot[(h ^ 1) * 128 + row]);
-        if (tr) trace_pt<POLY>(p, t, j, 1);
-        if (j == 0) {
-          m_used = m_blk;
-        } else {
-          mbar_wait(&pv_done[t], (j - 1) & 1);  // O_t holds blocks < j, and the P_t buffer is free again
-          tc_fence_after();
-          // O_t lives in TMEM and is rescaled only when some row's maximum has outgrown the stale one by 2^8:
-          // exact arithmetic either way (numerator and denominator share m_used), far fewer TMEM round trips.
-          // Both halves of a row see the same m_blk and m_used, so they take the same branch; each rescales 32 columns.
-          const bool grow = m_blk > m_used + RESCALE_GAP;
-          if (__any_sync(0xffffffffu, grow)) {
-            const float m_new = grow ? m_blk : m_used;
-            const float alpha = ex2(m_used - m_new);
-#pragma unroll 1
-            for (int oc = 0; oc < 32; oc += 8) {  // rare path: 8 columns at a time so the score row stays in registers
-              uint32_t o[8];
-              tmem_ld_32x32b_x8(o_addr + oc, o);
-              tmem_ld_wait();
-#pragma unroll
-              for (int e = 0; e < 8; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
-              tmem_st_32x32b_x8(o_addr + oc, o);
-            }
-            tmem_st_wait();
-            l_run *= alpha;
-            m_used = m_new;
-          }
-        }
-        if (pp) {
-          if (t == 0) {
-            if (j > 0) named_bar_sync(3, 512);
-          } else {
-            named_bar_sync(4, 512);
-          }
-        }
-        if (tr) trace_pt<POLY>(p, t, j, 2);
-        // P = exp2(S*c - m_used) -> fp16 -> swizzled shared memory (K-major A operand of the PV product)
-        float l0 = 0.f, l1 = 0.f;
-        auto emit = [&](const uint32_t (&sv)[32], int half32) {
-          uint32_t packed[16];
-#pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            const float a0 = fmaf(__uint_as_float(sv[e]), c, -m_used);
-            const float a1 = fmaf(__uint_as_float(sv[e + 1]), c, -m_used);
-            const float p0 = ((POLY >> (e & 7)) & 1) ? ex2_poly(a0) : ex2(a0);
-            const float p1 = ((POLY >> ((e + 1) & 7)) & 1) ? ex2_poly(a1) : ex2(a1);
-            l0 += p0;
-            l1 += p1;
-            __half2 hh = __floats2half2_rn(p0, p1);
-            packed[e >> 1] = *reinterpret_cast<uint32_t*>(&hh);
-          }
-          if constexpr (PT) {
-            tmem_st_32x32b_x16(p_tm + half32 * 16, packed);  // keys 2c, 2c+1 of the block in column c of the row's lane
-          } else {
-            // 32 keys = 4 chunks of 16 B inside this half's 64-key swizzle atom: chunks half32*4 .. +3
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int cc = half32 * 4 + q;
-              sts_v4(p_row_s + ((cc ^ (row & 7)) << 4), packed[q * 4], packed[q * 4 + 1], packed[q * 4 + 2], packed[q * 4 + 3]);
-            }
-          }
-        };
-        emit(s0, 0);
-        if (more) {  // S_t(j+1) has been complete for a long time (issued right after s_free(j)): no stall here
-          mbar_wait(&s_full[t], (j + 1) & 1);
-          tc_fence_after();
-          tmem_ld_32x32b_x32(s_addr, s0);
-        }
-        if (tr) trace_pt<POLY>(p, t, j, 3);
-        emit(s1, 1);
-        if (more) tmem_ld_32x32b_x32(s_addr + 32, s1);
-        if (pp) {
-          if (t == 0) {
-            named_bar_arrive(4, 512);
-          } else if (more) {
-            named_bar_arrive(3, 512);
-          }
-        }
-        l_run += l0 + l1;
-        if (tr) trace_pt<POLY>(p, t, j, 4);
-        // P_t(j) complete (tensor memory) / visible to the async proxy (shared memory), O_t accesses retired -> let the
-        // MMA warp go
-        if constexpr (PT) {
-          tmem_st_wait();
-        } else {
-          fence_proxy_async_smem();
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[t]);
-        if (more) {
-          tmem_ld_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&s_free[t]);
-        }
-        if (tr) trace_pt<POLY>(p, t, j, 5);
-      }
-      // epilogue: O / l, each half writes 32 of the 64 channels
-      float* lx = reinterpret_cast<float*>(smem + SMEM_XCH) + 1024 + t * 256;
-      lx[h * 128 + row] = l_run;
-      mbar_wait(&pv_done[t], (nblk - 1) & 1);
-      tc_fence_after();
-      uint32_t o0[32];
-      tmem_ld_32x32b_x32(o_addr, o0);
-      tmem_ld_wait();
-      named_bar_sync(1 + t, 256);
-      const float l_tot = lx[row] + lx[128 + row];
-      const int q = q0 + t * BQ + row;
-      if (q < p.T) {
-        const float inv = 1.f / l_tot;
-        __half* orow = p.out + (static_cast<long long>(b) * p.T + q) * p.ldo + head * HD + h * 32;
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          uint4 ov;
-          __half2* oh = reinterpret_cast<__half2*>(&ov);
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            oh[e] = __floats2half2_rn(__uint_as_float(o0[v * 8 + 2 * e]) * inv, __uint_as_float(o0[v * 8 + 2 * e + 1]) * inv);
-          *reinterpret_cast<uint4*>(orow + v * 8) = ov;
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp_idx == 2) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
-  }
-}
-
-}  // namespace
-
-
-// ------------------------------------------------------------------------------------------------------------------
-// Row-per-thread kernel (the product path).  Same tiling and barriers as above, but
-//   * one softmax THREAD owns a whole 128-key score row (8 softmax warps, 384 threads, up to 168 registers): the row
-//     maximum is thread-local (no shared-memory exchange, no named barrier per block) and the exponentials of a 32-key
-//     chunk are independent instruction streams deep enough to keep MUFU results in flight (the 16-warp kernel ran at
-//     one ex2 per ~30 cycles per warp: every result was consumed a few instructions after its issue because 96
-//     registers left no room for more);
-//   * P goes to TENSOR memory (tcgen05.st, fp16 pairs, 64 columns per tile) and the PV product takes its A operand
-//     from there (tcgen05.mma [d], [a_tmem], b_desc): no P tile in shared memory (64 KB of stores + 64 KB of operand
-//     reads per key block gone -- the shared-memory pipe was as busy as the MUFU pipe), no fence.proxy.async;
-//   * MMA order per key block and tile: P_t(j) V(j) when p_full_t(j) arrives, then S_t(j+2) (its buffer has been free since
-//     the warps pulled S_t(j+1) into registers during block j's exponentials);
-//   * issue_mode 2: the two query tiles take turns on the MUFU pipe (named barriers 3 / 4).
-// TMEM: S_t at t*128 (fp32, 128 columns), O_t at 256 + t*64, P_t at 384 + t*64 -> all 512 columns.
-constexpr int R_KV_STAGES = 4;
-constexpr int R_SMEM_BAR = QT * TILE_BYTES;
-constexpr int R_SMEM_KV = R_SMEM_BAR + 1024;
-constexpr int R_SMEM_TOTAL = R_SMEM_KV + R_KV_STAGES * 2 * TILE_BYTES + 1024;
-constexpr int R_NTHREADS = 128 + 256;  // 4 control warps + 8 softmax warps (tile = (w-4)/4, TMEM lane quarter = w%4)
-
-template <int POLY>
-__global__ void __launch_bounds__(R_NTHREADS, 1) attention_d64_row_kernel(const __grid_constant__ AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + R_SMEM_BAR);
-  uint64_t* q_full = bars;                     // 1
-  uint64_t* kv_full = bars + 1;                // R_KV_STAGES
-  uint64_t* kv_empty = kv_full + R_KV_STAGES;  // R_KV_STAGES
-  uint64_t* s_full = kv_empty + R_KV_STAGES;   // QT
-  uint64_t* p_full = s_full + QT;              // QT
-  uint64_t* pv_done = p_full + QT;             // QT: P_t(j) V(j) retired -> O_t current, P_t columns reusable
-  uint64_t* s_free = pv_done + QT;             // QT: S_t(j) is in the warpgroup's registers -> S_t(j+1) may be issued
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(s_free + QT);
-
-  const int warp_idx = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * (QT * BQ);
-  const int head = blockIdx.y;
-  const int b = blockIdx.z;
-  const int nctx = (p.Tc + BKV - 1) / BKV;
-  const int nsp = (p.T + BKV - 1) / BKV;
-  const int nblk = nctx + nsp;
-  const int ntile = (q0 + BQ < p.T) ? 2 : 1;  // the second query tile may not exist
-
-  if (warp_idx == 0 && lane == 0) {
-    tma_prefetch_desc(&p.tmQKV);
-    if (p.Tc > 0) tma_prefetch_desc(&p.tmEnc);
-  }
-  if (warp_idx == 1 && lane == 0) {
-    mbar_init(q_full, 1);
-    for (int i = 0; i < R_KV_STAGES; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
-    }
-    for (int i = 0; i < QT; ++i) {
-      mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 4);  // one arrival per softmax warp of the tile
-      mbar_init(&pv_done[i], 1);
-      mbar_init(&s_free[i], 4);
-    }
-    fence_barrier_init();
-  }
-  if (warp_idx == 2) {
-    tmem_alloc(tmem_ptr, TMEM_COLS);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-  pdl_wait();
-  pdl_launch();
-  // register re-partition (per warpgroup): the control warps hand most of theirs to the softmax warps, whose 128-score row,
-  // 16 packed P words and the exponentials in flight need ~200
-  if (warp_idx < 4) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-  if (warp_idx == 0) {
-    // ===================================== TMA producer =====================================
-    if (elect_one()) {
-      mbar_arrive_expect_tx(q_full, ntile * TILE_BYTES);
-      for (int t = 0; t < ntile; ++t)
-        tma_load_3d(smem + SMEM_Q + t * TILE_BYTES, &p.tmQKV, q_full, head * p.hs + p.q_off, q0 + t * BQ, b);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int j = 0; j < nblk; ++j) {
-        mbar_wait(&kv_empty[stage], phase ^ 1);
-        uint8_t* sK = smem + R_SMEM_KV + stage * 2 * TILE_BYTES;
-        uint8_t* sV = sK + TILE_BYTES;
-        mbar_arrive_expect_tx(&kv_full[stage], 2 * TILE_BYTES);
-        if (j < nctx) {
-          tma_load_3d(sK, &p.tmEnc, &kv_full[stage], head * p.ehs + p.ek_off, j * BKV, b);
-          tma_load_3d(sV, &p.tmEnc, &kv_full[stage], head * p.ehs + p.ev_off, j * BKV, b);
-        } else {
-          const int kv0 = (j - nctx) * BKV;
-          tma_load_3d(sK, &p.tmQKV, &kv_full[stage], head * p.hs + p.k_off, kv0, b);
-          tma_load_3d(sV, &p.tmQKV, &kv_full[stage], head * p.hs + p.v_off, kv0, b);
-        }
-        if (++stage == R_KV_STAGES) {
-          stage = 0;
-          phase ^= 1;
-        }
-      }
-    }
-  } else if (warp_idx == 1) {
-    // ===================================== MMA issuer ========================================
     if (elect_one()) {
       constexpr uint32_t idesc_s = make_idesc_f16(BQ, BKV, 0, 0);  // Q (K-major) x K (K-major)
       constexpr uint32_t idesc_o = make_idesc_f16(BQ, HD, 0, 1);   // P (K-major, tensor memory) x V (MN-major)
       auto issue_pv = [&](int t, int jb, int stage_b) {
-        const uint32_t v_addr = smem_u32(smem + R_SMEM_KV + stage_b * 2 * TILE_BYTES + TILE_BYTES);
+        const uint32_t v_addr = smem_u32(smem + SMEM_KV + stage_b * 2 * TILE_BYTES + TILE_BYTES);
         const uint32_t d = tmem_base + TM_O + t * HD;
         const uint32_t a = tmem_base + TM_P + t * 64;
 #pragma unroll
@@ -653,7 +197,7 @@ __global__ void __launch_bounds__(R_NTHREADS, 1) attention_d64_row_kernel(const 
       };
       auto issue_s = [&](int t, int stage_b) {
         const uint64_t adesc = make_sw128_desc(smem_u32(smem + SMEM_Q + t * TILE_BYTES));
-        const uint64_t bdesc = make_sw128_desc(smem_u32(smem + R_SMEM_KV + stage_b * 2 * TILE_BYTES));
+        const uint64_t bdesc = make_sw128_desc(smem_u32(smem + SMEM_KV + stage_b * 2 * TILE_BYTES));
         const uint32_t d = tmem_base + TM_S + t * BKV;
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k)
@@ -682,7 +226,7 @@ __global__ void __launch_bounds__(R_NTHREADS, 1) attention_d64_row_kernel(const 
         }
       }
       for (int j = 0; j < nblk; ++j) {
-        const int stage = j % R_KV_STAGES;
+        const int stage = j % KV_STAGES;
         for (int t = 0; t < ntile; ++t) {
           mbar_wait(&p_full[t], j & 1);
           trace_pt<POLY>(p, 2, j, t * 4 + 0);
@@ -693,11 +237,11 @@ __global__ void __launch_bounds__(R_NTHREADS, 1) attention_d64_row_kernel(const 
           trace_pt<POLY>(p, 2, j, t * 4 + 1);
           if (j + 2 < nblk) {
             const int j2 = j + 2;
-            if (t == 0) mbar_wait(&kv_full[j2 % R_KV_STAGES], (j2 / R_KV_STAGES) & 1);
+            if (t == 0) mbar_wait(&kv_full[j2 % KV_STAGES], (j2 / KV_STAGES) & 1);
             mbar_wait(&s_free[t], (j + 1) & 1);
             trace_pt<POLY>(p, 2, j, t * 4 + 2);
             tc_fence_after();
-            issue_s(t, j2 % R_KV_STAGES);
+            issue_s(t, j2 % KV_STAGES);
             trace_pt<POLY>(p, 2, j, t * 4 + 3);
           }
         }
@@ -706,6 +250,181 @@ __global__ void __launch_bounds__(R_NTHREADS, 1) attention_d64_row_kernel(const 
   }
   } else {
     // ===================================== softmax warps + epilogue ===========================
+    if constexpr (HALF) {
+    // ------------- 16 softmax warps: thread (t, h, row) owns keys [64h, 64h + 64) of one score row -------------
+    // Four softmax warps per sub-partition instead of two: the exponentials saturate the MUFU pipe (9.0 cycles per
+    // warp-wide ex2 against 12 with two warps, profiles/README.md) at the price of one shared-memory exchange + named
+    // barrier per block for the two halves of a row to agree on the maximum.
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    const int sw = warp_idx - 4;
+    const int t = sw >> 3;                        // query tile
+    const int h = (sw >> 2) & 1;                  // key half of the 128-key block
+    const int ew = warp_idx & 3;                  // TMEM lane quarter
+    const int row = ew * 32 + lane;               // query row in the tile == TMEM lane
+    if (t < ntile) {
+      const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
+      const uint32_t s_addr = lane_addr + TM_S + t * BKV + h * 64;
+      const uint32_t o_addr = lane_addr + TM_O + t * HD + h * 32;
+      const uint32_t p_tm = lane_addr + TM_P + t * 64 + h * 32;
+      float* xch = reinterpret_cast<float*>(smem + SMEM_XCH) + t * 512;  // [parity][half][row] block maxima
+      float m_used = 0.f;   // the (possibly stale) maximum the exponentials are taken against, log2 domain
+      float l_run = 0.f;    // this half's share of the row sum
+      const float c = p.scale_log2e;
+      const bool tr = (ew == 0 && lane == 0 && h == 0);
+      auto block_valid = [&](int j) {
+        return ((j < nctx) ? min(BKV, p.Tc - j * BKV) : min(BKV, p.T - (j - nctx) * BKV)) - h * 64;
+      };
+      float mxa = -INFINITY, mxb = -INFINITY;
+      auto land = [&](uint32_t (&sv)[32], int chunk, int valid) {
+        if (valid < 64) {  // ragged tail / short encoder block (block-uniform branch): masked scores -> -inf
+          asm volatile("" ::: "memory");
+          const uint32_t ninf = __float_as_uint(-INFINITY);
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (chunk * 32 + e >= valid) sv[e] = ninf;
+        }
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) {
+          mxa = fmax3(mxa, __uint_as_float(sv[e]), __uint_as_float(sv[e + 1]));
+          mxb = fmax3(mxb, __uint_as_float(sv[e + 2]), __uint_as_float(sv[e + 3]));
+        }
+      };
+      // the two halves of a row agree on the block maximum: shared memory, double-buffered by block parity, one
+      // 256-thread named barrier per block
+      auto exchange = [&](int jb) {
+        float* slot = xch + (jb & 1) * 256;
+        const float m_half = fmaxf(mxa, mxb) * c;
+        slot[h * 128 + row] = m_half;
+        named_bar_sync(1 + t, 256);
+        mxa = -INFINITY;
+        mxb = -INFINITY;
+        return fmaxf(m_half, slot[(h ^ 1) * 128 + row]);
+      };
+
+      uint32_t s0[32], s1[32];
+      mbar_wait_lean(&s_full[t], 0);
+      tc_fence_after();
+      tmem_ld_32x32b_x32(s_addr, s0);
+      tmem_ld_32x32b_x32(s_addr + 32, s1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[t]);
+      {
+        const int v0 = block_valid(0);
+        land(s0, 0, v0);
+        land(s1, 1, v0);
+      }
+      float m_blk = exchange(0);
+
+      for (int j = 0; j < nblk; ++j) {
+        const bool more = j + 1 < nblk;
+        const int vnext = more ? block_valid(j + 1) : 64;
+        if (tr) trace_pt<POLY>(p, t, j, 0);
+        float alpha = 1.f;
+        bool any_grow = false;
+        if (j == 0) {
+          m_used = m_blk;
+        } else {
+          // both halves of a row see the same m_blk and m_used, so they take the same decision
+          const bool grow = m_blk > m_used + RESCALE_GAP;
+          any_grow = __any_sync(0xffffffffu, grow);
+          if (grow) {
+            alpha = ex2(m_used - m_blk);
+            m_used = m_blk;
+          }
+        }
+        if (tr) trace_pt<POLY>(p, t, j, 1);
+        float l0 = 0.f, l1 = 0.f;
+        uint32_t pk[16];
+        auto emit = [&](const uint32_t (&sv)[32]) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const float a0 = fmaf(__uint_as_float(sv[e]), c, -m_used);
+            const float a1 = fmaf(__uint_as_float(sv[e + 1]), c, -m_used);
+            const float p0 = ((POLY >> (e & 7)) & 1) ? ex2_poly(a0) : ex2(a0);
+            const float p1 = ((POLY >> ((e + 1) & 7)) & 1) ? ex2_poly(a1) : ex2(a1);
+            l0 += p0;
+            l1 += p1;
+            __half2 hh = __floats2half2_rn(p0, p1);
+            pk[e >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+          }
+        };
+        emit(s0);
+        if (more) {  // S_t(j+1) has been complete for a long time (issued right after s_free(j)): no stall here
+          mbar_wait_lean(&s_full[t], (j + 1) & 1);
+          tc_fence_after();
+          tmem_ld_32x32b_x32(s_addr, s0);
+        }
+        if (tr) trace_pt<POLY>(p, t, j, 2);
+        // P_t's columns and O_t are needed only now: PV(j-1) had 32 exponentials of four warps (~1000 cycles) to retire
+        if (j > 0) {
+          mbar_wait_lean(&pv_done[t], (j - 1) & 1);
+          tc_fence_after();
+          if (any_grow) {
+#pragma unroll 1
+            for (int oc = 0; oc < 32; oc += 8) {  // rare path: this half rescales 32 of the row's 64 O columns
+              uint32_t o[8];
+              tmem_ld_32x32b_x8(o_addr + oc, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+              tmem_st_32x32b_x8(o_addr + oc, o);
+            }
+            l_run *= alpha;
+          }
+        }
+        if (tr) trace_pt<POLY>(p, t, j, 3);
+        tmem_st_32x32b_x16(p_tm, pk);  // keys 2c, 2c+1 of this half in column c of the row's lane
+        emit(s1);
+        tmem_st_32x32b_x16(p_tm + 16, pk);
+        if (more) {
+          tmem_ld_wait();
+          land(s0, 0, vnext);
+          tmem_ld_32x32b_x32(s_addr + 32, s1);
+        }
+        l_run += l0 + l1;
+        if (tr) trace_pt<POLY>(p, t, j, 4);
+        // P_t(j) complete in tensor memory, O_t accesses retired -> let the MMA warp go
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[t]);
+        if (more) {
+          tmem_ld_wait();
+          land(s1, 1, vnext);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_free[t]);
+          m_blk = exchange(j + 1);
+        }
+        if (tr) trace_pt<POLY>(p, t, j, 5);
+      }
+      // epilogue: O / l, each half writes 32 of the 64 channels
+      float* lx = reinterpret_cast<float*>(smem + SMEM_XCH) + 1024 + t * 256;
+      lx[h * 128 + row] = l_run;
+      mbar_wait_lean(&pv_done[t], (nblk - 1) & 1);
+      tc_fence_after();
+      tmem_ld_32x32b_x32(o_addr, s0);
+      tmem_ld_wait();
+      named_bar_sync(1 + t, 256);
+      const float l_tot = lx[row] + lx[128 + row];
+      const int q = q0 + t * BQ + row;
+      if (q < p.T) {
+        const float inv = 1.f / l_tot;
+        __half* orow = p.out + (static_cast<long long>(b) * p.T + q) * p.ldo + head * HD + h * 32;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          uint4 ov;
+          __half2* oh = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            oh[e] = __floats2half2_rn(__uint_as_float(s0[v * 8 + 2 * e]) * inv, __uint_as_float(s0[v * 8 + 2 * e + 1]) * inv);
+          *reinterpret_cast<uint4*>(orow + v * 8) = ov;
+        }
+      }
+    }
+    } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
     const int t = (warp_idx - 4) >> 2;            // query tile
     const int ew = warp_idx & 3;                  // TMEM lane quarter
@@ -745,7 +464,7 @@ __global__ void __launch_bounds__(R_NTHREADS, 1) attention_d64_row_kernel(const 
       // has landed), so when block j ends the next maximum is one FMNMX away: the MUFU pipe never waits for a
       // load -> maximum -> compare chain (the first row-per-thread version idled ~1400 of every ~3500 cycles there).
       uint32_t s0[32], s1[32], s2[32], s3[32];
-      mbar_wait(&s_full[t], 0);
+      mbar_wait_lean(&s_full[t], 0);
       tc_fence_after();
       tmem_ld_32x32b_x32(s_addr, s0);
       tmem_ld_32x32b_x32(s_addr + 32, s1);
@@ -804,7 +523,7 @@ __global__ void __launch_bounds__(R_NTHREADS, 1) attention_d64_row_kernel(const 
         uint32_t pk0[16], pk1[16], pk2[16], pk3[16];
         emit(s0, pk0);
         if (more) {  // S_t(j+1) has been complete for a long time (issued right after s_free(j)): no stall here
-          mbar_wait(&s_full[t], (j + 1) & 1);
+          mbar_wait_lean(&s_full[t], (j + 1) & 1);
           tc_fence_after();
           tmem_ld_32x32b_x32(s_addr, s0);
         }
@@ -823,7 +542,7 @@ __global__ void __launch_bounds__(R_NTHREADS, 1) attention_d64_row_kernel(const 
         }
         // P_t's columns and O_t are needed only now: PV(j-1) had three chunks of exponentials to retire
         if (j > 0) {
-          mbar_wait(&pv_done[t], (j - 1) & 1);
+          mbar_wait_lean(&pv_done[t], (j - 1) & 1);
           tc_fence_after();
           if (any_grow) {
 #pragma unroll 1
@@ -866,7 +585,7 @@ __global__ void __launch_bounds__(R_NTHREADS, 1) attention_d64_row_kernel(const 
         if (tr) trace_pt<POLY>(p, t, j, 5);
       }
       // epilogue: O / l, one 128-byte output row per thread
-      mbar_wait(&pv_done[t], (nblk - 1) & 1);
+      mbar_wait_lean(&pv_done[t], (nblk - 1) & 1);
       tc_fence_after();
       tmem_ld_32x32b_x32(o_addr, s0);
       tmem_ld_32x32b_x32(o_addr + 32, s1);
@@ -895,6 +614,7 @@ __global__ void __launch_bounds__(R_NTHREADS, 1) attention_d64_row_kernel(const 
         }
       }
     }
+    }  // HALF
   }
 
   tc_fence_before();
@@ -905,49 +625,33 @@ __global__ void __launch_bounds__(R_NTHREADS, 1) attention_d64_row_kernel(const 
   }
 }
 
+template <int POLY, bool HALF>
+static int launch_variant2(const AttnParams& p, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    K2_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<POLY, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       SMEM_TOTAL));
+    attr_set = true;
+  }
+  dim3 grid((p.T + QT * BQ - 1) / (QT * BQ), p.heads, p.B);
+  K2_CHECK_CUDA(launch_k(attention_d64_kernel<POLY, HALF>, grid, dim3(nthreads(HALF)), SMEM_TOTAL, stream, p));
+  return 0;
+}
 template <int POLY>
-static int launch_row_variant(const AttnParams& p, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    K2_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_row_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       R_SMEM_TOTAL));
-    attr_set = true;
-  }
-  dim3 grid((p.T + QT * BQ - 1) / (QT * BQ), p.heads, p.B);
-  K2_CHECK_CUDA(launch_k(attention_d64_row_kernel<POLY>, grid, dim3(R_NTHREADS), R_SMEM_TOTAL, stream, p));
-  return 0;
-}
-
-template <int POLY, bool PT>
 static int launch_variant(const AttnParams& p, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    K2_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<POLY, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Cfg<PT>::SMEM_TOTAL));
-    attr_set = true;
-  }
-  dim3 grid((p.T + QT * BQ - 1) / (QT * BQ), p.heads, p.B);
-  K2_CHECK_CUDA(launch_k(attention_d64_kernel<POLY, PT>, grid, dim3(NTHREADS), Cfg<PT>::SMEM_TOTAL, stream, p));
-  return 0;
+  return attention_half_rows() ? launch_variant2<POLY, true>(p, stream) : launch_variant2<POLY, false>(p, stream);
 }
 
-// pt: P in tensor memory (the product path) or in shared memory (round-1 kernel, kept for the A/B probe)
-int launch_attention_d64(const AttnParams& p, bool pt, cudaStream_t stream) {
-  const int poly = attention_poly_mode();  // share of the exponentials taken off the MUFU pipe: 0, 2/8, 3/8, 4/8
-  if (pt) {
-    switch (poly) {
-      case 0: return launch_row_variant<0x00>(p, stream);
-      case 1: return launch_row_variant<0x10>(p, stream);
-      case 2: return launch_row_variant<0x24>(p, stream);
-      case 4: return launch_row_variant<0x55>(p, stream);
-      case 200: return launch_row_variant<0x8000>(p, stream);  // traced
-      default: return launch_row_variant<0x52>(p, stream);
-    }
-  }
-  switch (poly) {
-    case 0: return launch_variant<0x00, false>(p, stream);
-    case 200: return launch_variant<0x8000, false>(p, stream);
-    default: return launch_variant<0x52, false>(p, stream);
+}  // namespace
+
+int launch_attention_d64(const AttnParams& p, cudaStream_t stream) {
+  switch (attention_poly_mode()) {  // tuning key 6: eighths of the exponentials evaluated without MUFU (default 0)
+    case 0: return launch_variant<0x00>(p, stream);
+    case 1: return launch_variant<0x10>(p, stream);
+    case 2: return launch_variant<0x24>(p, stream);
+    case 4: return launch_variant<0x55>(p, stream);
+    case 200: return launch_variant<0x8000>(p, stream);  // traced (clock64 stamps of CTA (0,0,0), profiles/attn_probe.py)
+    default: return launch_variant<0x52>(p, stream);
   }
 }
 
@@ -993,12 +697,7 @@ extern "C" int k2_attention_d64(const void* qkv, int ldq, int hs, int q_off, int
   p.scale_log2e = scale * 1.4426950408889634f;
   p.stagger_cycles = attention_stagger();
   p.trace = attention_trace_buffer();
-  // tuning key 9: 0 / 1 = shared-memory P with the fixed / event-driven issue order (round 1); 2 = P in tensor memory with
-  // the two query tiles' exponentials alternating (default); 3 / 4 = P in tensor memory, fixed / event-driven order
-  const int mode = attention_issue_mode();
-  const bool pt = mode >= 2;
-  p.issue_mode = (mode == 2) ? 2 : (mode == 3 ? 0 : (mode == 4 ? 1 : mode));
-  int rc = launch_attention_d64(p, pt, static_cast<cudaStream_t>(stream));
+  int rc = launch_attention_d64(p, static_cast<cudaStream_t>(stream));
   if (rc == 0) count_launch();
   return rc;
 }

@@ -10,10 +10,18 @@
 //   per CTA: Q[128, 512] resident in shared memory (8 K-major swizzle atoms of 16 KB)
 //   per 128-key block j:   S(j)   = Q K(j)^T      8 d-chunks x (M128 N128 K64)   -> TMEM S[j & 1]
 //                          P(j)   = exp2(S*c - m) one softmax thread per query row (128 scores), two passes over TMEM:
-//                                   row maximum first, then the exponentials -> fp16 -> swizzled shared memory
-//                          O     += P(j) V(j)     4 d-chunks (of this CTA's half) x (M128 N64 K128), V used MN-major as
-//                                                 TMA lands it, O rescaled lazily (only when a row maximum grows by 2^8)
-//   K / V chunks (128 keys x 64 channels = 16 KB) stream through ONE 4-stage ring in the order the MMA warp consumes them:
+//                                   row maximum first, then the exponentials -> fp16 pairs -> TENSOR memory, written over
+//                                   the first 64 columns of the very S buffer they came from (chunk c of P lands on
+//                                   columns the thread has already consumed)
+//                          O     += P(j) V(j)     4 d-chunks (of this CTA's half) x (M128 N64 K128), A operand = P from
+//                                                 tensor memory (tcgen05.mma [d], [a], b-desc), V used MN-major as TMA
+//                                                 lands it, O rescaled lazily (only when a row maximum grows by 2^8)
+//   Shared-memory operand reads per key block: S 256 KB + V 64 KB.  With P in shared memory (round-2 first version) the PV
+//   product re-read the 32 KB P tile for each of the four V chunks: 448 KB per block at 128 B/clk = 3500 cycles, exactly the
+//   measured 3584 -- the kernel was shared-memory-bandwidth bound, not tensor bound (3072 cycles of MMA per block).
+//   S(j+2) reuses the buffer of S(j) / P(j): it is issued after PV(j), and the tensor pipe executes in issue order, so no
+//   barrier is needed for that hand-back.
+//   K / V chunks (128 keys x 64 channels = 16 KB) stream through ONE 6-stage ring in the order the MMA warp consumes them:
 //   K(0); then K(j+1), V(j) per block, so S(j+1) is being produced while the softmax of block j runs.
 // Warp roles (256 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 softmax + epilogue.
 #include <string.h>
@@ -35,13 +43,12 @@ constexpr int NQC = CH / DC;             // 8 chunks of Q / K along the channels
 constexpr int OH = 256;                  // output channels per CTA
 constexpr int NVC = OH / DC;             // 4 V chunks per block
 constexpr int TILE_BYTES = 128 * DC * 2; // 16 KB
-constexpr int STAGES = 4;
+constexpr int STAGES = 6;
 constexpr int SMEM_Q = 0;
 constexpr int SMEM_RING = SMEM_Q + NQC * TILE_BYTES;        // 128 KB
-constexpr int SMEM_P = SMEM_RING + STAGES * TILE_BYTES;     // + 64 KB
-constexpr int SMEM_BAR = SMEM_P + 2 * TILE_BYTES;           // + 32 KB (P: two 64-key atoms)
+constexpr int SMEM_BAR = SMEM_RING + STAGES * TILE_BYTES;   // + 96 KB
 constexpr int SMEM_TOTAL = SMEM_BAR + 256 + 1024;           // barriers + alignment slack = 230,656 B <= 232,448
-constexpr int TM_S = 0;                  // S buffer b at columns b * 128
+constexpr int TM_S = 0;                  // S buffer b at columns b * 128; P(j) over columns [0, 64) of S[j & 1]
 constexpr int TM_O = 256;                // O: 256 columns
 constexpr float RESCALE_GAP = 8.f;
 
@@ -68,8 +75,7 @@ __global__ void __launch_bounds__(256, 1) attention_d512_kernel(const __grid_con
   uint64_t* ring_full = bars + 1;          // STAGES
   uint64_t* ring_empty = ring_full + STAGES;
   uint64_t* s_full = ring_empty + STAGES;  // 2
-  uint64_t* s_free = s_full + 2;           // 2: the softmax warps are done reading S[b]
-  uint64_t* p_full = s_free + 2;           // 1
+  uint64_t* p_full = s_full + 2;           // 1
   uint64_t* pv_done = p_full + 1;          // 1
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pv_done + 1);
 
@@ -89,7 +95,6 @@ __global__ void __launch_bounds__(256, 1) attention_d512_kernel(const __grid_con
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_free[i], 4);  // one arrival per softmax warp
     }
     mbar_init(p_full, 4);
     mbar_init(pv_done, 1);
@@ -133,7 +138,7 @@ __global__ void __launch_bounds__(256, 1) attention_d512_kernel(const __grid_con
     // ===================================== MMA issuer ========================================
     if (elect_one()) {
       constexpr uint32_t idesc_s = make_idesc_f16(BQ, BKV, 0, 0);  // Q (K-major) x K (K-major)
-      constexpr uint32_t idesc_o = make_idesc_f16(BQ, DC, 0, 1);   // P (K-major) x V (MN-major), N = 64
+      constexpr uint32_t idesc_o = make_idesc_f16(BQ, DC, 0, 1);   // P (K-major, tensor memory) x V (MN-major), N = 64
       int stage = 0;
       uint32_t phase = 0;
       auto next_stage = [&]() {
@@ -161,17 +166,12 @@ __global__ void __launch_bounds__(256, 1) attention_d512_kernel(const __grid_con
       tc_fence_after();
       issue_s(0);
       for (int j = 0; j < nblk; ++j) {
-        if (j + 1 < nblk) {
-          // S[(j+1) & 1] last held block j-1: the softmax warps must have finished reading it
-          if (j >= 1) {
-            mbar_wait(&s_free[(j + 1) & 1], ((j - 1) >> 1) & 1);
-            tc_fence_after();
-          }
-          issue_s(j + 1);
-        }
+        // S[(j+1) & 1] last held S(j-1) / P(j-1): the softmax warps finished with it before p_full(j-1), and PV(j-1) was
+        // issued in the previous iteration -- the tensor pipe retires it before this product starts
+        if (j + 1 < nblk) issue_s(j + 1);
         mbar_wait(p_full, j & 1);
         tc_fence_after();
-        const uint32_t p_addr = smem_u32(smem + SMEM_P);
+        const uint32_t p_tm = tmem_base + TM_S + (j & 1) * BKV;
         for (int c = 0; c < NVC; ++c) {
           mbar_wait(&ring_full[stage], phase);
           tc_fence_after();
@@ -179,11 +179,10 @@ __global__ void __launch_bounds__(256, 1) attention_d512_kernel(const __grid_con
           const uint32_t d = tmem_base + TM_O + c * DC;
 #pragma unroll
           for (int k = 0; k < BKV / 16; ++k) {
-            // A: P [128 q][128 keys] as two 64-key swizzle atoms of 16 KB, 32 B per 16-key step
-            const uint64_t adesc = make_sw128_desc(p_addr + (k >> 2) * TILE_BYTES) + static_cast<uint64_t>((k & 3) * 2);
+            // A: P from tensor memory, 16 keys = 8 columns of fp16 pairs per step
             // B: V chunk [128 keys][64 channels] (MN-major): 16 keys = 16 rows of 128 B = 2048 B per step
             const uint64_t bdesc = make_sw128_desc(v_addr + k * 2048);
-            umma_f16(d, adesc, bdesc, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
+            umma_f16_ts(d, p_tm + k * 8, bdesc, idesc_o, (j > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&ring_empty[stage]);
           next_stage();
@@ -197,7 +196,6 @@ __global__ void __launch_bounds__(256, 1) attention_d512_kernel(const __grid_con
     const int row = ew * 32 + lane;               // query row == TMEM lane
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
     const uint32_t o_addr = lane_addr + TM_O;
-    const uint32_t p_row = smem_u32(smem + SMEM_P + row * 128);
     const float c = p.scale_log2e;
     float m_used = 0.f, l_run = 0.f;
     for (int j = 0; j < nblk; ++j) {
@@ -223,10 +221,12 @@ __global__ void __launch_bounds__(256, 1) attention_d512_kernel(const __grid_con
       if (j == 0) {
         m_used = m_blk;
       } else {
-        mbar_wait(pv_done, (j - 1) & 1);  // O holds blocks < j and the P buffer is free again
-        tc_fence_after();
         const bool grow = m_blk > m_used + RESCALE_GAP;
         if (__any_sync(0xffffffffu, grow)) {
+          // rare path: O must hold every block < j before it is rescaled.  (The common path needs no wait at all: P(j)
+          // goes into S(j)'s own buffer, and S(j) was produced after PV(j-2) released it.)
+          mbar_wait(pv_done, (j - 1) & 1);
+          tc_fence_after();
           const float m_new = grow ? m_blk : m_used;
           const float alpha = ex2f(m_used - m_new);
 #pragma unroll 1
@@ -262,23 +262,16 @@ __global__ void __launch_bounds__(256, 1) attention_d512_kernel(const __grid_con
           __half2 hh = __floats2half2_rn(p0, p1);
           packed[e >> 1] = *reinterpret_cast<uint32_t*>(&hh);
         }
-        // 32 keys = 4 chunks of 16 B of the row: atom part / 2, chunks (part % 2) * 4 .. + 3
-        const uint32_t base = p_row + (part >> 1) * TILE_BYTES;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int cc = (part & 1) * 4 + q;
-          sts_v4(base + ((cc ^ (row & 7)) << 4), packed[q * 4], packed[q * 4 + 1], packed[q * 4 + 2], packed[q * 4 + 3]);
-        }
+        // keys 2c, 2c+1 of the block -> column c of S[j & 1]: chunk `part` covers columns [16 part, 16 part + 16), all of
+        // them inside score columns this thread has already pulled into registers
+        tmem_st_32x32b_x16(s_addr + part * 16, packed);
       }
       l_run += l0 + l1;
-      // S[j & 1] may be overwritten (block j + 2), P(j) is visible to the async proxy -> let the MMA warp go
+      // P(j) complete in tensor memory -> let the MMA warp go
+      tmem_st_wait();
       tc_fence_before();
-      fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&s_free[j & 1]);
-        mbar_arrive(p_full);
-      }
+      if (lane == 0) mbar_arrive(p_full);
     }
     // epilogue: O / l -> fp16, each thread writes the 256 channels of its row (512 contiguous bytes)
     mbar_wait(pv_done, (nblk - 1) & 1);

@@ -72,6 +72,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// The same bounded wait without the printf: no call, so no caller-saved registers are spilled around it (matters where the
+// waiting thread holds a full register file, e.g. the attention softmax warps).
+__device__ __forceinline__ void mbar_wait_lean(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+
 // make generic-proxy smem writes visible to the async proxy (UMMA / TMA reads of smem)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -97,16 +97,14 @@ struct AttnParams {
   __half* out;         // [B, T, ldo], channel h*64+d
   int ldo;
   float scale_log2e;   // softmax scale * log2(e)
-  int stagger_cycles;  // initial delay of the second query tile's first score product (de-phases the warpgroups)
+  int stagger_cycles;  // tuning key 5 (default 0): delay of the second query tile's first score product; measured: no gain
   unsigned long long* trace;  // diagnostics: 3 x 16 x 8 clock64 stamps of CTA (0,0,0), or null
-  int issue_mode;      // MMA issuer: 0 = fixed program order per key block, 1 = event driven (polls both query tiles),
-                       // 2 = ping-pong (per tile PV(j) then S(j+2); the softmax warpgroups alternate on the MUFU pipe)
 };
 int gn_apply_blocks_per_sm();  // tuning key 11: blocks per SM the GroupNorm apply kernels are sized for (0 = their occupancy)
 int attention_stagger();
 unsigned long long* attention_trace_buffer();
-int attention_issue_mode();
+int attention_half_rows();   // tuning key 9: 1 = 16 softmax warps with half a score row per thread, 0 = 8 warps, one row each
 int attention_poly_mode();  // eighths of the softmax exponentials evaluated without MUFU: 0, 2, 3, 4
-int launch_attention_d64(const AttnParams& p, bool pt, cudaStream_t stream);
+int launch_attention_d64(const AttnParams& p, cudaStream_t stream);
 
 }  // namespace k2

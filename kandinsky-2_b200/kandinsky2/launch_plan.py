@@ -15,17 +15,24 @@ from . import ops
 FOLD_MAX_RG = int(os.environ.get("K2_GN_FOLD_MAX_RG", "18"))
 TUNE = os.environ.get("K2_AUTOTUNE", "1") != "0"
 FORK = os.environ.get("K2_FORK", "1") != "0"
+# Layers with at most this many output rows (UNet levels 2-3: 4608 / 1152 rows at cfg-2) also try the single-CTA kernel and
+# split-K factors 2..4: their tile counts leave a large part of the machine idle in the configuration the cycle model picks
+# (level 3: 60 work units on 74 CTA pairs; N tile 192 x 2-way split-K on single CTAs = 144 units on 148 SMs is 23-30 %
+# faster, profiles/conv_sustain.py).  A K split changes the fp32 summation order: deterministic per configuration, not
+# bit-identical across configurations (the choice is cached per process and shape).
+TUNE_SMALL_M = int(os.environ.get("K2_TUNE_SMALL_M", "8192"))
 _tune_cache = {}
 
 
-def tune(key, run):
+def tune(key, run, m_rows=0):
     """Launch configuration of one conv / GEMM layer shape: (N tile, pair mode, splits, epilogue warp sets) for
-    k2_conv_gemm_cfg, picked by timing the bit-identical candidates (N tile x epilogue sets; the split-K factor stays the
-    cycle model's, it would change the summation order) with CUDA events on the current stream.  Cached per shape and
-    device; None = the library's own choice.  key = (kind, Cout, ...); run(cfg, info) must enqueue the launch."""
+    k2_conv_gemm_cfg, picked by timing candidates with CUDA events on the current stream: N tile x epilogue sets (bit-identical
+    results) everywhere, plus single-CTA / split-K variants for layers of at most TUNE_SMALL_M output rows (m_rows; see above).
+    Cached per shape and device; None = the library's own choice.  key = (kind, Cout, ...); run(cfg, info) must enqueue the
+    launch and report the configuration the library actually used in info."""
     if not TUNE:
         return None
-    key = (torch.cuda.current_device(),) + key
+    key = (torch.cuda.current_device(), TUNE_SMALL_M) + key
     if key in _tune_cache:
         return _tune_cache[key]
     info = [0] * 7
@@ -33,9 +40,22 @@ def tune(key, run):
     bn0, pair, splits = info[0], info[1], info[2]
     best = None
     if pair:
-        cout = key[2]
+        cout = key[3]
         bns = [bn0] if splits > 1 else [bn for bn in (128, 192, 256) if bn - 64 < cout or bn == bn0]
         cands = [(bn0, 0, splits, 1)] + [(bn, 0, splits, es) for bn in bns for es in (1, 2) if (bn, es) != (bn0, 1)]
+        if 0 < m_rows <= TUNE_SMALL_M and splits == 1:
+            for pm in (2, 1):        # CTA pairs / single CTAs
+                for bn in (128, 192, 256):
+                    if bn - 64 >= cout:
+                        continue
+                    for sp in ((2, 3, 4) if pm == 2 else (1, 2, 3, 4)):
+                        probe = [0] * 7
+                        try:
+                            run((bn, pm, sp, 1), probe)
+                        except Exception:
+                            continue
+                        if probe[0] == bn and probe[2] == sp and bool(probe[1]) == (pm == 2):  # else: the library refused
+                            cands.append((bn, pm, sp, 1))
 
         def timed(cfg, reps=6):
             run(cfg)
@@ -140,7 +160,7 @@ class LaunchPlan:
                                                    w_batch_stride=w_batch_stride)
         key = ("conv", cout, tuple(out.shape), geom, tuple((t.shape[-1], taps) for t, taps in srcs), residual is not None,
                part is not None, out_mode, w_batch_stride > 0)
-        cfg = tune(key, run)
+        cfg = tune(key, run, m_rows=out.shape[0] * out.shape[1] * out.shape[2] if out_mode == 0 and geom is None else 0)
         self._add(lambda: run(cfg, info), kind, flops)
         if part is not None and info[5]:
             self._parts[out.data_ptr()] = (part, info[6] // (geom[0] if geom is not None else out.shape[0]))
@@ -150,7 +170,7 @@ class LaunchPlan:
     def _gemm(self, x, w, cout, out, flops, bias=None, residual=None):
         """Flat-row GEMM step (no per-image structure, no statistics), tuned like _conv."""
         run = lambda cfg, info=None: ops.gemm_rows(x, w, cout, bias=bias, residual=residual, out=out, cfg=cfg, info=info)
-        cfg = tune(("gemm", cout, tuple(x.shape), residual is not None), run)
+        cfg = tune(("gemm", cout, tuple(x.shape), residual is not None), run, m_rows=x.shape[0] * x.shape[1])
         self._add(lambda: run(cfg), "conv_gemm", flops)
         self._parts.pop(out.data_ptr(), None)
 

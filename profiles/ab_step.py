@@ -3,7 +3,8 @@ round-robin so that clock / thermal drift hits all of them alike -- separate ben
 
     python profiles/ab_step.py "fold=0,tune=0" "fold=18,tune=0" "fold=18,tune=1" [--rounds 5 --steps 20 --hw 96x96 --batch 4]
 
-Variant keys: fold = launch_plan.FOLD_MAX_RG, tune = launch_plan.TUNE, fork = launch_plan.FORK, up2 = unet._UP2 (0/1), any k2_set_tuning key as
+Variant keys: fold = launch_plan.FOLD_MAX_RG, tune = launch_plan.TUNE, fork = launch_plan.FORK, smallm = launch_plan.TUNE_SMALL_M,
+up2 = unet._UP2 (0/1), any k2_set_tuning key as
 t<key>=<value>."""
 import argparse
 import os
@@ -46,6 +47,7 @@ def main():
         launch_plan.FOLD_MAX_RG = int(kv.get("fold", launch_plan.FOLD_MAX_RG))
         launch_plan.TUNE = kv.get("tune", "1") != "0"
         launch_plan.FORK = kv.get("fork", "1") != "0"
+        launch_plan.TUNE_SMALL_M = int(kv.get("smallm", "8192"))
         if hasattr(unet_mod, "_UP2"):
             unet_mod._UP2 = kv.get("up2", "1") != "0"
         tkeys = {int(k[1:]): int(v) for k, v in kv.items() if k[0] == "t" and k[1:].isdigit()}

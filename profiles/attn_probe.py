@@ -1,9 +1,10 @@
-"""Attention kernel A/B at the three UNet geometries: round-1 kernel (P through shared memory, key 9 = 0) against the
-tensor-memory-P kernel in its three issue orders (key 9 = 2 ping-pong, 3 fixed, 4 event driven), with the MUFU-free
-share of the exponentials (key 6) swept on the ping-pong variant.  Every variant is first checked against a torch fp32
-softmax(QK^T)V on a small slice, then timed with CUDA events; the last part prints the clock64 hand-over trace of
-CTA (0,0,0) in ping-pong mode (softmax points: 0 block start, 1 maximum exchanged, 2 turn taken, 3 / 4 first / second
-32 exponentials done, 5 P handed over; MMA points per tile: P arrived, PV issued, S buffer free, S(j+2) issued)."""
+"""Attention kernel (k2_attention_d64) at the three UNet geometries: checked against a torch fp32 softmax(QK^T)V on a
+slice, then timed with CUDA events for each MUFU-free share of the exponentials (tuning key 6) and two de-phasing delays
+(key 5); the last part prints the clock64 hand-over trace of CTA (0,0,0) (softmax points per key block: 0 block start,
+1 rescale decision taken, 2 first 64 exponentials done, 3 96 done + PV(j-1) barrier passed, 4 all 128 done, 5 P handed
+over / next maximum known; MMA points per tile: P arrived, PV issued, S buffer free, S(j+2) issued).
+History of this probe's output: attn_probe_r2*.txt (a: first P-in-TMEM variants of the 16-warp kernel, b: row-per-thread
+kernel, c: forced 8-deep MUFU bursts (slower), d: next-block maximum folded in + deferred PV wait, e: de-phasing sweep)."""
 import os
 import sys
 
@@ -37,8 +38,8 @@ for (B, heads, T, Tc) in geoms:
     flops = 4 * B * heads * T * (T + Tc) * 64
     nq = min(T, 384)
     ref = reference(qkv, enc, heads, b=B - 1, nq=nq)
-    for mode, poly, stag in ((0, 0, 300), (2, 0, 0), (2, 0, 600), (2, 0, 1200), (2, 0, 1800), (2, 0, 2400), (2, 1, 1200), (2, 1, 1800)):
-        ops.set_tuning(9, mode)
+    for half, poly, stag in ((0, 0, 0), (1, 0, 0), (1, 1, 0), (1, 2, 0), (1, 3, 0), (0, 1, 0)):
+        ops.set_tuning(9, half)
         ops.set_tuning(6, poly)
         ops.set_tuning(5, stag)
         out.zero_()
@@ -53,7 +54,7 @@ for (B, heads, T, Tc) in geoms:
         e.record()
         torch.cuda.synchronize()
         us = s.elapsed_time(e) / 20 * 1e3
-        print(f"T={T} heads={heads} mode={mode} poly={poly}/8 stagger={stag}: {us:.1f} us {flops / us / 1e6:.0f} TF/s "
+        print(f"T={T} heads={heads} {'half rows (16 warps)' if half else 'full rows (8 warps) '} poly={poly}/8: {us:.1f} us {flops / us / 1e6:.0f} TF/s "
               f"max|err| vs fp32 {err:.2e}", flush=True)
 
 # hand-over trace, ping-pong mode
@@ -72,17 +73,17 @@ def s32(v):
 
 ops.set_tuning(7, s32(addr))
 ops.set_tuning(8, s32(addr >> 32))
-for mode in (2,):
-    ops.set_tuning(9, mode)
+for half in (1, 0):
+    ops.set_tuning(9, half)
     ops.set_tuning(6, 200)
-    ops.set_tuning(5, 1500)
+    ops.set_tuning(5, 0)
     trace.zero_()
     for _ in range(3):
         ops.attention_d64(qkv, heads, enc, out=out)
     torch.cuda.synchronize()
     t = trace.cpu().view(3, 16, 8).tolist()
     base = min(v for r in t for b in r for v in b if v > 0)
-    print(f"== trace, key 9 = {mode}")
+    print(f"== trace, key 9 = {half}")
     names = ["WG0", "WG1", "MMA"]
     for r in range(3):
         for j in range(16):
@@ -90,5 +91,5 @@ for mode in (2,):
 ops.set_tuning(6, 0)
 ops.set_tuning(7, 0)
 ops.set_tuning(8, 0)
-ops.set_tuning(9, 2)
-ops.set_tuning(5, 300)
+ops.set_tuning(5, 0)
+ops.set_tuning(9, 0)

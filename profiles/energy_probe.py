@@ -103,10 +103,7 @@ def main():
         qkv = torch.randn(B, T, heads * 192, device="cuda", generator=g).half()
         enc = torch.randn(B, Tc, heads * 128, device="cuda", generator=g).half()
         out = torch.empty(B, T, heads * 64, device="cuda", dtype=torch.float16)
-        for mode in (0, 2):
-            ops.set_tuning(9, mode)
-            measure(f"attention T={T} heads={heads} (key 9 = {mode})", lambda: ops.attention_d64(qkv, heads, enc, out=out), cnt)
-    ops.set_tuning(9, 2)
+        measure(f"attention T={T} heads={heads}", lambda: ops.attention_d64(qkv, heads, enc, out=out), cnt)
     for (NB, Hh, W, C, cnt) in [(8, 96, 96, 384, 12), (8, 48, 48, 768, 26), (8, 24, 24, 1152, 27), (8, 12, 12, 1536, 30)]:
         x = torch.randn(NB, Hh, W, C, device="cuda", generator=g).half()
         gamma = torch.randn(C, device="cuda", generator=g)

@@ -23,6 +23,9 @@ def _ref_attention(qkv, enc, heads):
     return torch.einsum("bhts,bshd->bthd", w, v).reshape(B, T, heads * 64)
 
 
+ATTN_DEFAULT_LAYOUT = 1  # k2_api.cu g_attn_half
+
+
 @pytest.mark.parametrize("B,heads,T,Tc", [
     (2, 2, 64, 17),      # golden tiny config: one partial block each
     (1, 3, 144, 32),     # level-3 geometry: 2 query tiles, ragged key tail
@@ -31,13 +34,22 @@ def _ref_attention(qkv, enc, heads):
     (1, 1, 256, 0),      # no encoder tokens
     (1, 1, 130, 200),    # encoder longer than one block
 ])
-def test_attention_d64(B, heads, T, Tc):
+@pytest.mark.parametrize("half_rows", [0, 1])
+def test_attention_d64(B, heads, T, Tc, half_rows):
+    """both softmax layouts of k2_attention_d64 (tuning key 9: one thread per score row / half a row per thread) and, for the
+    level-1 geometry, the MUFU-free exp2 on 2/8 of the scores (key 6)"""
     from kandinsky2 import ops
     g = torch.Generator(device="cuda").manual_seed(0)
     qkv = torch.randn(B, T, heads * 192, device="cuda", generator=g).half()
     enc = torch.randn(B, Tc, heads * 128, device="cuda", generator=g).half() if Tc else None
-    out = ops.attention_d64(qkv, heads, enc)
-    torch.cuda.synchronize()
+    ops.set_tuning(9, half_rows)
+    ops.set_tuning(6, 2 if T == 2304 else 0)
+    try:
+        out = ops.attention_d64(qkv, heads, enc)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_tuning(9, ATTN_DEFAULT_LAYOUT)
+        ops.set_tuning(6, 0)
     ref = _ref_attention(qkv, enc, heads)
     err = (out.float() - ref).abs().max().item()
     # P is rounded to fp16 before PV (as in the reference's fp16 mode, unet.py:338): abs tol 4e-3 on O(1) values
@@ -46,13 +58,18 @@ def test_attention_d64(B, heads, T, Tc):
     assert rel < 2e-3, rel
 
 
-def test_attention_large_logits():
+@pytest.mark.parametrize("half_rows", [0, 1])
+def test_attention_large_logits(half_rows):
     """online-softmax rescaling: strongly peaked rows whose maximum moves between key blocks."""
     from kandinsky2 import ops
     g = torch.Generator(device="cuda").manual_seed(1)
     B, heads, T = 1, 2, 512
     qkv = (torch.randn(B, T, heads * 192, device="cuda", generator=g) * 3).half()
-    out = ops.attention_d64(qkv, heads, None)
+    ops.set_tuning(9, half_rows)
+    try:
+        out = ops.attention_d64(qkv, heads, None)
+    finally:
+        ops.set_tuning(9, ATTN_DEFAULT_LAYOUT)
     ref = _ref_attention(qkv, None, heads)
     assert torch.isfinite(out).all()
     assert (out.float() - ref).abs().max().item() < 3e-2
