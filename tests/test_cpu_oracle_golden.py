@@ -30,11 +30,16 @@ def test_unet_oracle_matches_reference_golden(name):
 
 @pytest.mark.parametrize("name", ["unet_tiny", "unet_tiny_inpaint"])
 def test_unet_oracle_fp16_mode_matches_reference_fp16_mode(name):
-    """The oracle's fp16 mode (to_reference_fp16 + fp16=True) against the output of the reference's own fp16 mode
-    (Text2ImUNet.convert_to_fp16(), run by oracle/make_golden.py).  It is the comparator of the GPU calibration test
-    (tests/test_gpu_unet.py::test_unet_full_size_fp16_calibration).  Bit-equal where the fixture was written; a tolerance of
-    one fp16 ulp of the O(1) activations absorbs CPU-dependent fp16 conv kernels."""
-    from oracle import synth, unet_oracle as uo
+    """The oracle's fp16 mode (to_reference_fp16 + fp16=True) against the reference's own fp16 mode
+    (Text2ImUNet.convert_to_fp16()).  It is the comparator of the GPU calibration test
+    (tests/test_gpu_unet.py::test_unet_full_size_fp16_calibration).
+
+    fp16 convolutions on a CPU depend on the CPU (AVX512-FP16 / F16C / scalar paths accumulate differently: the same fixture
+    re-run on another host moves by ~4e-3), so the pin has two parts: (1) where the reference tree is present (the build
+    container) the reference's fp16 mode is EXECUTED on this host and the oracle must reproduce it to 1e-5 -- same code
+    path, same kernels; (2) everywhere, the oracle stays within 3x the reference's own fp16-vs-fp32 gap of the committed
+    fixture (oracle/make_golden.py, bit-equal on the host that wrote it)."""
+    from oracle import ref_shim, synth, unet_oracle as uo
     fx = _load(name)
     sd = synth.synth_state_dict(uo.unet_param_spec(fx["cfg"]), seed=fx["weight_seed"])
     inp = fx["inputs"]
@@ -42,10 +47,21 @@ def test_unet_oracle_fp16_mode_matches_reference_fp16_mode(name):
     with torch.no_grad():
         y = uo.unet_forward(uo.to_reference_fp16(sd), fx["cfg"], inp["x"], inp["t"], fp16=True, **kw)
     assert y.dtype == torch.float32
-    assert (y - fx["out_ref_fp16"]).abs().max().item() <= 1e-3
+    gap = (fx["out_ref_fp16"] - fx["out"]).abs().max().item()
     # the reference's fp16 mode itself is ~5e-3 away from its fp32 mode at this size: the north_star's 1e-3 is not a property
     # of the reference
-    assert (fx["out_ref_fp16"] - fx["out"]).abs().max().item() > 1e-3
+    assert gap > 1e-3
+    assert (y - fx["out_ref_fp16"]).abs().max().item() <= 3 * gap
+    assert (y - fx["out"]).abs().max().item() <= 3 * gap
+    if ref_shim.available():
+        from oracle import make_golden as mg
+        model = mg.build_ref_unet(fx["cfg"])
+        model.load_state_dict(sd, strict=True)
+        model.dtype = torch.float16
+        model.convert_to_fp16()
+        with torch.no_grad():
+            y_ref16 = model(inp["x"], inp["t"], **{k: (v.half() if k.endswith("_emb") else v) for k, v in kw.items()})
+        assert (y - y_ref16).abs().max().item() <= 1e-5
 
 
 def test_movq_oracle_matches_reference_golden():
