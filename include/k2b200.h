@@ -35,11 +35,13 @@ long long k2_launch_count(void);
 void k2_reset_launch_count(void);
 /* Tuning knobs: key 0 = force conv/GEMM N tile (0 = auto); key 1 = split-K (0 auto, 1 off, n>1 forced);
  * key 2 = CTA-pair kernel (0 auto, 1 off, 2 on); key 3 = halo 3x3 kernel (0 off, 1-4 layout variants);
- * key 4 = programmatic dependent launch (0/1); key 5 = attention warpgroup de-phasing delay in cycles;
- * key 6 = eighths (0, 2, 3, 4) of the softmax exponentials evaluated on the FMA pipe instead of MUFU (1xx = ablations,
- * 2xx = traced variants); keys 7 / 8 = low / high 32 bits of a device buffer (384 x u64) that the traced attention
- * variants fill with clock64 stamps of CTA (0,0,0) -- diagnostics only, see profiles/attn_trace.py; key 9 = order of the
- * attention MMA issuer (0 fixed per key block, 1 event driven; default from the environment variable K2_ATTN_ISSUE, else 0);
+ * key 4 = programmatic dependent launch (0/1); key 5 = cycles by which the attention kernel's second query tile starts late
+ * (default 1200; each query tile has its own MMA-issuing thread, so the two tiles' softmax phases stay apart);
+ * key 6 = attention softmax arithmetic: n = eighths (0..3) of the exponentials evaluated on the FMA pipe instead of MUFU,
+ * + 10 = scale-and-subtract as packed FFMA2, + 30 = FFMA2 and packed FADD2 row sums (bit-identical to the same n), 200 = traced
+ * (default 0); keys 7 / 8 = low / high 32 bits of a device buffer (384 x u64) that the traced attention variant fills with
+ * clock64 stamps of CTA (0,0,0) -- diagnostics only, see profiles/attn_probe.py; key 9 = attention softmax layout (1 = 16 warps,
+ * half a score row per thread, default; 0 = 8 warps, one row per thread);
  * key 10 = default number of epilogue warp sets of the CTA-pair conv kernel (1; 2 = 384-thread variant whose second set drains
  * the other half of the 64-column pairs: bit-identical results, faster where the K loop is short).  Keys 0, 1, 2 and 10 are
  * process-wide defaults; k2_conv_gemm_cfg overrides them per call.  key 11 = blocks per SM the GroupNorm apply grids are sized

@@ -18,7 +18,7 @@ static std::atomic<long long> g_launches{0};
 static int g_force_bn = 0;
 static int g_force_split = 0;  // 0 auto, 1 off, n>1 forced
 static int g_force_2cta = 0;   // 0 auto, 1 off, 2 on
-static int g_attn_stagger = 0;
+static int g_attn_stagger = 1200;  // cycles query tile 1 starts late (independent MMA issuers keep the offset): 218 -> 200 us at level 1, profiles/attn_probe_r2.txt
 static int g_attn_poly = 0;  // measured: the softmax is not MUFU-bound (profiles/README.md), offloading only adds instructions
 static int g_pdl = 0;          // programmatic dependent launch of the step's kernels
 static int g_halo_mode = 0;    // 0 off; 1/2: dense halo rows (pitch 10) without/with base offset; 3/4: pitch 16

@@ -51,11 +51,14 @@ constexpr int HD = 64;          // head dim
 constexpr int TILE_BYTES = 128 * HD * 2;  // 16 KB: one Q / K / V tile
 constexpr int SMEM_Q = 0;
 constexpr int KV_STAGES = 4;
-constexpr int SMEM_BAR = QT * TILE_BYTES;
-constexpr int SMEM_XCH = SMEM_BAR + 1024;  // HALF: fp32 [tile][parity][half][128] block maxima + [tile][half][128] row sums
-constexpr int SMEM_KV = SMEM_XCH + 6144;
-constexpr int SMEM_TOTAL = SMEM_KV + KV_STAGES * 2 * TILE_BYTES + 1024;
+constexpr int SMEM_KV = QT * TILE_BYTES;
+constexpr int SMEM_TOTAL = SMEM_KV + KV_STAGES * 2 * TILE_BYTES + 1024;  // dynamic: Q + the K/V ring (+ alignment slack)
 static_assert(SMEM_KV % 1024 == 0, "K/V tiles must sit on the 1024 B swizzle period");
+// The mbarriers and the HALF layout's exchange buffer are STATIC shared memory: their shared-window addresses are link-time
+// constants.  As offsets from the 1024 B-aligned dynamic base they cost the softmax warps ~10 uniform instructions per
+// barrier operation (the aligned base is re-derived from the generic pointer each time: the compiler rematerialises rather
+// than spend one of the warps' 96 registers), ~60 of the ~440 instructions a warp issued per key block.
+constexpr int XCH_FLOATS = 1536;  // fp32 [tile][parity][half][128] block maxima, then [tile][half][128] row sums
 // HALF = false: 4 control warps + 8 softmax warps, one thread per score row (tile = (w-4)/4, TMEM lane quarter = w%4)
 // HALF = true : 4 control warps + 16 softmax warps, half a row per thread (tile = (w-4)/8, key half = ((w-4)/4)%2)
 constexpr int nthreads(bool half) { return 128 + (half ? 512 : 256); }
@@ -92,12 +95,15 @@ __device__ __forceinline__ void trace_pt(const AttnParams& p, int role, int j, i
   }
 }
 
-template <int POLY, bool HALF>
+// PK: bit 0 -> scale-and-subtract as FFMA2 (two scores per instruction), bit 1 -> row sums as FADD2
+template <int POLY, bool HALF, int PK>
 __global__ void __launch_bounds__(nthreads(HALF), 1) attention_d64_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_BAR);
+  __shared__ __align__(8) uint64_t bars[24];
+  __shared__ __align__(1024) float xch_buf[XCH_FLOATS];
+  __shared__ uint32_t tmem_slot;
   uint64_t* q_full = bars;                     // 1
   uint64_t* kv_full = bars + 1;                // KV_STAGES
   uint64_t* kv_empty = kv_full + KV_STAGES;  // KV_STAGES
@@ -105,7 +111,7 @@ __global__ void __launch_bounds__(nthreads(HALF), 1) attention_d64_kernel(const 
   uint64_t* p_full = s_full + QT;              // QT
   uint64_t* pv_done = p_full + QT;             // QT: P_t(j) V(j) retired -> O_t current, P_t columns reusable
   uint64_t* s_free = pv_done + QT;             // QT: S_t(j) is in the warpgroup's registers -> S_t(j+1) may be issued
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(s_free + QT);
+  uint32_t* tmem_ptr = &tmem_slot;
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -125,7 +131,7 @@ __global__ void __launch_bounds__(nthreads(HALF), 1) attention_d64_kernel(const 
     mbar_init(q_full, 1);
     for (int i = 0; i < KV_STAGES; ++i) {
       mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+      mbar_init(&kv_empty[i], ntile);  // one tcgen05.commit arrival per query tile's issuer
     }
     for (int i = 0; i < QT; ++i) {
       mbar_init(&s_full[i], 1);
@@ -180,12 +186,20 @@ __global__ void __launch_bounds__(nthreads(HALF), 1) attention_d64_kernel(const 
         }
       }
     }
-  } else if (warp_idx == 1) {
-    // ===================================== MMA issuer ========================================
-    if (elect_one()) {
+  } else if (warp_idx == 1 || warp_idx == 3) {
+    // ===================================== MMA issuers =======================================
+    // One issuing thread PER QUERY TILE (warp 1: tile 0, warp 3: tile 1).  With a single issuer serving the tiles in turn
+    // (wait p_full[0], issue, wait p_full[1], issue, ...) each tile's next step waited for the other tile's softmax: the
+    // two tiles ran in lock-step, all sixteen softmax warps took their exponentials at the same time (MUFU saturated for
+    // ~2100 of every ~3600 cycles, idle for the rest: profiles/README.md) and a start-up offset was pulled back within one
+    // key block.  Independent issuers leave the tiles coupled only through the K/V ring (kv_empty counts one arrival per
+    // tile), so tile 1's deliberate start-up delay (stagger_cycles) persists and one tile's exponentials fall into the
+    // other's hand-over phase.
+    const int t = warp_idx >> 1;
+    if (t < ntile && elect_one()) {
       constexpr uint32_t idesc_s = make_idesc_f16(BQ, BKV, 0, 0);  // Q (K-major) x K (K-major)
       constexpr uint32_t idesc_o = make_idesc_f16(BQ, HD, 0, 1);   // P (K-major, tensor memory) x V (MN-major)
-      auto issue_pv = [&](int t, int jb, int stage_b) {
+      auto issue_pv = [&](int jb, int stage_b) {
         const uint32_t v_addr = smem_u32(smem + SMEM_KV + stage_b * 2 * TILE_BYTES + TILE_BYTES);
         const uint32_t d = tmem_base + TM_O + t * HD;
         const uint32_t a = tmem_base + TM_P + t * 64;
@@ -195,7 +209,7 @@ __global__ void __launch_bounds__(nthreads(HALF), 1) attention_d64_kernel(const 
           umma_f16_ts(d, a + k * 8, make_sw128_desc(v_addr + k * 2048), idesc_o, (jb > 0 || k > 0) ? 1u : 0u);
         }
       };
-      auto issue_s = [&](int t, int stage_b) {
+      auto issue_s = [&](int stage_b) {
         const uint64_t adesc = make_sw128_desc(smem_u32(smem + SMEM_Q + t * TILE_BYTES));
         const uint64_t bdesc = make_sw128_desc(smem_u32(smem + SMEM_KV + stage_b * 2 * TILE_BYTES));
         const uint32_t d = tmem_base + TM_S + t * BKV;
@@ -207,43 +221,36 @@ __global__ void __launch_bounds__(nthreads(HALF), 1) attention_d64_kernel(const 
       mbar_wait(q_full, 0);
       mbar_wait(&kv_full[0], 0);
       tc_fence_after();
-      for (int t = 0; t < ntile; ++t) {
-        issue_s(t, 0);
-        if (t == 0 && ntile == 2 && p.stagger_cycles > 0) {
-          // de-phase the two query tiles (tuning key 5): tile 1 starts this many cycles late, so that one tile's
-          // hand-over / decision phase falls into the other's exponentials; nothing below couples the tiles' phases
-          const long long t0 = clock64();
-          while (clock64() - t0 < p.stagger_cycles) {
-          }
+      if (t == 1 && p.stagger_cycles > 0) {
+        // de-phase the two query tiles (tuning key 5): tile 1 starts this many cycles late
+        const long long t0 = clock64();
+        while (clock64() - t0 < p.stagger_cycles) {
         }
       }
+      issue_s(0);
       if (nblk > 1) {
         mbar_wait(&kv_full[1], 0);
-        for (int t = 0; t < ntile; ++t) {
-          mbar_wait(&s_free[t], 0);
-          tc_fence_after();
-          issue_s(t, 1);
-        }
+        mbar_wait(&s_free[t], 0);
+        tc_fence_after();
+        issue_s(1);
       }
       for (int j = 0; j < nblk; ++j) {
         const int stage = j % KV_STAGES;
-        for (int t = 0; t < ntile; ++t) {
-          mbar_wait(&p_full[t], j & 1);
-          trace_pt<POLY>(p, 2, j, t * 4 + 0);
+        mbar_wait(&p_full[t], j & 1);
+        trace_pt<POLY>(p, 2, j, t * 4 + 0);
+        tc_fence_after();
+        issue_pv(j, stage);
+        umma_commit(&pv_done[t]);
+        umma_commit(&kv_empty[stage]);  // one arrival per tile: the stage is free when both tiles' PV(j) have retired
+        trace_pt<POLY>(p, 2, j, t * 4 + 1);
+        if (j + 2 < nblk) {
+          const int j2 = j + 2;
+          mbar_wait(&kv_full[j2 % KV_STAGES], (j2 / KV_STAGES) & 1);
+          mbar_wait(&s_free[t], (j + 1) & 1);
+          trace_pt<POLY>(p, 2, j, t * 4 + 2);
           tc_fence_after();
-          issue_pv(t, j, stage);
-          umma_commit(&pv_done[t]);
-          if (t == ntile - 1) umma_commit(&kv_empty[stage]);
-          trace_pt<POLY>(p, 2, j, t * 4 + 1);
-          if (j + 2 < nblk) {
-            const int j2 = j + 2;
-            if (t == 0) mbar_wait(&kv_full[j2 % KV_STAGES], (j2 / KV_STAGES) & 1);
-            mbar_wait(&s_free[t], (j + 1) & 1);
-            trace_pt<POLY>(p, 2, j, t * 4 + 2);
-            tc_fence_after();
-            issue_s(t, j2 % KV_STAGES);
-            trace_pt<POLY>(p, 2, j, t * 4 + 3);
-          }
+          issue_s(j2 % KV_STAGES);
+          trace_pt<POLY>(p, 2, j, t * 4 + 3);
         }
       }
     }
@@ -263,17 +270,22 @@ __global__ void __launch_bounds__(nthreads(HALF), 1) attention_d64_kernel(const 
     const int row = ew * 32 + lane;               // query row in the tile == TMEM lane
     if (t < ntile) {
       const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
+      // addresses pinned in one register each (pin_reg; the 104-register budget has room for two): the tile's four
+      // mbarriers (s_full, p_full, pv_done, s_free are consecutive pairs: +0, +16, +32, +48) and its exchange slot
       const uint32_t s_addr = lane_addr + TM_S + t * BKV + h * 64;
       const uint32_t o_addr = lane_addr + TM_O + t * HD + h * 32;
       const uint32_t p_tm = lane_addr + TM_P + t * 64 + h * 32;
-      float* xch = reinterpret_cast<float*>(smem + SMEM_XCH) + t * 512;  // [parity][half][row] block maxima
+      const uint32_t bar_t = pin_reg(smem_u32(&s_full[t]));
+      constexpr uint32_t B_SFULL = 0, B_PFULL = 16, B_PVDONE = 32, B_SFREE = 48;
+      // fp32 [tile][parity][half][row] block maxima; the buffer is 1024 B-aligned, so the partner half's slot is own ^ 512
+      const uint32_t xch_own = pin_reg(smem_u32(xch_buf) + t * 2048 + h * 512 + row * 4);
       float m_used = 0.f;   // the (possibly stale) maximum the exponentials are taken against, log2 domain
       float l_run = 0.f;    // this half's share of the row sum
       const float c = p.scale_log2e;
       const bool tr = (ew == 0 && lane == 0 && h == 0);
-      auto block_valid = [&](int j) {
-        return ((j < nctx) ? min(BKV, p.Tc - j * BKV) : min(BKV, p.T - (j - nctx) * BKV)) - h * 64;
-      };
+      // only the last encoder block and the last spatial block can be ragged: their key counts are fixed before the loop
+      const int v_ctx_tail = p.Tc - (nctx - 1) * BKV - h * 64, v_sp_tail = p.T - (nsp - 1) * BKV - h * 64;
+      auto block_valid = [&](int j) { return (j == nctx - 1) ? v_ctx_tail : (j == nblk - 1) ? v_sp_tail : BKV; };
       float mxa = -INFINITY, mxb = -INFINITY;
       auto land = [&](uint32_t (&sv)[32], int chunk, int valid) {
         if (valid < 64) {  // ragged tail / short encoder block (block-uniform branch): masked scores -> -inf
@@ -292,24 +304,24 @@ __global__ void __launch_bounds__(nthreads(HALF), 1) attention_d64_kernel(const 
       // the two halves of a row agree on the block maximum: shared memory, double-buffered by block parity, one
       // 256-thread named barrier per block
       auto exchange = [&](int jb) {
-        float* slot = xch + (jb & 1) * 256;
+        const uint32_t slot = xch_own + (jb & 1) * 1024;
         const float m_half = fmaxf(mxa, mxb) * c;
-        slot[h * 128 + row] = m_half;
+        sts_f32(slot, m_half);
         named_bar_sync(1 + t, 256);
         mxa = -INFINITY;
         mxb = -INFINITY;
-        return fmaxf(m_half, slot[(h ^ 1) * 128 + row]);
+        return fmaxf(m_half, lds_f32(slot ^ 512));
       };
 
       uint32_t s0[32], s1[32];
-      mbar_wait_lean(&s_full[t], 0);
+      mbar_wait_lean_s(bar_t + B_SFULL, 0);
       tc_fence_after();
       tmem_ld_32x32b_x32(s_addr, s0);
       tmem_ld_32x32b_x32(s_addr + 32, s1);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_free[t]);
+      if (lane == 0) mbar_arrive_s(bar_t + B_SFREE);
       {
         const int v0 = block_valid(0);
         land(s0, 0, v0);
@@ -337,29 +349,40 @@ __global__ void __launch_bounds__(nthreads(HALF), 1) attention_d64_kernel(const 
         if (tr) trace_pt<POLY>(p, t, j, 1);
         float l0 = 0.f, l1 = 0.f;
         uint32_t pk[16];
+        const uint64_t c2 = pack_f32x2(c, c), nm2 = pack_f32x2(-m_used, -m_used);
+        uint64_t l2 = pack_f32x2(0.f, 0.f);
         auto emit = [&](const uint32_t (&sv)[32]) {
 #pragma unroll
           for (int e = 0; e < 32; e += 2) {
-            const float a0 = fmaf(__uint_as_float(sv[e]), c, -m_used);
-            const float a1 = fmaf(__uint_as_float(sv[e + 1]), c, -m_used);
+            float a0, a1;
+            if constexpr ((PK & 1) != 0) {  // FFMA2: both scores of a pair in one instruction
+              unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), c2, nm2), a0, a1);
+            } else {
+              a0 = fmaf(__uint_as_float(sv[e]), c, -m_used);
+              a1 = fmaf(__uint_as_float(sv[e + 1]), c, -m_used);
+            }
             const float p0 = ((POLY >> (e & 7)) & 1) ? ex2_poly(a0) : ex2(a0);
             const float p1 = ((POLY >> ((e + 1) & 7)) & 1) ? ex2_poly(a1) : ex2(a1);
-            l0 += p0;
-            l1 += p1;
+            if constexpr ((PK & 2) != 0) {
+              l2 = add_f32x2(l2, pack_f32x2(p0, p1));  // FADD2
+            } else {
+              l0 += p0;
+              l1 += p1;
+            }
             __half2 hh = __floats2half2_rn(p0, p1);
             pk[e >> 1] = *reinterpret_cast<uint32_t*>(&hh);
           }
         };
         emit(s0);
         if (more) {  // S_t(j+1) has been complete for a long time (issued right after s_free(j)): no stall here
-          mbar_wait_lean(&s_full[t], (j + 1) & 1);
+          mbar_wait_lean_s(bar_t + B_SFULL, (j + 1) & 1);
           tc_fence_after();
           tmem_ld_32x32b_x32(s_addr, s0);
         }
         if (tr) trace_pt<POLY>(p, t, j, 2);
         // P_t's columns and O_t are needed only now: PV(j-1) had 32 exponentials of four warps (~1000 cycles) to retire
         if (j > 0) {
-          mbar_wait_lean(&pv_done[t], (j - 1) & 1);
+          mbar_wait_lean_s(bar_t + B_PVDONE, (j - 1) & 1);
           tc_fence_after();
           if (any_grow) {
 #pragma unroll 1
@@ -383,32 +406,33 @@ __global__ void __launch_bounds__(nthreads(HALF), 1) attention_d64_kernel(const 
           land(s0, 0, vnext);
           tmem_ld_32x32b_x32(s_addr + 32, s1);
         }
+        if constexpr ((PK & 2) != 0) unpack_f32x2(l2, l0, l1);
         l_run += l0 + l1;
         if (tr) trace_pt<POLY>(p, t, j, 4);
         // P_t(j) complete in tensor memory, O_t accesses retired -> let the MMA warp go
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[t]);
+        if (lane == 0) mbar_arrive_s(bar_t + B_PFULL);
         if (more) {
           tmem_ld_wait();
           land(s1, 1, vnext);
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&s_free[t]);
+          if (lane == 0) mbar_arrive_s(bar_t + B_SFREE);
           m_blk = exchange(j + 1);
         }
         if (tr) trace_pt<POLY>(p, t, j, 5);
       }
       // epilogue: O / l, each half writes 32 of the 64 channels
-      float* lx = reinterpret_cast<float*>(smem + SMEM_XCH) + 1024 + t * 256;
-      lx[h * 128 + row] = l_run;
-      mbar_wait_lean(&pv_done[t], (nblk - 1) & 1);
+      const uint32_t lx = smem_u32(xch_buf) + 4096 + t * 1024 + row * 4;
+      sts_f32(lx + h * 512, l_run);
+      mbar_wait_lean_s(bar_t + B_PVDONE, (nblk - 1) & 1);
       tc_fence_after();
       tmem_ld_32x32b_x32(o_addr, s0);
       tmem_ld_wait();
       named_bar_sync(1 + t, 256);
-      const float l_tot = lx[row] + lx[128 + row];
+      const float l_tot = lds_f32(lx) + lds_f32(lx + 512);
       const int q = q0 + t * BQ + row;
       if (q < p.T) {
         const float inv = 1.f / l_tot;
@@ -438,7 +462,9 @@ __global__ void __launch_bounds__(nthreads(HALF), 1) attention_d64_kernel(const 
       float l_run = 0.f;    // row sum
       const float c = p.scale_log2e;
       const bool tr = (ew == 0 && lane == 0);
-      auto block_valid = [&](int j) { return (j < nctx) ? min(BKV, p.Tc - j * BKV) : min(BKV, p.T - (j - nctx) * BKV); };
+      // only the last encoder block and the last spatial block can be ragged: their key counts are fixed before the loop
+      const int v_ctx_tail = p.Tc - (nctx - 1) * BKV, v_sp_tail = p.T - (nsp - 1) * BKV;
+      auto block_valid = [&](int j) { return (j == nctx - 1) ? v_ctx_tail : (j == nblk - 1) ? v_sp_tail : BKV; };
       // a 32-score chunk that has just landed in registers: mask the keys past the end of a ragged / short block
       // (block-uniform branch) and fold the chunk into the row maximum of ITS block (two FMNMX3 chains)
       float mxa = -INFINITY, mxb = -INFINITY;
@@ -507,15 +533,26 @@ __global__ void __launch_bounds__(nthreads(HALF), 1) attention_d64_kernel(const 
         if (tr) trace_pt<POLY>(p, t, j, 1);
         // P = exp2(S*c - m_used) -> fp16 pairs, 16 words per 32-key chunk
         float l0 = 0.f, l1 = 0.f;
+        const uint64_t c2 = pack_f32x2(c, c), nm2 = pack_f32x2(-m_used, -m_used);
+        uint64_t l2 = pack_f32x2(0.f, 0.f);
         auto emit = [&](const uint32_t (&sv)[32], uint32_t (&packed)[16]) {
 #pragma unroll
           for (int e = 0; e < 32; e += 2) {
-            const float a0 = fmaf(__uint_as_float(sv[e]), c, -m_used);
-            const float a1 = fmaf(__uint_as_float(sv[e + 1]), c, -m_used);
+            float a0, a1;
+            if constexpr ((PK & 1) != 0) {  // FFMA2: both scores of a pair in one instruction
+              unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(sv[e]), __uint_as_float(sv[e + 1])), c2, nm2), a0, a1);
+            } else {
+              a0 = fmaf(__uint_as_float(sv[e]), c, -m_used);
+              a1 = fmaf(__uint_as_float(sv[e + 1]), c, -m_used);
+            }
             const float p0 = ((POLY >> (e & 7)) & 1) ? ex2_poly(a0) : ex2(a0);
             const float p1 = ((POLY >> ((e + 1) & 7)) & 1) ? ex2_poly(a1) : ex2(a1);
-            l0 += p0;
-            l1 += p1;
+            if constexpr ((PK & 2) != 0) {
+              l2 = add_f32x2(l2, pack_f32x2(p0, p1));  // FADD2
+            } else {
+              l0 += p0;
+              l1 += p1;
+            }
             __half2 hh = __floats2half2_rn(p0, p1);
             packed[e >> 1] = *reinterpret_cast<uint32_t*>(&hh);
           }
@@ -568,6 +605,7 @@ __global__ void __launch_bounds__(nthreads(HALF), 1) attention_d64_kernel(const 
           land(s2, 2, vnext);
           tmem_ld_32x32b_x32(s_addr + 96, s3);
         }
+        if constexpr ((PK & 2) != 0) unpack_f32x2(l2, l0, l1);
         l_run += l0 + l1;
         if (tr) trace_pt<POLY>(p, t, j, 4);
         // P_t(j) complete in tensor memory, O_t accesses retired -> let the MMA warp go
@@ -625,33 +663,40 @@ __global__ void __launch_bounds__(nthreads(HALF), 1) attention_d64_kernel(const 
   }
 }
 
-template <int POLY, bool HALF>
+template <int POLY, bool HALF, int PK>
 static int launch_variant2(const AttnParams& p, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    K2_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<POLY, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    K2_CHECK_CUDA(cudaFuncSetAttribute(attention_d64_kernel<POLY, HALF, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        SMEM_TOTAL));
     attr_set = true;
   }
   dim3 grid((p.T + QT * BQ - 1) / (QT * BQ), p.heads, p.B);
-  K2_CHECK_CUDA(launch_k(attention_d64_kernel<POLY, HALF>, grid, dim3(nthreads(HALF)), SMEM_TOTAL, stream, p));
+  K2_CHECK_CUDA(launch_k(attention_d64_kernel<POLY, HALF, PK>, grid, dim3(nthreads(HALF)), SMEM_TOTAL, stream, p));
   return 0;
 }
-template <int POLY>
+template <int POLY, int PK = 0>
 static int launch_variant(const AttnParams& p, cudaStream_t stream) {
-  return attention_half_rows() ? launch_variant2<POLY, true>(p, stream) : launch_variant2<POLY, false>(p, stream);
+  return attention_half_rows() ? launch_variant2<POLY, true, PK>(p, stream) : launch_variant2<POLY, false, PK>(p, stream);
 }
 
 }  // namespace
 
 int launch_attention_d64(const AttnParams& p, cudaStream_t stream) {
-  switch (attention_poly_mode()) {  // tuning key 6: eighths of the exponentials evaluated without MUFU (default 0)
+  // tuning key 6: n = eighths of the exponentials evaluated without MUFU (ex2_poly), + 10 x (1: FFMA2, 3: FFMA2 + FADD2)
+  switch (attention_poly_mode()) {
     case 0: return launch_variant<0x00>(p, stream);
     case 1: return launch_variant<0x10>(p, stream);
     case 2: return launch_variant<0x24>(p, stream);
-    case 4: return launch_variant<0x55>(p, stream);
+    case 3: return launch_variant<0x52>(p, stream);
+    case 10: return launch_variant<0x00, 1>(p, stream);
+    case 11: return launch_variant<0x10, 1>(p, stream);
+    case 12: return launch_variant<0x24, 1>(p, stream);
+    case 30: return launch_variant<0x00, 3>(p, stream);
+    case 31: return launch_variant<0x10, 3>(p, stream);
+    case 32: return launch_variant<0x24, 3>(p, stream);
     case 200: return launch_variant<0x8000>(p, stream);  // traced (clock64 stamps of CTA (0,0,0), profiles/attn_probe.py)
-    default: return launch_variant<0x52>(p, stream);
+    default: return launch_variant<0x00>(p, stream);
   }
 }
 

@@ -418,4 +418,68 @@ __device__ __forceinline__ float ex2_poly(float x) {
   return __int_as_float(__float_as_int(p) + ((__float_as_int(t) - 0x4B400000) << 23));
 }
 
+// Packed fp32 pairs (sm_100 FFMA2 / FADD2): one issue slot for two lanes' worth of arithmetic.  The attention softmax is
+// issue-limited next to its MUFU work (profiles/README.md: 7.8 instructions per exponential before, IPC 0.6 per sub-partition
+// with the MUFU pipe 61 % busy), so the scale-and-subtract and the row sum go two elements per instruction.
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// explicit shared-window accesses: pointers derived from the aligned dynamic-shared base lose their address space and
+// become generic LD / ST otherwise
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+
+// Same mbarrier operations on a 32-bit shared-window address (kept in one register by the caller, see pin_reg).
+__device__ __forceinline__ bool mbar_try_wait_s(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.b32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_lean_s(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait_s(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait_s(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void mbar_arrive_s(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Makes a value opaque to the optimiser: it stays in ONE register instead of being re-derived (rematerialised) from
+// %tid / kernel parameters at every use -- what ptxas otherwise does for the softmax warps' tensor-memory, barrier and
+// exchange addresses (~8 instructions per use, ~60 per key block).
+__device__ __forceinline__ uint32_t pin_reg(uint32_t v) {
+  asm volatile("mov.b32 %0, %0;" : "+r"(v));
+  return v;
+}
+
 }  // namespace k2

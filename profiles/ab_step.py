@@ -5,7 +5,8 @@ round-robin so that clock / thermal drift hits all of them alike -- separate ben
 
 Variant keys: fold = launch_plan.FOLD_MAX_RG, tune = launch_plan.TUNE, fork = launch_plan.FORK, smallm = launch_plan.TUNE_SMALL_M,
 up2 = unet._UP2 (0/1), any k2_set_tuning key as
-t<key>=<value>."""
+t<key>=<value>; drop=<kind>+<kind> removes every launch of those kinds from the captured graph (results are then WRONG: it measures
+what a kernel family costs INSIDE the power-capped graph replay, which the eager per-kernel event sums cannot)."""
 import argparse
 import os
 import statistics
@@ -20,6 +21,9 @@ import bench  # noqa: E402
 from kandinsky2 import launch_plan, ops  # noqa: E402
 from kandinsky2.model import unet as unet_mod  # noqa: E402
 from kandinsky2.model.gaussian_diffusion import FusedStep, create_ddpm_v22  # noqa: E402
+
+
+TUNING_DEFAULTS = {4: 1, 5: 1200, 9: 1}  # k2_api.cu defaults that are not 0 (key 4 is switched on by this script)
 
 
 def main():
@@ -59,11 +63,15 @@ def main():
         st = FusedStep(model, B, H, W, dict(image_emb=emb), guidance_scale=4.0, cond_first=False, clip_range=2.0,
                        threshold_mode=0)
         x = torch.randn(B, 4, H, W, device=dev)
+        if kv.get("drop"):
+            dropped = set(kv["drop"].split("+"))
+            st.plan.steps = [s for s in st.plan.steps if s[1] not in dropped]
+            st.plan.graph = None
         for n in range(3):  # builds + captures the graph with this variant's settings
             st.noise.normal_()
             st.run(x, ts[40], coef[40])
         for k in tkeys:
-            ops.set_tuning(k, 0)
+            ops.set_tuning(k, TUNING_DEFAULTS.get(k, 0))
         steps.append((spec, st, x))
     torch.cuda.synchronize()
     times = {spec: [] for spec, _, _ in steps}

@@ -27,6 +27,11 @@ def reference(qkv, enc, heads, b=0, nq=256):
     return torch.einsum("hqk,khd->qhd", w, v).reshape(nq, heads * 64)
 
 
+# tuning key 6: eighths of the exponentials on the FMA pipe, + 10 = FFMA2 scale-and-subtract, + 30 = FFMA2 and FADD2 row sums
+MODES = [int(v) for v in os.environ.get("K2_ATTN_MODES", "0,1,2,10,11,12,30,31").split(",")]
+# tuning key 5: cycles the second query tile's MMA issuer starts late (the tiles have independent issuers and stay apart)
+STAGGER = [int(v) for v in os.environ.get("K2_ATTN_STAGGER", "0").split(",")]
+TRACE_STAGGER = int(os.environ.get("K2_ATTN_TRACE_STAGGER", "0"))
 g = torch.Generator(device="cuda").manual_seed(0)
 geoms = [(8, 12, 2304, 32), (8, 18, 576, 32), (8, 24, 144, 32)]
 if len(sys.argv) > 1 and sys.argv[1] == "cfg3":
@@ -38,7 +43,7 @@ for (B, heads, T, Tc) in geoms:
     flops = 4 * B * heads * T * (T + Tc) * 64
     nq = min(T, 384)
     ref = reference(qkv, enc, heads, b=B - 1, nq=nq)
-    for half, poly, stag in ((0, 0, 0), (1, 0, 0), (1, 1, 0), (1, 2, 0), (1, 3, 0), (0, 1, 0)):
+    for half, poly, stag in [(h, m, st) for h in (1, 0) for m in MODES for st in STAGGER]:
         ops.set_tuning(9, half)
         ops.set_tuning(6, poly)
         ops.set_tuning(5, stag)
@@ -54,7 +59,7 @@ for (B, heads, T, Tc) in geoms:
         e.record()
         torch.cuda.synchronize()
         us = s.elapsed_time(e) / 20 * 1e3
-        print(f"T={T} heads={heads} {'half rows (16 warps)' if half else 'full rows (8 warps) '} poly={poly}/8: {us:.1f} us {flops / us / 1e6:.0f} TF/s "
+        print(f"T={T} heads={heads} {'half rows (16 warps)' if half else 'full rows (8 warps) '} mode={poly:2d} stagger={stag:4d}: {us:.1f} us {flops / us / 1e6:.0f} TF/s "
               f"max|err| vs fp32 {err:.2e}", flush=True)
 
 # hand-over trace, ping-pong mode
@@ -76,14 +81,14 @@ ops.set_tuning(8, s32(addr >> 32))
 for half in (1, 0):
     ops.set_tuning(9, half)
     ops.set_tuning(6, 200)
-    ops.set_tuning(5, 0)
+    ops.set_tuning(5, TRACE_STAGGER)
     trace.zero_()
     for _ in range(3):
         ops.attention_d64(qkv, heads, enc, out=out)
     torch.cuda.synchronize()
     t = trace.cpu().view(3, 16, 8).tolist()
     base = min(v for r in t for b in r for v in b if v > 0)
-    print(f"== trace, key 9 = {half}")
+    print(f"== trace, key 9 = {half}, stagger {TRACE_STAGGER}")
     names = ["WG0", "WG1", "MMA"]
     for r in range(3):
         for j in range(16):
@@ -91,5 +96,5 @@ for half in (1, 0):
 ops.set_tuning(6, 0)
 ops.set_tuning(7, 0)
 ops.set_tuning(8, 0)
-ops.set_tuning(5, 0)
-ops.set_tuning(9, 0)
+ops.set_tuning(5, 1200)
+ops.set_tuning(9, 1)

@@ -34,13 +34,19 @@ __global__ void mufu_chain(float* out, long long* cyc, int iters) {
   if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
-// the softmax inner pattern on 32 values per iteration: fma -> ex2 -> two running sums -> fp16 pack
+// the softmax inner pattern on 32 values per iteration: fma -> ex2 -> two running sums -> fp16 pack.
+// PACKED: the scale-and-subtract and the sums as fma.rn.f32x2 / add.f32x2 (FFMA2 / FADD2: two elements per issue slot)
+template <bool PACKED>
 __global__ void softmax_like(const float* in, uint32_t* out, long long* cyc, int iters, float c, float m) {
   float s[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) s[i] = in[(threadIdx.x * 32 + i) & 1023];
   float l0 = 0.f, l1 = 0.f;
   uint32_t acc = 0;
+  uint64_t c2, nm2, l2;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(c2) : "f"(c));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(nm2) : "f"(-m));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(l2) : "f"(0.f));
   __syncthreads();
   const long long t0 = clock64();
   for (int it = 0; it < iters; ++it) {
@@ -48,10 +54,22 @@ __global__ void softmax_like(const float* in, uint32_t* out, long long* cyc, int
 #pragma unroll
     for (int e = 0; e < 32; e += 2) {
       float p0, p1;
-      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(s[e], c, -m)));
-      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(s[e + 1], c, -m)));
-      l0 += p0;
-      l1 += p1;
+      if constexpr (PACKED) {
+        uint64_t a, d, pp;
+        float a0, a1;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(s[e]), "f"(s[e + 1]));
+        asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(c2), "l"(nm2));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(d));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(a0));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(a1));
+        asm("mov.b64 %0, {%1, %2};" : "=l"(pp) : "f"(p0), "f"(p1));
+        asm("add.f32x2 %0, %1, %2;" : "=l"(l2) : "l"(l2), "l"(pp));
+      } else {
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(fmaf(s[e], c, -m)));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(fmaf(s[e + 1], c, -m)));
+        l0 += p0;
+        l1 += p1;
+      }
       __half2 hh = __floats2half2_rn(p0, p1);
       packed[e >> 1] = *reinterpret_cast<uint32_t*>(&hh);
     }
@@ -61,6 +79,7 @@ __global__ void softmax_like(const float* in, uint32_t* out, long long* cyc, int
     for (int i = 0; i < 32; ++i) s[i] += 0.25f;  // new "scores" for the next round (one FADD per element)
   }
   const long long t1 = clock64();
+  if constexpr (PACKED) asm("mov.b64 {%0, %1}, %2;" : "=f"(l0), "=f"(l1) : "l"(l2));
   out[blockIdx.x * blockDim.x + threadIdx.x] = acc + __float_as_uint(l0 + l1);
   if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
@@ -147,16 +166,18 @@ int main() {
     run_chain<8>(out, cyc, threads);
     run_chain<16>(out, cyc, threads);
   }
-  for (int threads : {128, 256, 512}) {
-    const int iters = 500;
-    softmax_like<<<148, threads>>>(in, reinterpret_cast<uint32_t*>(out), cyc, iters, 0.18f, 3.f);
-    cudaDeviceSynchronize();
-    long long h;
-    cudaMemcpy(&h, cyc, sizeof h, cudaMemcpyDeviceToHost);
-    const double wps = threads / 32 / 4.0;
-    printf("softmax pattern (fma, ex2, sum, pack; +1 FADD): %2d warps/CTA: %.2f cycles per ex2 per sub-partition\n",
-           threads / 32, static_cast<double>(h) / (iters * 32) / wps);
-  }
+  for (int packed = 0; packed < 2; ++packed)
+    for (int threads : {128, 256, 512}) {
+      const int iters = 500;
+      if (packed) softmax_like<true><<<148, threads>>>(in, reinterpret_cast<uint32_t*>(out), cyc, iters, 0.18f, 3.f);
+      else softmax_like<false><<<148, threads>>>(in, reinterpret_cast<uint32_t*>(out), cyc, iters, 0.18f, 3.f);
+      cudaDeviceSynchronize();
+      long long h;
+      cudaMemcpy(&h, cyc, sizeof h, cudaMemcpyDeviceToHost);
+      const double wps = threads / 32 / 4.0;
+      printf("softmax pattern (%s, ex2, sum, pack; +1 FADD): %2d warps/CTA: %.2f cycles per ex2 per sub-partition\n",
+             packed ? "FFMA2 / FADD2" : "fma", threads / 32, static_cast<double>(h) / (iters * 32) / wps);
+    }
   for (int mode = 0; mode < 2; ++mode) {
     for (int threads : {128, 256}) {
       const int iters = 1000;

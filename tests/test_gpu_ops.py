@@ -24,6 +24,7 @@ def _ref_attention(qkv, enc, heads):
 
 
 ATTN_DEFAULT_LAYOUT = 1  # k2_api.cu g_attn_half
+ATTN_DEFAULT_STAGGER = 1200  # k2_api.cu g_attn_stagger
 
 
 @pytest.mark.parametrize("B,heads,T,Tc", [
@@ -56,6 +57,36 @@ def test_attention_d64(B, heads, T, Tc, half_rows):
     assert err < 4e-3, err
     rel = ((out.float() - ref).norm() / ref.norm()).item()
     assert rel < 2e-3, rel
+
+
+@pytest.mark.parametrize("half_rows", [0, 1])
+def test_attention_d64_modes_bit_identical(half_rows):
+    """The start-up offset of the second query tile (tuning key 5; each tile has its own MMA issuer) only moves work in time,
+    and the packed FFMA2 / FADD2 softmax arithmetic (key 6 + 10 / + 30) rounds exactly like the scalar instructions: the
+    output must not change by a bit.  T = 600 gives two full query tiles per CTA plus a ragged third CTA."""
+    from kandinsky2 import ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    B, heads, T, Tc = 2, 3, 600, 32
+    qkv = torch.randn(B, T, heads * 192, device="cuda", generator=g).half()
+    enc = torch.randn(B, Tc, heads * 128, device="cuda", generator=g).half()
+    ops.set_tuning(9, half_rows)
+    outs = {}
+    try:
+        for mode, stagger in ((0, 1200), (0, 0), (0, 5000), (10, 1200), (30, 1200), (1, 1200), (31, 300)):
+            ops.set_tuning(6, mode)
+            ops.set_tuning(5, stagger)
+            outs[(mode, stagger)] = ops.attention_d64(qkv, heads, enc)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_tuning(9, ATTN_DEFAULT_LAYOUT)
+        ops.set_tuning(6, 0)
+        ops.set_tuning(5, ATTN_DEFAULT_STAGGER)
+    ref = _ref_attention(qkv, enc, heads)
+    assert (outs[(0, 1200)].float() - ref).abs().max().item() < 4e-3
+    for key in ((0, 0), (0, 5000), (10, 1200), (30, 1200)):
+        assert torch.equal(outs[key], outs[(0, 1200)]), key
+    assert torch.equal(outs[(31, 300)], outs[(1, 1200)])
+    assert (outs[(1, 1200)].float() - ref).abs().max().item() < 4e-3
 
 
 @pytest.mark.parametrize("half_rows", [0, 1])
