@@ -45,7 +45,9 @@ void k2_reset_launch_count(void);
  * key 10 = default number of epilogue warp sets of the CTA-pair conv kernel (1; 2 = 384-thread variant whose second set drains
  * the other half of the 64-column pairs: bit-identical results, faster where the K loop is short).  Keys 0, 1, 2 and 10 are
  * process-wide defaults; k2_conv_gemm_cfg overrides them per call.  key 11 = blocks per SM the GroupNorm apply grids are sized
- * for (0 = each kernel's real occupancy, i.e. one full wave; 4 = the round-1 sizing). */
+ * for (0 = each kernel's real occupancy, i.e. one full wave; 4 = the round-1 sizing); key 12 = tail split of the CTA-pair conv
+ * kernel's last partial wave (0 off, default; 1 = where the K loop is long enough to pay for the hand-over; 2 = wherever
+ * possible: tests and probes). */
 int k2_set_tuning(int key, int value);
 
 /* ---------------------------------------------------------------------------------------------
@@ -65,7 +67,13 @@ int k2_set_tuning(int key, int value);
  * workspace (may be NULL): caller-owned scratch for split-K.  Where a cycle model of the launch (waves of work units x
  * K chunks per unit, plus the second pass) says so -- small M with a huge K -- K is split over several CTAs that write
  * fp32 partial tiles [split][M][Cout] there, and a second launch sums them in a fixed order (+bias, +residual) --
- * deterministic, no atomics.
+ * deterministic, no atomics.  The split-K partials use the LOWER half of the workspace.  The UPPER half serves the tail
+ * split of the CTA-pair kernel (tuning key 12, off by default: measured neutral inside the power-capped step): when the last wave of work units would occupy only part of
+ * the CTA pairs, each of its units is cut into 2..4 parts along K that run on the idle pairs, and the owning part adds the
+ * others' fp32 accumulator tiles (handed over through the upper half, fixed summation order) before its ordinary epilogue --
+ * one launch, same outputs and GroupNorm partials, a different (still deterministic) fp32 summation order.  The last
+ * 64 KB of the workspace are hand-over flags: they must be ZERO before the first launch that uses the workspace; the library
+ * leaves them zero after every launch.  Launches sharing a workspace must be stream-ordered.
  * gn_partial (may be NULL): fp32 [row groups][Cout][2]; when given and the launch qualifies (fp16 output, Cout % 64 == 0,
  * N tile >= 64) the launch also emits (sum, sum of squares) partials of the ROUNDED output, image-major, which
  * k2_gn_finalize turns into GroupNorm statistics -- the consumer's statistics pass disappears.  Row groups: one per M tile
@@ -113,6 +121,10 @@ int k2_conv_gemm_cfg(const K2ConvSrc* srcs, int nsrc, int NB, int H, int W, cons
  * info = int[7] with the meaning given above. */
 int k2_conv_plan(int NB, int H, int W, int taps, int Ktot, int Cout, int out_mode, long long workspace_bytes,
                  int want_gn_partial, int* info);
+
+/* K parts the last partial wave's units were cut into (tail split, see k2_conv_gemm) by the most recent k2_conv_gemm /
+ * k2_conv_gemm_cfg / k2_conv_plan call of this thread: 1 = not used.  Diagnostics for tests and tooling. */
+int k2_conv_last_tail_split(void);
 
 /* ---------------------------------------------------------------------------------------------
  * GroupNorm (32 groups in the UNet) statistics + fused apply.

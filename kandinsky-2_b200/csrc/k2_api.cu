@@ -18,6 +18,11 @@ static std::atomic<long long> g_launches{0};
 static int g_force_bn = 0;
 static int g_force_split = 0;  // 0 auto, 1 off, n>1 forced
 static int g_force_2cta = 0;   // 0 auto, 1 off, 2 on
+static int g_tail_split = 0;  // tuning key 12: stream-K over a CTA-pair launch's last, partial wave: 0 off (default), 1 where the
+                              // model says it pays, 2 wherever possible (tests / probes).  Measured (profiles/README.md):
+                              // 9-14 % on the level-2 2304 -> 1152 convolutions timed alone, nothing inside the power-capped
+                              // step (a partial wave's busy SMs clock higher), and it costs bit-identical results across
+                              // batch slots -> off.
 static int g_attn_stagger = 1200;  // cycles query tile 1 starts late (independent MMA issuers keep the offset): 218 -> 200 us at level 1, profiles/attn_probe_r2.txt
 static int g_attn_poly = 0;  // measured: the softmax is not MUFU-bound (profiles/README.md), offloading only adds instructions
 static int g_pdl = 0;          // programmatic dependent launch of the step's kernels
@@ -154,7 +159,13 @@ struct ConvPlan {
   int BN, two_cta, splits;
   int fuse_stats, row_groups;
   int es;  // epilogue warp sets of the CTA-pair kernel (1 or 2)
+  int tail_first, tail_count, tail_split, tail_kps;  // stream-K over the last partial wave (tail_split <= 1: off; else 4 = slot
+                                                     // stride), tail_kps = K chunks per CTA pair's span
 };
+
+// Workspace layout: split-K partial sums use the lower half; the upper half holds the tail-split hand-over tiles, its last
+// 64 KB the hand-over flags (zero whenever no conv launch is in flight: the caller zeroes them once, owners reset them).
+constexpr long long TAIL_FLAG_BYTES = 64 << 10;
 
 // cfg (may be null): per-call overrides {N tile, CTA-pair mode (1 off / 2 on), split-K factor, epilogue warp sets}; 0 = the
 // process-wide tuning knob, else automatic.  The caller's launch plan bakes its choice per launch (kandinsky2/model/unet.py).
@@ -208,7 +219,7 @@ static void plan_conv(int NB, int H, int W, bool any9, int kchunks, int Cout, in
     if (sp == 1) return true;
     const int kps = (kchunks + sp - 1) / sp;
     return can_split && kps >= 8 && (sp - 1) * kps < kchunks &&
-           static_cast<long long>(sp) * M_total * Cout * 4 <= workspace_bytes;
+           static_cast<long long>(sp) * M_total * Cout * 4 <= workspace_bytes / 2;  // upper half: tail-split hand-over
   };
   auto model = [&](int bn, int sp, bool pair) {
     const long long nt = (Cout + bn - 1) / bn;
@@ -257,6 +268,44 @@ static void plan_conv(int NB, int H, int W, bool any9, int kchunks, int Cout, in
     pl.m_tiles_phase = two_cta ? (pl.m_tiles + 1) / 2 * 2 : pl.m_tiles;
   }
 
+  // Tail split = stream-K over the LAST wave only (profiles/README.md, "level-2 wave quantisation"): units = m_pairs x n_tiles
+  // on P = SMs / 2 CTA pairs; when the last wave holds R < P units, their K loops laid end to end (R x kchunks chunks) are cut
+  // into P equal spans of L chunks, one per pair, so the wave takes L / kchunks of a unit's time instead of a whole unit.  A tile
+  // is then the sum of up to 4 K parts computed by different pairs: the part with the tile's first chunk adds the others' fp32
+  // accumulators in its epilogue (k2_conv_gemm.cu), in a fixed order.  Same outputs / GroupNorm partials layout, a different
+  // (deterministic) fp32 summation order than the unsplit launch.  L >= kchunks / 3 bounds the parts per tile.
+  pl.tail_first = pl.tail_count = pl.tail_kps = 0;
+  pl.tail_split = 1;
+  if (g_tail_split && two_cta && splits == 1 && !pl.halo_pitch && out_mode == 0 && Cout % 64 == 0 && BN % 64 == 0 && has_workspace) {
+    const int m_pairs = ((up2 ? 4 * pl.m_tiles_phase : pl.m_tiles) + 1) / 2;
+    const int units = m_pairs * ((Cout + BN - 1) / BN);
+    const int P = num_sms() / 2;
+    const int R = units % P;
+    if (R > 0 && kchunks >= 16) {
+      long long L = (static_cast<long long>(R) * kchunks + P - 1) / P;
+      L = std::max<long long>(L, (kchunks + 2) / 3);
+      int max_parts = 1;
+      for (int t = 0; t < R; ++t) {
+        const long long first = static_cast<long long>(t) * kchunks / L;
+        const long long last = std::min((static_cast<long long>(t + 1) * kchunks - 1) / L, (static_cast<long long>(R) * kchunks - 1) / L);
+        max_parts = std::max(max_parts, static_cast<int>(last - first + 1));
+      }
+      const long long buf_bytes = static_cast<long long>(R) * 2 * 3 * 128 * BN * 4;
+      const long long flag_bytes = static_cast<long long>(R) * 2 * 3 * 8 * 4;
+      // the hand-over (partner tiles through L2, the owner's epilogue after them) costs ~8 us that nothing overlaps: the K
+      // time saved, (kchunks - L) chunks of 2*BN + 60 cycles, must be a multiple of that (profiles/tail_probe_r2.txt: a gain at
+      // K = 162 / 324 chunks, a loss at 54 chunks and for the 18-chunk qkv GEMMs)
+      const long long saved_cycles = (kchunks - L) * (2LL * BN + 60);
+      if ((saved_cycles >= 26000 || (g_tail_split == 2 && L < kchunks)) && max_parts <= 4 && buf_bytes <= workspace_bytes / 2 - TAIL_FLAG_BYTES &&
+          flag_bytes <= TAIL_FLAG_BYTES) {
+        pl.tail_first = units - R;
+        pl.tail_count = R;
+        pl.tail_split = 4;  // slot stride: up to 3 partner parts per CTA half of a tile
+        pl.tail_kps = static_cast<int>(L);
+      }
+    }
+  }
+
   // fused GroupNorm partial statistics: from the epilogue when a tile never straddles two images (one partial per M
   // tile: the epilogue folds its four warps) or when it holds 16 pixels of each of 8 images (one partial per (image,
   // spatial tile): every half warp of the epilogue holds exactly one image's pixels); split-K launches produce them in
@@ -274,7 +323,9 @@ static void plan_conv(int NB, int H, int W, bool any9, int kchunks, int Cout, in
   }
 }
 
+static thread_local int g_last_tail_split = 1;
 static void plan_to_info(const ConvPlan& pl, int* info) {
+  g_last_tail_split = pl.tail_split;
   if (!info) return;
   info[0] = pl.BN; info[1] = pl.two_cta; info[2] = pl.splits; info[3] = pl.m_tiles; info[4] = pl.TN;
   info[5] = pl.fuse_stats; info[6] = pl.row_groups;
@@ -289,6 +340,7 @@ extern "C" {
 const char* k2_last_error(void) { return g_err.c_str(); }
 int k2_version(void) { return 100; }
 long long k2_launch_count(void) { return g_launches.load(); }
+int k2_conv_last_tail_split(void) { return g_last_tail_split; }
 void k2_reset_launch_count(void) { g_launches.store(0); }
 int k2_set_tuning(int key, int value) {
   if (key == 0) {
@@ -313,6 +365,10 @@ int k2_set_tuning(int key, int value) {
   }
   if (key == 5) {
     g_attn_stagger = value;
+    return 0;
+  }
+  if (key == 12) {
+    g_tail_split = value;
     return 0;
   }
   if (key == 6) {
@@ -438,6 +494,15 @@ int k2_conv_gemm_cfg(const K2ConvSrc* srcs, int nsrc, int NB, int H, int W, cons
   p.k_per_split = (kchunks + splits - 1) / splits;
   p.M_total = static_cast<long long>(NB) * H * W * (up2 ? 4 : 1);
   p.ws = reinterpret_cast<float*>(workspace);
+  p.tail_first = pl.tail_first;
+  p.tail_count = pl.tail_count;
+  p.tail_split = pl.tail_split;
+  p.tail_kps = pl.tail_kps;
+  if (pl.tail_split > 1) {
+    char* wsb = reinterpret_cast<char*>(workspace);
+    p.tail_buf = reinterpret_cast<float*>(wsb + (workspace_bytes / 2 / 256) * 256);
+    p.tail_flags = reinterpret_cast<unsigned int*>(wsb + ((workspace_bytes - TAIL_FLAG_BYTES) / 256) * 256);
+  }
   p.n_tiles = (Cout + BN - 1) / BN;
   p.Cout = Cout;
   {

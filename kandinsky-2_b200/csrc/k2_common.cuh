@@ -482,4 +482,15 @@ __device__ __forceinline__ uint32_t pin_reg(uint32_t v) {
   return v;
 }
 
+// GPU-scope release store / acquire load of a flag in global memory (hand-over of data written with ordinary stores before a
+// __threadfence on the producer side; the consumer reads the data with ld.global.cg after the acquire).
+__device__ __forceinline__ void st_release_gpu(unsigned int* addr, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* addr) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
+  return v;
+}
+
 }  // namespace k2

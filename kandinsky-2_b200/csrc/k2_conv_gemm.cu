@@ -78,10 +78,14 @@ __device__ __forceinline__ void decode_m_tile(const ConvGemmParams& p, int m_idx
 // ES = number of epilogue warp SETS (each set = 4 warps covering the 4 TMEM lane quarters).  ES = 1 is the validated
 // configuration; with ES = 2 (384-thread variant of the CTA-pair kernel, tuning key 10, round-2 candidate) set `es` handles
 // the 64-column pairs jp with jp % 2 == es, so two warps per scheduler drain the accumulator.
-template <int BN, int ES = 1>
+template <int BN, int ES = 1, bool TAIL = false>
 __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t tmem_base, int acc_col, int ew, int lane,
                                               int n0, int y0, int x0, int n_idx, int split, int m_idx, float* stat_smem,
-                                              int es_arg = 0, int phase = 0) {
+                                              int es_arg = 0, int phase = 0, int tail_role = 0, int tail_slot = 0, int tail_np = 0) {
+  // tail_role (CTA-pair kernel only): 0 = ordinary tile; 1 = a K part >= 1 of a tail-split tile: the raw fp32 accumulator goes
+  // to p.tail_buf slot tail_slot, then the warp raises its flag; 2 = part 0 (the owner): waits for the flags of slots
+  // tail_slot .. tail_slot + tail_np - 1, adds those partial tiles to its accumulator in a fixed order and carries on with the
+  // normal epilogue (bias, residual, fp16 store, GroupNorm partials): the consumers cannot tell a tail-split tile from another.
   const int es = (ES == 1) ? 0 : es_arg;
   const int row = ew * 32 + lane;
   const int thw = p.TH * p.TW;
@@ -136,13 +140,49 @@ __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t 
             }
             return;
           }
+          constexpr int NP = BN / 64;
+          if (TAIL && tail_role == 1) {
+            // accumulator order: float4 (jp, q) of row r at [(jp * 16 + q) * 128 + r] -- a warp stores / loads 512 contiguous bytes
+            float4* buf = reinterpret_cast<float4*>(p.tail_buf) + static_cast<long long>(tail_slot) * (32 * BN);
+#pragma unroll 1
+            for (int jp = 0; jp < NP; ++jp) {
+              if (n_idx * BN + jp * 64 >= p.Cout || (ES > 1 && (jp % ES) != es)) continue;
+              uint32_t r[64];
+              {
+                uint32_t(&r0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[0]);
+                uint32_t(&r1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&r[32]);
+                tmem_ld_32x32b_x32(taddr0 + jp * 64, r0);
+                tmem_ld_32x32b_x32(taddr0 + jp * 64 + 32, r1);
+                tmem_ld_wait();
+              }
+#pragma unroll
+              for (int q = 0; q < 16; ++q)
+                __stcg(buf + (jp * 16 + q) * 128 + row, make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                                                   __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3])));
+            }
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) st_release_gpu(p.tail_flags + tail_slot * 8 + es * 4 + ew, 1u);
+            return;
+          }
+          if (TAIL && tail_role == 2) {
+            if (lane == 0) {
+              for (int pt = 0; pt < tail_np; ++pt) {
+                const unsigned int* flag = p.tail_flags + (tail_slot + pt) * 8 + es * 4 + ew;
+                const long long t0 = clock64();
+                while (ld_acquire_gpu(flag) == 0u) {
+                  if (clock64() - t0 > 4000000000LL) __trap();  // a scheduling bug traps instead of hanging the GPU
+                }
+              }
+            }
+            __syncwarp();
+          }
           if (p.bias) {
 #pragma unroll
             for (int c = lane; c < BN; c += 32) bsm[c] = (n_idx * BN + c < p.Cout) ? __ldg(p.bias + n_idx * BN + c) : 0.f;
             __syncwarp();
           }
           __half* outb = reinterpret_cast<__half*>(p.out);
-          constexpr int NP = BN / 64;
           float4 st[NP];   // fused GroupNorm statistics of this warp's 32 rows: (sum, sumsq) of columns 2l, 2l+1 per pair
           uint4 rpre[8];   // residual of the NEXT 64-column pair, in flight while the current one is processed
           auto load_res = [&](int jp) {
@@ -183,6 +223,26 @@ __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t 
                   if (p.residual && jp + 1 < NP) load_res(jp + 1);
                 }
                 tmem_ld_wait();
+              }
+              if (TAIL && tail_role == 2) {
+                for (int pt = 0; pt < tail_np; ++pt) {
+                  const float4* buf = reinterpret_cast<const float4*>(p.tail_buf) + static_cast<long long>(tail_slot + pt) * (32 * BN);
+#pragma unroll
+                  for (int q0 = 0; q0 < 16; q0 += 4) {  // four loads in flight at a time: 16 registers, not 64
+                    float4 t[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) t[u] = __ldcg(buf + (jp * 16 + q0 + u) * 128 + row);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                      const int q = q0 + u;
+                      r[4 * q] = __float_as_uint(__uint_as_float(r[4 * q]) + t[u].x);
+                      r[4 * q + 1] = __float_as_uint(__uint_as_float(r[4 * q + 1]) + t[u].y);
+                      r[4 * q + 2] = __float_as_uint(__uint_as_float(r[4 * q + 2]) + t[u].z);
+                      r[4 * q + 3] = __float_as_uint(__uint_as_float(r[4 * q + 3]) + t[u].w);
+                    }
+                    asm volatile("" ::: "memory");
+                  }
+                }
               }
 #pragma unroll
               for (int v = 0; v < 8; ++v) {  // 8 columns = one 16-byte piece of the staged row
@@ -250,6 +310,11 @@ __device__ __forceinline__ void epilogue_tile(const ConvGemmParams& p, uint32_t 
               }
               __syncwarp();
             }
+          }
+          if (TAIL && tail_role == 2) {  // every partial of this warp's rows has been read: the flags are zero again for the next launch
+            __syncwarp();
+            if (lane == 0)
+              for (int pt = 0; pt < tail_np; ++pt) p.tail_flags[(tail_slot + pt) * 8 + es * 4 + ew] = 0u;
           }
           if (p.gn_part && p.gn_mode == 1) {
             // one partial per (M tile, column): the four warps' sums are folded in a fixed order through the (now idle)
@@ -557,7 +622,9 @@ struct Cfg2 {
   static constexpr int THREADS = 128 + 128 * ES;             // 4 control warps + ES sets of 4 epilogue warps
 };
 
-template <int BN, int ES = 1>
+// TAIL: the launch uses the tail split (stream-K over the last partial wave); a separate instantiation, so that the default
+// kernels stay instruction-for-instruction what they were before the feature existed.
+template <int BN, int ES = 1, bool TAIL = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 128 * ES, 1)
 conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p) {
   using C = Cfg2<BN, ES>;
@@ -605,7 +672,49 @@ conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p) {
   pdl_launch();
 
   const int m_pairs = (p.m_tiles + 1) >> 1;
-  const int total_tiles = m_pairs * p.n_tiles * p.splits;
+  // Work items of this launch: the tiles (x split-K parts), or -- tail split -- the tiles of the full waves followed by ONE
+  // more wave in which the K loops of the remaining tail_count tiles, laid end to end (tail_count x num_k_chunks chunks), are
+  // cut into equal spans of tail_kps chunks, one span per CTA pair (stream-K over the last wave only).  A span covers the
+  // end of one tile and possibly the start of the next: up to two sub-items per pair (items tail_first + pair and
+  // tail_first + num_pairs + pair).  The sub-item holding a tile's first chunk owns the tile (part 0); it is always the
+  // LAST thing its pair does, and it only waits for sub-items that are the FIRST thing their pairs do in this wave: no cycles.
+  const int total_tiles = TAIL ? p.tail_first + 2 * num_pairs : m_pairs * p.n_tiles * p.splits;
+  // -> false: an empty sub-item (all three roles skip it); part < 0: ordinary item; nparts = K parts of the tile
+  auto decode_item = [&](int item, int& tile, int& part, int& nparts, int& split, int& k0, int& k1) -> bool {
+    if (TAIL && item >= p.tail_first) {
+      const int idx = item - p.tail_first;
+      const int sub = idx / num_pairs, i = idx - sub * num_pairs;
+      const int nk = p.num_k_chunks, L = p.tail_kps;
+      const int g0 = i * L, g1 = min(g0 + L, p.tail_count * nk);
+      if (g0 >= g1) return false;
+      int ta = g0 / nk;
+      const int ka0 = g0 - ta * nk, ka1 = min(nk, ka0 + (g1 - g0));
+      if (sub == 0) {
+        k0 = ka0;
+        k1 = ka1;
+      } else {
+        const int rest = (g1 - g0) - (ka1 - ka0);
+        if (rest <= 0) return false;
+        ++ta;
+        k0 = 0;
+        k1 = rest;
+      }
+      const int first_span = (ta * nk) / L;
+      const int last_span = min(((ta + 1) * nk - 1) / L, (p.tail_count * nk - 1) / L);
+      part = i - first_span;
+      nparts = last_span - first_span + 1;
+      tile = p.tail_first + ta;
+      split = 0;
+      return true;
+    }
+    tile = item;
+    part = -1;
+    nparts = 1;
+    split = tile / (m_pairs * p.n_tiles);
+    k0 = split * p.k_per_split;
+    k1 = min(p.num_k_chunks, k0 + p.k_per_split);
+    return true;
+  };
 
   if (warp_idx == 0) {
     // ===================================== TMA producer (both CTAs) ==========================
@@ -613,15 +722,14 @@ conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p) {
       int stage = 0;
       uint32_t ring_phase = 0;
       const uint32_t tx_bytes = 2u * (p.a_box_bytes + C::B_STAGE_BYTES);
-      for (int tile = pair; tile < total_tiles; tile += num_pairs) {
+      for (int item = pair; item < total_tiles; item += num_pairs) {
+        int tile, part, nparts, split, k0, k1;
+        if (!decode_item(item, tile, part, nparts, split, k0, k1)) continue;
         const int m_idx = (tile % m_pairs) * 2 + static_cast<int>(rank);
         const int n_idx = (tile / m_pairs) % p.n_tiles;
-        const int split = tile / (m_pairs * p.n_tiles);
         int n0, y0, x0, phase;
         decode_m_tile(p, m_idx, n0, y0, x0, phase);  // m_idx == m_tiles (odd tail): n0 >= NB -> the box is all zero-fill
         const int kb = phase * p.num_k_chunks;  // up2: each phase has its own 4-tap weight block
-        const int k0 = split * p.k_per_split;
-        const int k1 = min(p.num_k_chunks, k0 + p.k_per_split);
         int s = 0, rem = k0;
         while (rem >= p.seg_taps[s] * p.seg_kchunks[s]) {
           rem -= p.seg_taps[s] * p.seg_kchunks[s];
@@ -662,12 +770,13 @@ conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p) {
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = pair; tile < total_tiles; tile += num_pairs) {
+      for (int item = pair; item < total_tiles; item += num_pairs) {
+        int tile, part, nparts, split, k0, k1;
+        if (!decode_item(item, tile, part, nparts, split, k0, k1)) continue;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 256);
-        const int split = tile / (m_pairs * p.n_tiles);
-        const int nk = min(p.num_k_chunks, (split + 1) * p.k_per_split) - split * p.k_per_split;
+        const int nk = k1 - k0;
         for (int kc = 0; kc < nk; ++kc) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -697,15 +806,20 @@ conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p) {
     uint32_t acc_phase = 0;
     const uint32_t leader_empty0 = mapa_u32(smem_u32(&tmem_empty[0]), 0);
     const uint32_t leader_empty1 = mapa_u32(smem_u32(&tmem_empty[1]), 0);
-    for (int tile = pair; tile < total_tiles; tile += num_pairs) {
+    for (int item = pair; item < total_tiles; item += num_pairs) {
+      int tile, part, nparts, split, k0, k1;
+      if (!decode_item(item, tile, part, nparts, split, k0, k1)) continue;
       const int m_idx = (tile % m_pairs) * 2 + static_cast<int>(rank);
       const int n_idx = (tile / m_pairs) % p.n_tiles;
-      const int split = tile / (m_pairs * p.n_tiles);
       int n0, y0, x0, phase;
       decode_m_tile(p, m_idx, n0, y0, x0, phase);
+      // tail split: (tail_split - 1) hand-over slots per CTA half of a tail tile, one per K part >= 1
+      const int tail_role = (part < 0 || nparts == 1) ? 0 : (part > 0 ? 1 : 2);
+      const int tail_slot = (part < 0) ? 0 : ((tile - p.tail_first) * 2 + static_cast<int>(rank)) * (p.tail_split - 1) + max(part - 1, 0);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      epilogue_tile<BN, ES>(p, tmem_base, acc * 256, ew, lane, n0, y0, x0, n_idx, split, m_idx, stat_smem, es, phase);
+      epilogue_tile<BN, ES, TAIL>(p, tmem_base, acc * 256, ew, lane, n0, y0, x0, n_idx, split, m_idx, stat_smem, es, phase,
+                                  tail_role, tail_slot, nparts - 1);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(acc ? leader_empty1 : leader_empty0);
@@ -722,38 +836,30 @@ conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p) {
   }
 }
 
-template <int BN>
-int launch_bn2(const ConvGemmParams& p, cudaStream_t stream) {
-  using C = Cfg2<BN>;
+template <int BN, int ES, bool TAIL>
+int launch_pair(const ConvGemmParams& p, cudaStream_t stream) {
+  using C = Cfg2<BN, ES>;
   static bool attr_set = false;
   if (!attr_set) {
-    K2_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    K2_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm2_kernel<BN, ES, TAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
   const int m_pairs = (p.m_tiles + 1) / 2;
   const int total = m_pairs * p.n_tiles * p.splits;
   const int max_pairs = num_sms() / 2;
-  const int pairs = total < max_pairs ? total : max_pairs;
-  K2_CHECK_CUDA(launch_k(conv_gemm2_kernel<BN>, dim3(2 * pairs), dim3(256), C::SMEM_BYTES, stream, p));
+  const int pairs = (TAIL || total >= max_pairs) ? max_pairs : total;  // tail split: one K span per CTA pair of the device
+  K2_CHECK_CUDA(launch_k(conv_gemm2_kernel<BN, ES, TAIL>, dim3(2 * pairs), dim3(C::THREADS), C::SMEM_BYTES, stream, p));
   return 0;
 }
-
+template <int BN>
+int launch_bn2(const ConvGemmParams& p, cudaStream_t stream) {
+  return p.tail_split > 1 ? launch_pair<BN, 1, true>(p, stream) : launch_pair<BN, 1, false>(p, stream);
+}
 // CTA-pair kernel with two epilogue warp sets (384 threads, one pipeline stage fewer); bit-identical to the one-set kernel
 // (tests/test_gpu_conv_gemm.py::test_two_epilogue_sets_bit_identical).
 template <int BN>
 int launch_bn2e(const ConvGemmParams& p, cudaStream_t stream) {
-  using C = Cfg2<BN, 2>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    K2_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm2_kernel<BN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
-  }
-  const int m_pairs = (p.m_tiles + 1) / 2;
-  const int total = m_pairs * p.n_tiles * p.splits;
-  const int max_pairs = num_sms() / 2;
-  const int pairs = total < max_pairs ? total : max_pairs;
-  K2_CHECK_CUDA(launch_k(conv_gemm2_kernel<BN, 2>, dim3(2 * pairs), dim3(C::THREADS), C::SMEM_BYTES, stream, p));
-  return 0;
+  return p.tail_split > 1 ? launch_pair<BN, 2, true>(p, stream) : launch_pair<BN, 2, false>(p, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -82,6 +82,13 @@ struct ConvGemmParams {
                        //    straddles two phases -- its two boxes share one weight tile)
   int halo_pitch;      // 0: per-tap boxes; 10 / 16: halo kernel, pixels per halo row in shared memory
   int halo_bo;         // halo kernel: 1 = put (start >> 7) & 7 into the descriptor's base-offset field
+  // Tail split (CTA-pair kernel, splits == 1) = stream-K over the last, partial wave: the K loops of tiles [tail_first,
+  // tail_first + tail_count) laid end to end are cut into spans of tail_kps chunks, one per CTA pair; the part holding a tile's
+  // first chunk (the owner) adds the other parts' fp32 accumulator tiles, handed over through tail_buf / tail_flags, before its
+  // normal epilogue.  tail_split <= 1: off; else tail_split - 1 = hand-over slots per CTA half of a tile.
+  int tail_first, tail_count, tail_split, tail_kps;
+  float* tail_buf;            // [tile - tail_first][CTA rank][part - 1][128 x BN] fp32, accumulator (column-quad, row) order
+  unsigned int* tail_flags;   // [...same...][8 epilogue warps]: 1 = that warp's rows of the part are in tail_buf; zero between launches
 };
 int launch_conv_gemm(const ConvGemmParams& p, int BN, int epilogue_sets, cudaStream_t stream);
 int launch_splitk_finalize(const float* ws, int splits, long long M, int Cout, const float* bias, const __half* residual,

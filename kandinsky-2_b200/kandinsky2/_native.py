@@ -32,6 +32,7 @@ SIGNATURES = {
     "k2_version": (_I, []),
     "k2_launch_count": (_LL, []),
     "k2_reset_launch_count": (None, []),
+    "k2_conv_last_tail_split": (_I, []),
     "k2_set_tuning": (_I, [_I, _I]),
     "k2_conv_gemm": (_I, [ctypes.POINTER(K2ConvSrc), _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _P, _I, _P, _I, _I, _P, _LL, _P,
                          ctypes.POINTER(ctypes.c_int), _P]),

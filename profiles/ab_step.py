@@ -23,7 +23,7 @@ from kandinsky2.model import unet as unet_mod  # noqa: E402
 from kandinsky2.model.gaussian_diffusion import FusedStep, create_ddpm_v22  # noqa: E402
 
 
-TUNING_DEFAULTS = {4: 1, 5: 1200, 9: 1}  # k2_api.cu defaults that are not 0 (key 4 is switched on by this script)
+TUNING_DEFAULTS = {4: 1, 5: 1200, 9: 1, 12: 0}  # k2_api.cu defaults that are not 0 (key 4 is switched on by this script)
 
 
 def main():

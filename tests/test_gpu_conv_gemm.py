@@ -290,3 +290,85 @@ def test_conv3x3_over_nearest_upsample(NB, H, W, Cin, Cout):
         want = ops.gn_apply(y, None, ops.gn_stats(y), gamma, beta, act=1)
         torch.cuda.synchronize()
         assert (got.float() - want.float()).abs().max().item() <= 2e-3 * max(1.0, want.float().abs().max().item())
+
+
+@pytest.mark.parametrize("NB,H,W,Cin,Cs,Cout,cfg,parts", [
+    (8, 24, 24, 1152, 0, 1152, None, 4),          # UNet level 2: 120 units on 74 CTA pairs, 46 in the last wave
+    (8, 24, 24, 1152, 384, 1152, (192, 2, 1, 2), 4),  # + 1x1 skip segment, residual, two epilogue warp sets
+    (2, 24, 24, 576, 0, 1152, (192, 2, 1, 1), 4),  # fewer units than CTA pairs: every tile is cut
+    (8, 96, 96, 128, 0, 384, (192, 2, 1, 1), 4),   # level-0 geometry: 576 units, a short K loop (18 chunks)
+    (8, 48, 48, 256, 0, 768, None, 4),             # 216 units, last wave 92 % full: only the forced mode splits it
+])
+def test_tail_split(NB, H, W, Cin, Cs, Cout, cfg, parts):
+    _tail_split_case(NB, H, W, Cin, Cs, Cout, cfg, parts)
+
+
+def test_tail_split_policy():
+    """key 12: 0 (default) never; 1 = on for the long K loops of UNet level 2, off where the hand-over would cost more than it
+    saves (short K loops, nearly full last waves)."""
+    from kandinsky2 import ops
+    ops.conv_plan(8, 24, 24, 9, 9 * 1152, 1152)
+    assert ops.conv_last_tail_split() == 1
+    ops.set_tuning(12, 1)
+    try:
+        ops.conv_plan(8, 24, 24, 9, 9 * 1152, 1152)
+        assert ops.conv_last_tail_split() == 4
+        for geo in ((8, 96, 96, 9, 9 * 384, 384), (8, 48, 48, 9, 9 * 768, 768), (1, 1, 4608, 1, 1152, 3456)):
+            ops.conv_plan(*geo)
+            assert ops.conv_last_tail_split() == 1, geo
+    finally:
+        ops.set_tuning(12, 0)
+
+
+def _tail_split_case(NB, H, W, Cin, Cs, Cout, cfg, parts):
+    """Stream-K over the last partial wave of the CTA-pair kernel (tuning key 12): tiles of that wave are sums of up to 4 K
+    parts computed by different CTA pairs and added, in a fixed order, in the owning part's epilogue.  Checked against torch
+    fp32, against the unsplit launch (same values up to the fp32 summation order, i.e. fp16 rounding flips), for run-to-run
+    bit-identity and for the fused GroupNorm partial sums (which must describe the STORED values exactly)."""
+    from kandinsky2 import ops
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn(NB, H, W, Cin, device="cuda", generator=g).half()
+    w = torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) / (3 * Cin ** 0.5)
+    b = torch.randn(Cout, device="cuda", generator=g)
+    srcs, wp = [(x, 9)], ops.pack_conv_weight(w)
+    ref = _ref_conv(x, w, b, 1) if NB * H * W <= 8 * 48 * 48 else torch.cat([_ref_conv(x[i:i + 1], w, b, 1) for i in range(NB)])
+    res = None
+    if Cs:
+        xs = torch.randn(NB, H, W, Cs, device="cuda", generator=g).half()
+        w1 = torch.randn(Cout, Cs, 1, 1, device="cuda", generator=g) / Cs ** 0.5
+        res = torch.randn(NB, H, W, Cout, device="cuda", generator=g).half()
+        srcs.append((xs, 1))
+        wp = torch.cat([wp, ops.pack_conv_weight(w1)], 1).contiguous()
+        ref = ref + _ref_conv(xs, w1, None, 0) + res.float()
+
+    def run(tail):
+        ops.set_tuning(12, 2 * tail)  # 2: wherever possible, whatever the benefit model says
+        try:
+            part = torch.zeros(ops.gn_part_floats(NB, H, W, Cout), device="cuda")
+            info = [0] * 7
+            y = ops.conv_gemm(srcs, wp, Cout, bias=b, residual=res, gn_part=part, info=info, cfg=cfg)
+            used = ops.conv_last_tail_split()
+            torch.cuda.synchronize()
+            return y, part, info, used
+        finally:
+            ops.set_tuning(12, 0)
+
+    y0, part0, info0, used0 = run(0)
+    y1, part1, info1, used1 = run(1)
+    y2, part2, _, _ = run(1)
+    assert used0 == 1 and used1 == parts, (used0, used1)
+    assert info0[:3] == info1[:3] and info1[5] == 1
+    assert torch.equal(y1, y2) and torch.equal(part1, part2)          # deterministic
+    rel = ((y1.float() - ref).norm() / ref.norm()).item()
+    assert rel < 1e-3, rel
+    if parts > 1:
+        d = (y1.float() - y0.float()).abs()
+        assert d.max().item() <= 2e-2 and (d > 0).float().mean().item() < 0.2   # fp16 rounding flips only
+    else:
+        assert torch.equal(y1, y0)
+    # the partial sums are those of the stored fp16 values: per image, sum over row groups == sum over the image's pixels
+    rg = info1[6] // NB
+    ps = part1[:NB * rg * Cout * 2].view(NB, rg, Cout, 2).double().sum(1)
+    yd = y1.double().view(NB, H * W, Cout)
+    assert torch.allclose(ps[..., 0], yd.sum(1), rtol=0, atol=2e-3 * H * W ** 0.5)
+    assert torch.allclose(ps[..., 1], (yd * yd).sum(1), rtol=2e-4, atol=1e-2)
