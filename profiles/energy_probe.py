@@ -78,7 +78,53 @@ def measure(name, fn, per_step, seconds=1.5, batch=50):
     return us, pw, mhz
 
 
+def attention_modes():
+    """python profiles/energy_probe.py attn: energy per launch of the level-1 / level-2 attention geometry for each softmax
+    arithmetic mode (tuning key 6), layout (key 9) and start-up offset (key 5), then the whole step with the attention mode baked
+    into its graph.  In an energy-bound step the mode with the fewest joules wins, whatever its time alone."""
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for (B, heads, T, Tc, cnt) in [(8, 12, 2304, 32, 7), (8, 18, 576, 32, 7)]:
+        qkv = torch.randn(B, T, heads * 192, device="cuda", generator=g).half()
+        enc = torch.randn(B, Tc, heads * 128, device="cuda", generator=g).half()
+        out = torch.empty(B, T, heads * 64, device="cuda", dtype=torch.float16)
+        for (half, mode, stag) in [(1, 0, 1200), (1, 0, 0), (1, 30, 1200), (1, 1, 1200), (1, 31, 1200), (0, 0, 1200), (0, 30, 1200)]:
+            ops.set_tuning(9, half)
+            ops.set_tuning(6, mode)
+            ops.set_tuning(5, stag)
+            measure(f"attention T={T} layout {half} mode {mode:2d} stagger {stag:4d}", lambda: ops.attention_d64(qkv, heads, enc, out=out), cnt,
+                    seconds=1.2)
+    import bench
+    from kandinsky2.model import unet as unet_mod
+    from kandinsky2.model.gaussian_diffusion import FusedStep, create_ddpm_v22
+    dev = torch.device("cuda", 0)
+    ops.set_tuning(4, 1)
+    model = unet_mod.Text2ImUNet(**bench.UNET_CFG, device=dev, param_dtype=torch.float16)
+    model.init_synthetic_(seed=0)
+    model.finalize(release_params=True)
+    Bn = 4
+    emb = torch.randn(2 * Bn, 1280, device=dev)
+    coef, ts = create_ddpm_v22(50)._tables(dev)
+    x = torch.randn(Bn, 4, 96, 96, device=dev)
+    for rep in range(2):
+        for (half, mode, stag) in [(1, 0, 1200), (1, 30, 1200), (1, 0, 0), (0, 30, 1200)]:
+            ops.set_tuning(9, half)
+            ops.set_tuning(6, mode)
+            ops.set_tuning(5, stag)
+            model._plans = {}
+            st = FusedStep(model, Bn, 96, 96, dict(image_emb=emb), guidance_scale=4.0, cond_first=False, clip_range=2.0, threshold_mode=0)
+            for n in range(3):
+                st.noise.normal_()
+                st.run(x, ts[40], coef[40])
+            measure(f"whole step, attention layout {half} mode {mode:2d} stagger {stag:4d}", lambda: st.run(x, ts[25], coef[25]), 1,
+                    seconds=2.0, batch=10)
+    ops.set_tuning(9, 1)
+    ops.set_tuning(6, 0)
+    ops.set_tuning(5, 1200)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "attn":
+        return attention_modes()
     g = torch.Generator(device="cuda").manual_seed(0)
     time.sleep(0.5)
     print(f"idle: {read_power():.0f} W, {pynvml.nvmlDeviceGetClockInfo(H, pynvml.NVML_CLOCK_SM)} MHz; "
